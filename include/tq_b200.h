@@ -1,0 +1,138 @@
+/*
+ * tq_b200.h -- C ABI of libtq_b200.so: the B200 (sm_100a) implementation of the
+ * term-quantization hot path of BradMcDanel/term-quantization.
+ *
+ * This is the drop-in boundary.  Every entry point takes plain device pointers,
+ * explicit sizes and the caller's CUDA stream; none takes a torch type.  The
+ * reference exposes this path through one pybind11 function,
+ *
+ *     at::Tensor tr(const at::Tensor input, const float sf, const int32_t bitwidth,
+ *                   const int32_t group_size, const int32_t num_keep_terms)
+ *                                                    (kernels/tr_cuda.cpp:20-28)
+ *
+ * whose launcher (kernels/tr_cuda_kernel.cu:128-160) reads B = size(0),
+ * C = size(1), W*H = size(2)*size(3) and launches tr_cuda_kernel on the legacy
+ * default stream.  tq_tr_encode() below is what that binding calls instead; the
+ * remaining entry points replace the Python/torch loops that surround it in
+ * tr_layer.py (cited per function).  INTEGRATION.md shows the binding a
+ * maintainer of the reference would add.
+ *
+ * All functions are asynchronous on `stream` (a cudaStream_t passed as void*,
+ * NULL = legacy default stream), run on the current CUDA device, never
+ * synchronise, and return TQ_OK or an error code; tq_last_error() returns a
+ * thread-local message for the last failure.  There is no CPU fallback.
+ */
+#ifndef TQ_B200_H
+#define TQ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TQ_VERSION 100
+
+/* status codes */
+#define TQ_OK               0
+#define TQ_ERR_INVALID      1   /* bad argument (range, NULL pointer, sf <= 0 ...)   */
+#define TQ_ERR_UNSUPPORTED  2   /* valid in principle but not implemented            */
+#define TQ_ERR_CUDA         3   /* launch or runtime failure, see tq_last_error()    */
+
+/* element types of the floating tensors (reference dispatches float/double only,
+ * kernels/tr_cuda_kernel.cu:146; bf16/f16 are upcast to fp32 and then identical) */
+#define TQ_F32   0
+#define TQ_F64   1
+#define TQ_BF16  2
+#define TQ_F16   3
+
+/* element types of integer code tensors */
+#define TQ_I8    0   /* saturating is an error: caller must know |code| <= 127 */
+#define TQ_I16   1
+#define TQ_I32   2
+#define TQ_U8    3   /* for ReLU-ed activations, |code| <= 255                 */
+
+/* term encodings.  The reference kernel implements HESE only
+ * (kernels/tr_cuda_kernel.cu:29-55); BINARY (bit_utils.py:63-73) and radix-2
+ * BOOTH (verilog/booth_encoder.v:57-78) are additions with the same selection rule. */
+#define TQ_ENC_HESE    0
+#define TQ_ENC_BINARY  1
+#define TQ_ENC_BOOTH   2
+
+/* flags */
+#define TQ_FLAG_RELU       1u  /* clamp negative inputs to +0 before quantising (fused ReLU,
+                                  verilog/relu_quantizer.v:119-137 pipeline order)        */
+#define TQ_FLAG_RECIP_DIV  2u  /* tq_hese_term_count: w * (1/sf) instead of w / sf -- what
+                                  torch's CUDA `tensor / python_float` computes            */
+
+/* limits (reference: MAX_GROUP_SIZE 32, kernels/tr_cuda_kernel.cu:9) */
+#define TQ_MAX_GROUP   32
+#define TQ_MAX_BITS    16
+
+int         tq_version(void);
+const char *tq_last_error(void);
+/* number of kernels this library has launched in this process (bench.py gpu_launches) */
+uint64_t    tq_launch_count(void);
+
+/*
+ * Term-reveal a (B, C, WH) tensor: uniform-quantise every element to
+ * q = min(round_half_up(|x|/sf), 2^bits-1), expand q into signed power-of-two
+ * terms, keep the `alpha` largest terms of every group of `g` consecutive
+ * channels (fixed b and wh, element stride WH; ties -> lowest channel), sum the
+ * survivors and write sign(x) * sum * sf in the input dtype.
+ * Replaces tr_cuda() (kernels/tr_cuda_kernel.cu:58-160) bit for bit wherever the
+ * reference is defined.  Where it is not (C % g != 0: race + out-of-bounds,
+ * SURVEY 8a-3) the tail group holds the C % g real channels and the full budget,
+ * i.e. the reference's result on a zero-padded tensor.
+ *   1 <= g <= 32, 1 <= bits <= 16, alpha >= 0, sf > 0 and finite.
+ * in and out may alias exactly (in-place) but not partially.
+ */
+int tq_tr_encode(const void *in, void *out, int dtype,
+                 int64_t B, int64_t C, int64_t WH,
+                 float sf, int bits, int g, int alpha,
+                 int encoding, unsigned flags, void *stream);
+
+/*
+ * Same selection, but writes the signed integer code (sign(x) * sum of surviving
+ * terms, |code| <= 2^bits) instead of the dequantised value: the operand format of
+ * the integer conv/linear (tr_layer.py:126,154 computed on integers).  A code that
+ * does not fit code_dtype sets *overflow (device int, may be NULL) to 1 and is
+ * written saturated.
+ */
+int tq_tr_encode_codes(const void *in, void *codes, int dtype, int code_dtype,
+                       int64_t B, int64_t C, int64_t WH,
+                       float sf, int bits, int g, int alpha,
+                       int encoding, unsigned flags, int *overflow, void *stream);
+
+/*
+ * hist[b] += number of x in bin b, with torch.histc's CUDA binning
+ * (tr_layer.py:92: torch.histc(x, 8192, -50, 50)); hist is float32[nbins] on the
+ * device.  Elements are counted exactly in counts_scratch (uint32, left zeroed again on
+ * return) and added to hist with one fp32 rounding per bin per call.
+ */
+int tq_hist_accumulate(const void *x, int dtype, int64_t n,
+                       float *hist, uint32_t *counts_scratch /* nbins, zeroed once by the caller */,
+                       int nbins, float lo, float hi, void *stream);
+
+/*
+ * Fused calibration sweep (tr_layer.py:43-54): for every scale factor sfs[s],
+ * errs[s] = sum_b hist[b] * (x[b] - tr(x[b]; sfs[s], bits, g=1, terms))^2, each
+ * elementwise op rounded to fp32 as torch does, the sum in fp64; *argmin = index
+ * of the first minimum of (float)errs.  All pointers are device pointers;
+ * (errs: nsf doubles).  Two launches instead of 2048 launches + 2048 host syncs.
+ */
+int tq_mse_profile(const float *hist, const float *x, int nbins,
+                   const float *sfs, int nsf, int bits, int terms,
+                   double *errs, int *argmin, void *stream);
+
+/*
+ * *count += sum_i len(hese(int(w[i] / sf)))  (tr_layer.py:57-63, the per-element
+ * Python loop of compute_compressed_hese); count is a device uint64.
+ */
+int tq_hese_term_count(const void *w, int dtype, int64_t n, float sf, unsigned flags,
+                       unsigned long long *count, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TQ_B200_H */

@@ -1,0 +1,502 @@
+// tq_encode.cu -- term-reveal encode-and-truncate kernels for B200 (sm_100a).
+//
+// Replaces tr_cuda_kernel (kernels/tr_cuda_kernel.cu:58-125): that kernel launches one
+// thread per ELEMENT of which 1/g do work, keeps 8.3 KB of term lists per thread in local
+// memory and uses scalar strided accesses.  Here the term list never exists: a value's
+// terms are two bit masks (term_masks), and "the alpha largest terms of the group" is a
+// cut level p* found by counting set bits -- every term above p* survives, at p* the first
+// r values (lowest channel first) keep theirs, everything below is dropped.
+//
+// Three kernels:
+//   tr_elem_kernel    g == 1 (every activation, tr_layer.py:97-98).  A pure stream:
+//                     128-bit loads/stores, 4 vectors in flight per thread, persistent grid
+//                     sized to the SM count.  For bits <= 12 the whole quantised-value ->
+//                     output map is a 2^(bits+1)-entry table in shared memory built once per
+//                     CTA, so the per-element work is divide, round, one LDS.
+//   tr_group_kernel   g in {2,4,8,16,32}, fp32 (weights, tr_layer.py:120,148,178,185):
+//                     one thread owns one group in registers, popc-based binary search for
+//                     the cut level; vector loads when groups are contiguous (WH == 1).
+//   tr_generic_kernel anything else (odd g, tail groups, fp64/bf16/f16 groups, misaligned
+//                     pointers): same selection rule, plain loops.
+//
+// HBM traffic is the algorithmic minimum: each element is read once and written once.
+#include <type_traits>
+
+#include "tq_common.cuh"
+
+namespace tq {
+
+struct EncParams {
+    float sf;
+    float maxv;      // 2^bits - 1
+    int bits;
+    int alpha;       // budget per group (g == 1: terms per value)
+    int enc;
+    int relu;
+};
+
+// =========================================================================================
+// g == 1 : elementwise stream
+// =========================================================================================
+constexpr int ELEM_THREADS = 256;
+constexpr int ELEM_UNROLL = 4;
+
+template <typename Tin, typename Tout, bool DEQ>
+__device__ __forceinline__ Tout elem_out_compute(Tin xin, const EncParams &p, bool &ovf)
+{
+    uint32_t neg;
+    const uint32_t q = quantize_any<Tin>(xin, p.sf, p.maxv, p.relu != 0, neg);
+    int code = elem_code(q, p.enc, p.alpha);
+    code = neg ? -code : code;
+    if constexpr (DEQ) {
+        return dequant<Tout>(code, p.sf);
+    } else {
+        return pack_code<Tout>(code, ovf);
+    }
+}
+
+// table entry: the final output bit pattern (<= 32 bit) for index q | neg << bits.  Integer
+// codes narrower than 32 bit carry "did not fit" in bit 31.
+template <typename Tout, bool DEQ>
+__device__ __forceinline__ uint32_t lut_entry(uint32_t idx, const EncParams &p)
+{
+    if constexpr (sizeof(Tout) > 4) {
+        return 0u;                                   // fp64 never takes the table path
+    } else {
+        const uint32_t q = idx & ((1u << p.bits) - 1u);
+        const uint32_t neg = idx >> p.bits;
+        int code = elem_code(q, p.enc, p.alpha);
+        code = neg ? -code : code;
+        uint32_t b = 0u;
+        if constexpr (DEQ) {
+            const Tout o = dequant<Tout>(code, p.sf);
+            memcpy(&b, &o, sizeof(Tout));
+        } else {
+            bool ov = false;
+            const Tout o = pack_code<Tout>(code, ov);
+            memcpy(&b, &o, sizeof(Tout));
+            if (sizeof(Tout) < 4 && ov) b |= 0x80000000u;
+        }
+        return b;
+    }
+}
+
+template <typename Tout>
+__device__ __forceinline__ Tout lut_decode(uint32_t e)
+{
+    Tout o;
+    if constexpr (sizeof(Tout) > 4) o = Tout(0);
+    else memcpy(&o, &e, sizeof(Tout));
+    return o;
+}
+
+template <typename Tin, typename Tout, bool DEQ>
+__global__ void __launch_bounds__(ELEM_THREADS)
+tr_elem_kernel(const Tin *__restrict__ in, Tout *__restrict__ out, int64_t n, EncParams p,
+               int use_lut, int *__restrict__ overflow)
+{
+    constexpr int VEC = 16 / sizeof(Tin);
+    using VIn = Vec<Tin, VEC>;
+    using VOut = Vec<Tout, VEC>;
+    extern __shared__ uint32_t lut[];
+    bool ovf = false;
+
+    if (use_lut) {
+        const uint32_t entries = 2u << p.bits;
+        for (uint32_t i = threadIdx.x; i < entries; i += ELEM_THREADS) lut[i] = lut_entry<Tout, DEQ>(i, p);
+        __syncthreads();
+    }
+
+    const int64_t nvec = n / VEC;
+    const int64_t chunk = (int64_t)ELEM_THREADS * ELEM_UNROLL;
+    const int64_t nchunks = (nvec + chunk - 1) / chunk;
+    const VIn *vin = reinterpret_cast<const VIn *>(in);
+    VOut *vout = reinterpret_cast<VOut *>(out);
+
+    for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const int64_t v0 = c * chunk + threadIdx.x;
+        VIn x[ELEM_UNROLL];
+#pragma unroll
+        for (int u = 0; u < ELEM_UNROLL; ++u) {
+            const int64_t vi = v0 + (int64_t)u * ELEM_THREADS;
+            if (vi < nvec) {
+                const int4 raw = __ldcs(reinterpret_cast<const int4 *>(vin + vi));
+                memcpy(&x[u], &raw, 16);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < ELEM_UNROLL; ++u) {
+            const int64_t vi = v0 + (int64_t)u * ELEM_THREADS;
+            if (vi < nvec) {
+                VOut y;
+                if (use_lut) {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) {
+                        uint32_t neg;
+                        const uint32_t q = quantize_any<Tin>(x[u].v[e], p.sf, p.maxv, p.relu != 0, neg);
+                        const uint32_t ent = lut[q | (neg << p.bits)];
+                        if (!DEQ && sizeof(Tout) < 4) ovf |= (ent >> 31) != 0u;
+                        y.v[e] = lut_decode<Tout>(ent);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) y.v[e] = elem_out_compute<Tin, Tout, DEQ>(x[u].v[e], p, ovf);
+                }
+                vout[vi] = y;
+            }
+        }
+    }
+
+    // ragged tail (n % VEC elements), one thread
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int64_t i = nvec * VEC; i < n; ++i) out[i] = elem_out_compute<Tin, Tout, DEQ>(in[i], p, ovf);
+    }
+    if (!DEQ && ovf && overflow) atomicExch(overflow, 1);
+}
+
+// =========================================================================================
+// g in {2,4,8,16,32}, fp32 : one thread per group, registers only
+// =========================================================================================
+constexpr int GROUP_THREADS = 128;
+
+// number of terms at level >= p over the group; W packs two 16-bit term masks per word
+template <int NW>
+__device__ __forceinline__ int count_at_or_above(const uint32_t (&W)[NW], int p)
+{
+    const uint32_t m = ((0xFFFFu << p) & 0xFFFFu) * 0x00010001u;
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) c += __popc(W[i] & m);
+    return c;
+}
+
+template <int G, bool CONTIG, typename Tout, bool DEQ>
+__global__ void __launch_bounds__(GROUP_THREADS)
+tr_group_kernel(const float *__restrict__ in, Tout *__restrict__ out,
+                int64_t B, int64_t C, int64_t WH, EncParams p, int *__restrict__ overflow)
+{
+    static_assert(G >= 2 && G <= 32 && (G & (G - 1)) == 0, "G must be a power of two");
+    constexpr int NW = G / 2;
+    const int64_t CG = C / G;                       // caller guarantees C % G == 0
+    const int64_t total = B * CG * WH;
+    bool ovf = false;
+
+    for (int64_t t = (int64_t)blockIdx.x * GROUP_THREADS + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * GROUP_THREADS) {
+        int64_t base, stride;
+        if (CONTIG) {
+            base = t * G;
+            stride = 1;
+        } else {
+            const int64_t wh = t % WH;
+            const int64_t bc = t / WH;              // = b * CG + cg
+            base = bc * G * WH + wh;
+            stride = WH;
+        }
+
+        float x[G];
+        if (CONTIG) {
+            constexpr int NV = (G * 4) / 16 ? (G * 4) / 16 : 1;
+            if constexpr (G >= 4) {
+                const int4 *src = reinterpret_cast<const int4 *>(in + base);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const int4 raw = __ldcs(src + v);
+                    memcpy(&x[v * 4], &raw, 16);
+                }
+            } else {
+                const float2 raw = __ldcs(reinterpret_cast<const float2 *>(in + base));
+                x[0] = raw.x; x[1] = raw.y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < G; ++j) x[j] = __ldg(in + base + j * stride);
+        }
+
+        uint32_t qs[G];                              // q | sign << 31
+        uint32_t W[NW];
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            uint32_t neg;
+            const uint32_t q = quantize_any<float>(x[j], p.sf, p.maxv, p.relu != 0, neg);
+            qs[j] = q | (neg << 31);
+            uint32_t T, N;
+            term_masks(q, p.enc, T, N);
+            if (j & 1) W[j >> 1] |= T << 16; else W[j >> 1] = T;
+        }
+
+        // cut level: largest pc with (#terms at level >= pc) > alpha; none -> keep everything
+        uint32_t himask = 0xFFFFFFFFu, cutbit = 0u;
+        int r = 0;
+        if (count_at_or_above<NW>(W, 0) > p.alpha) {
+            int pc = 0;
+#pragma unroll
+            for (int step = 8; step >= 1; step >>= 1) {
+                const int cand = pc + step;
+                if (cand <= p.bits && count_at_or_above<NW>(W, cand) > p.alpha) pc = cand;
+            }
+            r = p.alpha - ((pc + 1 <= 15) ? count_at_or_above<NW>(W, pc + 1) : 0);
+            cutbit = 1u << pc;
+            himask = ~((cutbit << 1) - 1u);
+        }
+
+        int cnt = 0;
+        int codes[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const uint32_t T = (j & 1) ? (W[j >> 1] >> 16) : (W[j >> 1] & 0xFFFFu);
+            uint32_t Tq, N;
+            term_masks(qs[j] & 0x7FFFFFFFu, p.enc, Tq, N);
+            uint32_t K = T & himask;
+            const uint32_t at_cut = T & cutbit;
+            if (at_cut) { if (cnt < r) K |= cutbit; ++cnt; }
+            const int v = (int)K - 2 * (int)(K & N);
+            codes[j] = (qs[j] >> 31) ? -v : v;
+        }
+
+        Tout y[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            if constexpr (DEQ) y[j] = dequant<Tout>(codes[j], p.sf);
+            else y[j] = pack_code<Tout>(codes[j], ovf);
+        }
+        constexpr int OUT_BYTES = (int)sizeof(Tout) * G;
+        if (CONTIG && OUT_BYTES % 16 == 0) {
+            int4 *dst = reinterpret_cast<int4 *>(out + base);
+#pragma unroll
+            for (int v = 0; v < OUT_BYTES / 16; ++v) {
+                int4 raw;
+                memcpy(&raw, reinterpret_cast<const char *>(y) + 16 * v, 16);
+                dst[v] = raw;
+            }
+        } else if (CONTIG && OUT_BYTES == 8) {
+            int2 raw;
+            memcpy(&raw, y, 8);
+            *reinterpret_cast<int2 *>(out + base) = raw;
+        } else if (CONTIG && OUT_BYTES == 4) {
+            int raw;
+            memcpy(&raw, y, 4);
+            *reinterpret_cast<int *>(out + base) = raw;
+        } else {
+#pragma unroll
+            for (int j = 0; j < G; ++j) out[base + j * stride] = y[j];
+        }
+    }
+    if (!DEQ && ovf && overflow) atomicExch(overflow, 1);
+}
+
+// =========================================================================================
+// generic fallback: any g <= 32, any dtype, tail groups, any alignment
+// =========================================================================================
+template <typename Tin, typename Tout, bool DEQ>
+__global__ void __launch_bounds__(128)
+tr_generic_kernel(const Tin *__restrict__ in, Tout *__restrict__ out,
+                  int64_t B, int64_t C, int64_t WH, int g, EncParams p, int *__restrict__ overflow)
+{
+    const int64_t CG = (C + g - 1) / g;
+    const int64_t total = B * CG * WH;
+    bool ovf = false;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t wh = t % WH;
+        const int64_t bc = t / WH;
+        const int64_t cg = bc % CG;
+        const int64_t b = bc / CG;
+        const int n = (int)((cg * g + g <= C) ? g : (C - cg * g));   // tail group: C % g values
+        const int64_t base = (b * C + cg * g) * WH + wh;
+
+        uint32_t T[TQ_MAX_GROUP], N[TQ_MAX_GROUP];
+        uint32_t negmask = 0u;
+        for (int j = 0; j < n; ++j) {
+            uint32_t neg;
+            const uint32_t q = quantize_any<Tin>(in[base + (int64_t)j * WH], p.sf, p.maxv, p.relu != 0, neg);
+            negmask |= neg << j;
+            term_masks(q, p.enc, T[j], N[j]);
+        }
+        // walk levels from the top until the budget runs out
+        int rem = p.alpha, pc = -1, r = 0;
+        for (int lvl = p.bits; lvl >= 0; --lvl) {
+            int c = 0;
+            for (int j = 0; j < n; ++j) c += (T[j] >> lvl) & 1u;
+            if (c > rem) { pc = lvl; r = rem; break; }
+            rem -= c;
+        }
+        const uint32_t cutbit = pc >= 0 ? (1u << pc) : 0u;
+        const uint32_t himask = pc >= 0 ? ~((cutbit << 1) - 1u) : 0xFFFFFFFFu;
+        int cnt = 0;
+        for (int j = 0; j < n; ++j) {
+            uint32_t K = T[j] & himask;
+            if (T[j] & cutbit) { if (cnt < r) K |= cutbit; ++cnt; }
+            int v = (int)K - 2 * (int)(K & N[j]);
+            v = ((negmask >> j) & 1u) ? -v : v;
+            const int64_t idx = base + (int64_t)j * WH;
+            if constexpr (DEQ) out[idx] = dequant<Tout>(v, p.sf);
+            else out[idx] = pack_code<Tout>(v, ovf);
+        }
+    }
+    if (!DEQ && ovf && overflow) atomicExch(overflow, 1);
+}
+
+// =========================================================================================
+// host dispatch
+// =========================================================================================
+static int grid_for(int64_t work_items, int threads, int ctas_per_sm)
+{
+    const int64_t need = (work_items + threads - 1) / threads;
+    const int64_t cap = (int64_t)num_sms() * ctas_per_sm;
+    return (int)(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
+template <typename Tin, typename Tout, bool DEQ>
+static int launch_elem(const void *in, void *out, int64_t n, const EncParams &p, int *overflow,
+                       cudaStream_t s)
+{
+    constexpr int VEC = 16 / sizeof(Tin);
+    const int use_lut = (p.bits <= 12 && sizeof(Tout) <= 4 && n >= 4096) ? 1 : 0;
+    const size_t smem = use_lut ? (size_t)(2u << p.bits) * sizeof(uint32_t) : 0;
+    const int64_t chunks = (n / VEC + ELEM_THREADS * ELEM_UNROLL - 1) / (ELEM_THREADS * ELEM_UNROLL);
+    int grid = (int)(chunks < 1 ? 1 : chunks);
+    const int cap = num_sms() * 6;
+    if (grid > cap) grid = cap;
+    tr_elem_kernel<Tin, Tout, DEQ><<<grid, ELEM_THREADS, smem, s>>>(
+        (const Tin *)in, (Tout *)out, n, p, use_lut, overflow);
+    count_launch();
+    return check_launch("tr_elem_kernel");
+}
+
+template <typename Tout, bool DEQ>
+static int launch_group_f32(const void *in, void *out, int64_t B, int64_t C, int64_t WH, int g,
+                            const EncParams &p, int *overflow, cudaStream_t s)
+{
+    const int64_t total = B * (C / g) * WH;
+    const int grid = grid_for(total, GROUP_THREADS, 8);
+    const bool contig = (WH == 1);
+#define TQ_LAUNCH_G(GG)                                                                         \
+    case GG:                                                                                    \
+        if (contig)                                                                             \
+            tr_group_kernel<GG, true, Tout, DEQ><<<grid, GROUP_THREADS, 0, s>>>(                \
+                (const float *)in, (Tout *)out, B, C, WH, p, overflow);                         \
+        else                                                                                    \
+            tr_group_kernel<GG, false, Tout, DEQ><<<grid, GROUP_THREADS, 0, s>>>(               \
+                (const float *)in, (Tout *)out, B, C, WH, p, overflow);                         \
+        break;
+    switch (g) {
+        TQ_LAUNCH_G(2)
+        TQ_LAUNCH_G(4)
+        TQ_LAUNCH_G(8)
+        TQ_LAUNCH_G(16)
+        TQ_LAUNCH_G(32)
+        default: return fail(TQ_ERR_INVALID, "internal: group kernel called with g=%d", g);
+    }
+#undef TQ_LAUNCH_G
+    count_launch();
+    return check_launch("tr_group_kernel");
+}
+
+template <typename Tin, typename Tout, bool DEQ>
+static int launch_generic(const void *in, void *out, int64_t B, int64_t C, int64_t WH, int g,
+                          const EncParams &p, int *overflow, cudaStream_t s)
+{
+    const int64_t total = B * ((C + g - 1) / g) * WH;
+    const int grid = grid_for(total, 128, 8);
+    tr_generic_kernel<Tin, Tout, DEQ><<<grid, 128, 0, s>>>((const Tin *)in, (Tout *)out, B, C, WH, g, p, overflow);
+    count_launch();
+    return check_launch("tr_generic_kernel");
+}
+
+static bool aligned16(const void *a, const void *b)
+{
+    return (((uintptr_t)a | (uintptr_t)b) & 15u) == 0;
+}
+
+static int validate(const void *in, const void *out, int64_t B, int64_t C, int64_t WH, float sf,
+                    int bits, int g, int alpha, int enc, EncParams &p, unsigned flags)
+{
+    if (B < 0 || C < 0 || WH < 0) return fail(TQ_ERR_INVALID, "negative dimension");
+    if ((!in || !out) && B * C * WH > 0) return fail(TQ_ERR_INVALID, "NULL tensor pointer");
+    if (!(sf > 0.0f) || !(sf < INFINITY)) return fail(TQ_ERR_INVALID, "sf must be positive and finite (got %g)", (double)sf);
+    if (bits < 1 || bits > TQ_MAX_BITS) return fail(TQ_ERR_INVALID, "bitwidth must be in [1, %d] (got %d)", TQ_MAX_BITS, bits);
+    if (g < 1 || g > TQ_MAX_GROUP) return fail(TQ_ERR_INVALID, "group_size must be in [1, %d] (got %d)", TQ_MAX_GROUP, g);
+    if (alpha < 0) return fail(TQ_ERR_INVALID, "num_keep_terms must be >= 0 (got %d)", alpha);
+    if (enc < 0 || enc > 2) return fail(TQ_ERR_INVALID, "unknown encoding %d", enc);
+    p.sf = sf;
+    p.maxv = (float)((1u << bits) - 1u);
+    p.bits = bits;
+    p.alpha = alpha;
+    p.enc = enc;
+    p.relu = (flags & TQ_FLAG_RELU) ? 1 : 0;
+    return TQ_OK;
+}
+
+template <typename Tin, typename Tout, bool DEQ>
+static int dispatch(const void *in, void *out, int64_t B, int64_t C, int64_t WH, int g,
+                    const EncParams &p, int *overflow, cudaStream_t s)
+{
+    const int64_t n = B * C * WH;
+    if (n == 0) return TQ_OK;
+    if (g == 1) {
+        // groups of one: the (B, C, WH) structure is irrelevant, stream the flat tensor
+        if (aligned16(in, out)) return launch_elem<Tin, Tout, DEQ>(in, out, n, p, overflow, s);
+        return launch_generic<Tin, Tout, DEQ>(in, out, 1, n, 1, 1, p, overflow, s);
+    }
+    // register-resident fast path: fp32 in, fp32 / int8 / int16 out, power-of-two groups
+    if constexpr (std::is_same<Tin, float>::value &&
+                  (DEQ || std::is_same<Tout, int8_t>::value || std::is_same<Tout, int16_t>::value)) {
+        const bool pow2 = (g & (g - 1)) == 0;
+        if (pow2 && C % g == 0 && p.bits <= 15 && (WH != 1 || aligned16(in, out)))
+            return launch_group_f32<Tout, DEQ>(in, out, B, C, WH, g, p, overflow, s);
+    }
+    return launch_generic<Tin, Tout, DEQ>(in, out, B, C, WH, g, p, overflow, s);
+}
+
+}  // namespace tq
+
+using namespace tq;
+
+extern "C" int tq_tr_encode(const void *in, void *out, int dtype, int64_t B, int64_t C, int64_t WH,
+                            float sf, int bits, int g, int alpha, int encoding, unsigned flags,
+                            void *stream)
+{
+    EncParams p;
+    int rc = validate(in, out, B, C, WH, sf, bits, g, alpha, encoding, p, flags);
+    if (rc != TQ_OK) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (dtype) {
+        case TQ_F32:  return dispatch<float, float, true>(in, out, B, C, WH, g, p, nullptr, s);
+        case TQ_F64:  return dispatch<double, double, true>(in, out, B, C, WH, g, p, nullptr, s);
+        case TQ_BF16: return dispatch<__nv_bfloat16, __nv_bfloat16, true>(in, out, B, C, WH, g, p, nullptr, s);
+        case TQ_F16:  return dispatch<__half, __half, true>(in, out, B, C, WH, g, p, nullptr, s);
+        default: return fail(TQ_ERR_INVALID, "unknown dtype %d", dtype);
+    }
+}
+
+template <typename Tin>
+static int encode_codes_t(const void *in, void *codes, int code_dtype, int64_t B, int64_t C,
+                          int64_t WH, int g, const EncParams &p, int *overflow, cudaStream_t s)
+{
+    switch (code_dtype) {
+        case TQ_I8:  return dispatch<Tin, int8_t, false>(in, codes, B, C, WH, g, p, overflow, s);
+        case TQ_U8:  return dispatch<Tin, uint8_t, false>(in, codes, B, C, WH, g, p, overflow, s);
+        case TQ_I16: return dispatch<Tin, int16_t, false>(in, codes, B, C, WH, g, p, overflow, s);
+        case TQ_I32: return dispatch<Tin, int32_t, false>(in, codes, B, C, WH, g, p, overflow, s);
+        default: return fail(TQ_ERR_INVALID, "unknown code dtype %d", code_dtype);
+    }
+}
+
+extern "C" int tq_tr_encode_codes(const void *in, void *codes, int dtype, int code_dtype,
+                                  int64_t B, int64_t C, int64_t WH, float sf, int bits, int g,
+                                  int alpha, int encoding, unsigned flags, int *overflow,
+                                  void *stream)
+{
+    EncParams p;
+    int rc = validate(in, codes, B, C, WH, sf, bits, g, alpha, encoding, p, flags);
+    if (rc != TQ_OK) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (dtype) {
+        case TQ_F32:  return encode_codes_t<float>(in, codes, code_dtype, B, C, WH, g, p, overflow, s);
+        case TQ_BF16: return encode_codes_t<__nv_bfloat16>(in, codes, code_dtype, B, C, WH, g, p, overflow, s);
+        case TQ_F16:
+        case TQ_F64:  return fail(TQ_ERR_UNSUPPORTED, "integer codes are produced from f32 or bf16 inputs only");
+        default: return fail(TQ_ERR_INVALID, "unknown dtype %d", dtype);
+    }
+}
