@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- ResNet-18 TQ (g=8, alpha=12) inference throughput on B200, with the TR-encode
+kernel's HBM roofline and the reference's CPU path timed beside it.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (rank 0 only)
+
+A step = one forward of the term-quantised ResNet-18 over one synthetic batch of 256 images
+per GPU (BASELINE.json configs[1]; reference setting evaluate_group_size.py:71-74: 9-bit
+weights/activations, g=8, alpha=12, data_terms=3; first conv unwrapped).  Weak scaling: every
+rank runs its own 256 images and the logits are all-gathered (NCCL) inside the step.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+SETTING = dict(weight_bits=9, group_size=8, weight_terms=12, data_bits=9, data_terms=3)
+BATCH = 256
+METRIC = "resnet18_tq_g8_a12_images_per_sec"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        while self.nv is not None and not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.05)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------------------------
+def build_tq_resnet18(device):
+    from torchvision.models import resnet18
+    from term_quantization_b200 import cnn_models
+    torch.manual_seed(0)
+    model = resnet18(weights=None).eval().to(device)
+    params = cnn_models.static_conv_layer_settings(model, SETTING["weight_bits"], SETTING["group_size"],
+                                                   SETTING["weight_terms"])
+    qmodel = cnn_models.convert_model(model, params, SETTING["data_bits"], SETTING["data_terms"])
+    return qmodel.eval()
+
+
+class TRTimer:
+    """Wraps tr_cuda.tr so that every launch inside the timed region is bracketed by CUDA events
+    on the launching stream: per-launch durations for the roofline object."""
+
+    def __init__(self):
+        from term_quantization_b200 import tr_cuda
+        self.mod, self.orig, self.records, self.on = tr_cuda, tr_cuda.tr, [], False
+
+    def __enter__(self):
+        def timed(input, *a, **k):
+            if not self.on:
+                return self.orig(input, *a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = self.orig(input, *a, **k)
+            e1.record()
+            self.records.append((e0, e1, input.numel() * input.element_size() * 2))
+            return out
+        self.mod.tr = timed
+        return self
+
+    def __exit__(self, *exc):
+        self.mod.tr = self.orig
+
+    def summary(self):
+        ms = sum(a.elapsed_time(b) for a, b, _ in self.records)
+        by = sum(n for _, _, n in self.records)
+        return len(self.records), by, ms
+
+
+def run_b200(args):
+    from term_quantization_b200 import _lib, inference
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    # fp32 convs must be true fp32 for the 1e-5 logit tolerance (TF32 keeps 10 mantissa bits)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+
+    model = build_tq_resnet18(dev)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    nbuf = 2
+    images = [torch.randn(BATCH, 3, 224, 224, device=dev, generator=gen) for _ in range(nbuf)]
+    inference.calibrate(model, [images[0][:64]])          # untimed: histograms + fused sweep
+    runner = inference.ShardedInference(model, dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM ----------------------------------------------------
+    for i in range(args.warmup):
+        runner.forward(images[i % nbuf])
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    with TRTimer() as trt:
+        trt.on = True
+        launches0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            out = runner.forward(images[i % nbuf])
+        e1.record()
+        barrier()
+        launches = _lib.launch_count() - launches0
+        trt.on = False
+        ms_total = e0.elapsed_time(e1)
+        n_tr, tr_bytes, tr_ms = trt.summary()
+    clocks = sampler.finish()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    assert out.shape == (BATCH * world, 1000) and bool(torch.isfinite(out).all())
+
+    # ---- e2e: pinned host images -> H2D -> forward -> all-gather -> logits D2H -------------
+    host = [torch.randn(BATCH, 3, 224, 224).pin_memory() for _ in range(2)]
+    slot = runner.stage(host[0])
+    for i in range(max(args.warmup, 1)):
+        nxt = runner.stage(host[(i + 1) % 2])
+        runner.run(slot)
+        slot = nxt
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        nxt = runner.stage(host[i % 2])
+        host_logits = runner.run(slot)
+        slot = nxt
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    assert bool(torch.isfinite(host_logits).all())
+
+    line = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        ach = tr_bytes / (tr_ms * 1e-3) / 1e9 if tr_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": BATCH * world * args.steps / (ms_total * 1e-3),
+            "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 values / int32 term codes (TR encode); f32 conv",
+            "data": "synthetic (randn images, random-init torchvision resnet18, seed 0)",
+            "config": {"workload": "ResNet-18 TQ inference, batch 256 per GPU at 3x224x224 "
+                                   "(BASELINE.json configs[1])", **SETTING,
+                       "global_batch": BATCH * world, "parallelism": f"batch-sharded x{world}, "
+                       "logits all-gather (NCCL)" if world > 1 else "single GPU",
+                       "conv_backend": args.conv_backend,
+                       "l2": "activations per step (2.08 GB fp32 through TR) exceed the 126 MB L2; "
+                             "input batches rotate between 2 buffers"},
+            "e2e": {"value": BATCH * world * args.steps / (e2e_ms * 1e-3), "unit": "images/s",
+                    "h2d_bytes_per_step": BATCH * 3 * 224 * 224 * 4,
+                    "d2h_bytes_per_step": BATCH * world * 1000 * 4,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "tq::tr_elem_kernel<float,float> (g=1 TR encode of every wrapped "
+                                   "conv's input, 19 launches per forward)",
+                         "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "launches_timed": n_tr, "algorithmic_bytes": tr_bytes,
+                         "kernel_ms_total": tr_ms, "share_of_step": tr_ms / ms_total},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference_images_per_sec(sample_batch=args.cpu_batch, steps=1)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the reference's module stack on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_images_per_sec(sample_batch, steps, warmup=0):
+    """Times the reference stack (oracle/ref_stack.py: reference kernel body on the host for TR,
+    PyTorch CPU fp32 convs) on a bounded sample of the same workload."""
+    from torchvision.models import resnet18
+    from oracle import ref_stack, tq_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = resnet18(weights=None).eval()
+    t0 = time.time()
+    q = ref_stack.convert_cnn(model, SETTING["weight_bits"], SETTING["group_size"], SETTING["weight_terms"],
+                              SETTING["data_bits"], SETTING["data_terms"])
+    convert_s = time.time() - t0
+    x = torch.randn(sample_batch, 3, 224, 224, generator=torch.Generator().manual_seed(1234))
+    # timing-only scale factors (max/2^bits of a tracking pass); logit parity is tested in tests/
+    maxes = []
+
+    def grab(mod, inp):
+        maxes.append(float(inp[0].abs().max()))
+    hs = [m.register_forward_pre_hook(grab) for m in ref_stack.quantizers(q)]
+    with torch.no_grad():
+        q(x[:2])
+    for h in hs:
+        h.remove()
+    ref_stack.set_scale_factors(q, [max(m, 1e-6) / 2 ** SETTING["data_bits"] for m in maxes])
+    with torch.no_grad():
+        for _ in range(warmup):
+            q(x)
+        t0 = time.time()
+        for _ in range(steps):
+            q(x)
+        dt = time.time() - t0
+    return {"value": sample_batch * steps / dt, "unit": "images/s", "cores": cores,
+            "kind": "reference" if O.have_ref() else "port",
+            "sample": f"{steps} forward(s) of batch {sample_batch} (of the 256-image step), TR via "
+                      f"{'oracle/_ref (reference kernel body on host)' if O.have_ref() else 'oracle port'}"
+                      f" on {cores} threads + torch CPU fp32 conv; weight conversion {convert_s:.1f}s untimed",
+            "seconds": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    base = cpu_reference_images_per_sec(sample_batch=args.cpu_batch, steps=args.steps, warmup=min(args.warmup, 1))
+    v = base["value"]
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.cpu_batch / v,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (randn images, random-init torchvision resnet18, seed 0)",
+            "config": {"workload": "ResNet-18 TQ inference, batch 256 per GPU at 3x224x224 "
+                                   "(BASELINE.json configs[1])", **SETTING,
+                       "note": f"each step is a bounded sample: batch {args.cpu_batch} on the host cores"},
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--conv-backend", default="cudnn_fp32")
+    ap.add_argument("--cpu-batch", type=int, default=16, help="images per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

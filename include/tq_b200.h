@@ -65,6 +65,9 @@ extern "C" {
 #define TQ_FLAG_RECIP_DIV  2u  /* tq_hese_term_count: w * (1/sf) instead of w / sf -- what
                                   torch's CUDA `tensor / python_float` computes            */
 
+#define TQ_FLAG_EXACT_DIV  4u  /* tq_tr_encode*: force the per-element div.rn.f32 variant even
+                                  when the hoisted-reciprocal divide applies (testing)     */
+
 /* limits (reference: MAX_GROUP_SIZE 32, kernels/tr_cuda_kernel.cu:9) */
 #define TQ_MAX_GROUP   32
 #define TQ_MAX_BITS    16
@@ -131,6 +134,13 @@ int tq_mse_profile(const float *hist, const float *x, int nbins,
  */
 int tq_hese_term_count(const void *w, int dtype, int64_t n, float sf, unsigned flags,
                        unsigned long long *count, void *stream);
+
+/*
+ * Device self-test: quantises n pseudo-random (a, sf) pairs (sf in [2^-30, 2^30], a over all
+ * non-negative floats and the quantiser's rounding boundaries) with the hoisted-reciprocal
+ * divide and with div.rn.f32 and adds the number of disagreements to *mismatch (device).
+ */
+int tq_selftest_division(uint64_t n, uint32_t seed, unsigned long long *mismatch, void *stream);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ TQ_OK, TQ_ERR_INVALID, TQ_ERR_UNSUPPORTED, TQ_ERR_CUDA = 0, 1, 2, 3
 TQ_F32, TQ_F64, TQ_BF16, TQ_F16 = 0, 1, 2, 3
 TQ_I8, TQ_I16, TQ_I32, TQ_U8 = 0, 1, 2, 3
 ENC_HESE, ENC_BINARY, ENC_BOOTH = 0, 1, 2
-FLAG_RELU, FLAG_RECIP_DIV = 1, 2
+FLAG_RELU, FLAG_RECIP_DIV, FLAG_EXACT_DIV = 1, 2, 4
 
 # every symbol include/tq_b200.h declares: (restype, argtypes)
 _i64, _i, _f, _p, _u = C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_uint
@@ -26,6 +26,7 @@ SYMBOLS = {
     "tq_hist_accumulate": (_i, [_p, _i, _i64, _p, _p, _i, _f, _f, _p]),
     "tq_mse_profile": (_i, [_p, _p, _i, _p, _i, _i, _i, _p, _p, _p]),
     "tq_hese_term_count": (_i, [_p, _i, _i64, _f, _u, _p, _p]),
+    "tq_selftest_division": (_i, [C.c_uint64, C.c_uint32, _p, _p]),
 }
 
 _lib = None

@@ -75,12 +75,12 @@ mse_profile_kernel(const float *__restrict__ hist, const float *__restrict__ x, 
 {
     const int s = blockIdx.x;
     const float sf = sfs[s];
-    const float maxv = (float)((1u << bits) - 1u);
+    const Quant k = make_quant(sf, (float)((1u << bits) - 1u));
     double acc = 0.0;
     for (int b = threadIdx.x; b < nbins; b += MSE_THREADS) {
         const float xv = x[b];
         uint32_t neg;
-        const uint32_t q = quantize_any<float>(xv, sf, maxv, false, neg);
+        const uint32_t q = quantize_any<float, false>(xv, k, false, neg);
         int code = elem_code(q, TQ_ENC_HESE, terms);
         code = neg ? -code : code;
         const float xh = __fmul_rn((float)code, sf);
@@ -108,9 +108,7 @@ argmin_kernel(const double *__restrict__ errs, int nsf, int *__restrict__ argmin
     int idx = 0x7FFFFFFF;
     for (int i = threadIdx.x; i < nsf; i += 1024) {
         const float e = (float)errs[i];
-        if (e < best || (e == best && i < idx) || idx == 0x7FFFFFFF) {
-            if (idx == 0x7FFFFFFF || e < best || (e == best && i < idx)) { best = e; idx = i; }
-        }
+        if (idx == 0x7FFFFFFF || e < best) { best = e; idx = i; }   // i ascends: first minimum wins
     }
     bv[threadIdx.x] = best;
     bi[threadIdx.x] = idx;
@@ -149,6 +147,46 @@ hese_count_kernel(const Tin *__restrict__ w, int64_t n, float sf, float inv_sf, 
     }
     for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, o);
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+}
+
+// ---- on-device check of the hoisted-reciprocal divide against div.rn.f32 ---------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+__global__ void selftest_division_kernel(uint64_t n, uint32_t seed, unsigned long long *mismatch)
+{
+    unsigned long long bad = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t h1 = mix32((uint32_t)i ^ seed), h2 = mix32((uint32_t)(i >> 32) + h1 + 0x9e3779b9u);
+        // sf: random mantissa, exponent uniformly in [2^-30, 2^30]
+        const int es = (int)(h1 % 61u) - 30;
+        float sf = __uint_as_float(((uint32_t)(es + 127) << 23) | (h2 & 0x7FFFFFu));
+        sf = fminf(sf, 1073741824.0f);
+        // a: any non-negative float bit pattern (zero, denormals, huge, inf included), or a
+        // near-half-integer multiple of sf (the quantiser's rounding boundaries)
+        const uint32_t h3 = mix32(h2 ^ 0x85ebca6bu);
+        float a;
+        if (h3 & 1u) {
+            a = fmaxf(__uint_as_float(mix32(h3) & 0x7FFFFFFFu), 0.0f);
+        } else {
+            const float kk = (float)((h3 >> 1) & 0x3FFu) * 0.5f;
+            a = __uint_as_float(__float_as_uint(kk * sf) + ((h3 >> 12) & 3u) - 1u);
+            a = fmaxf(fabsf(a), 0.0f);
+        }
+        const Quant k = make_quant(sf, 65535.0f);
+        const uint32_t qa = quantize_f32<true>(a, k);
+        const uint32_t qb = quantize_f32<false>(a, k);
+        bad += (qa != qb);
+        // in the range where the quotient matters the divide itself must agree bit for bit
+        if (a >= 1e-24f && a <= 1.4e14f) {
+            bad += (__float_as_uint(div_rn_nonneg<true>(a, k)) != __float_as_uint(div_rn_nonneg<false>(a, k)));
+        }
+    }
+    if (bad) atomicAdd(mismatch, bad);
 }
 
 static int grid_cap(int64_t items, int threads, int per_sm)
@@ -232,4 +270,13 @@ extern "C" int tq_hese_term_count(const void *w, int dtype, int64_t n, float sf,
     }
     count_launch();
     return check_launch("hese_count_kernel");
+}
+
+extern "C" int tq_selftest_division(uint64_t n, uint32_t seed, unsigned long long *mismatch,
+                                    void *stream)
+{
+    if (!mismatch) return fail(TQ_ERR_INVALID, "NULL pointer");
+    selftest_division_kernel<<<num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(n, seed, mismatch);
+    count_launch();
+    return check_launch("selftest_division_kernel");
 }

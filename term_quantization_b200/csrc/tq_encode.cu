@@ -33,6 +33,7 @@ struct EncParams {
     int alpha;       // budget per group (g == 1: terms per value)
     int enc;
     int relu;
+    int fastdiv;     // 2^-30 <= sf <= 2^30: hoisted-reciprocal divide is exact (tq_common.cuh)
 };
 
 // =========================================================================================
@@ -41,11 +42,11 @@ struct EncParams {
 constexpr int ELEM_THREADS = 256;
 constexpr int ELEM_UNROLL = 4;
 
-template <typename Tin, typename Tout, bool DEQ>
-__device__ __forceinline__ Tout elem_out_compute(Tin xin, const EncParams &p, bool &ovf)
+template <typename Tin, typename Tout, bool DEQ, bool FAST>
+__device__ __forceinline__ Tout elem_out_compute(Tin xin, const EncParams &p, const Quant &k, bool &ovf)
 {
     uint32_t neg;
-    const uint32_t q = quantize_any<Tin>(xin, p.sf, p.maxv, p.relu != 0, neg);
+    const uint32_t q = quantize_any<Tin, FAST>(xin, k, p.relu != 0, neg);
     int code = elem_code(q, p.enc, p.alpha);
     code = neg ? -code : code;
     if constexpr (DEQ) {
@@ -90,7 +91,7 @@ __device__ __forceinline__ Tout lut_decode(uint32_t e)
     return o;
 }
 
-template <typename Tin, typename Tout, bool DEQ>
+template <typename Tin, typename Tout, bool DEQ, bool FAST>
 __global__ void __launch_bounds__(ELEM_THREADS)
 tr_elem_kernel(const Tin *__restrict__ in, Tout *__restrict__ out, int64_t n, EncParams p,
                int use_lut, int *__restrict__ overflow)
@@ -100,6 +101,9 @@ tr_elem_kernel(const Tin *__restrict__ in, Tout *__restrict__ out, int64_t n, En
     using VOut = Vec<Tout, VEC>;
     extern __shared__ uint32_t lut[];
     bool ovf = false;
+    const Quant k = make_quant(p.sf, p.maxv);
+    const bool relu = p.relu != 0;
+    const int bits = p.bits;
 
     if (use_lut) {
         const uint32_t entries = 2u << p.bits;
@@ -133,14 +137,14 @@ tr_elem_kernel(const Tin *__restrict__ in, Tout *__restrict__ out, int64_t n, En
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) {
                         uint32_t neg;
-                        const uint32_t q = quantize_any<Tin>(x[u].v[e], p.sf, p.maxv, p.relu != 0, neg);
-                        const uint32_t ent = lut[q | (neg << p.bits)];
+                        const uint32_t q = quantize_any<Tin, FAST>(x[u].v[e], k, relu, neg);
+                        const uint32_t ent = lut[q | (neg << bits)];
                         if (!DEQ && sizeof(Tout) < 4) ovf |= (ent >> 31) != 0u;
                         y.v[e] = lut_decode<Tout>(ent);
                     }
                 } else {
 #pragma unroll
-                    for (int e = 0; e < VEC; ++e) y.v[e] = elem_out_compute<Tin, Tout, DEQ>(x[u].v[e], p, ovf);
+                    for (int e = 0; e < VEC; ++e) y.v[e] = elem_out_compute<Tin, Tout, DEQ, FAST>(x[u].v[e], p, k, ovf);
                 }
                 vout[vi] = y;
             }
@@ -149,7 +153,7 @@ tr_elem_kernel(const Tin *__restrict__ in, Tout *__restrict__ out, int64_t n, En
 
     // ragged tail (n % VEC elements), one thread
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (int64_t i = nvec * VEC; i < n; ++i) out[i] = elem_out_compute<Tin, Tout, DEQ>(in[i], p, ovf);
+        for (int64_t i = nvec * VEC; i < n; ++i) out[i] = elem_out_compute<Tin, Tout, DEQ, FAST>(in[i], p, k, ovf);
     }
     if (!DEQ && ovf && overflow) atomicExch(overflow, 1);
 }
@@ -170,13 +174,14 @@ __device__ __forceinline__ int count_at_or_above(const uint32_t (&W)[NW], int p)
     return c;
 }
 
-template <int G, bool CONTIG, typename Tout, bool DEQ>
+template <int G, bool CONTIG, typename Tout, bool DEQ, bool FAST>
 __global__ void __launch_bounds__(GROUP_THREADS)
 tr_group_kernel(const float *__restrict__ in, Tout *__restrict__ out,
                 int64_t B, int64_t C, int64_t WH, EncParams p, int *__restrict__ overflow)
 {
     static_assert(G >= 2 && G <= 32 && (G & (G - 1)) == 0, "G must be a power of two");
     constexpr int NW = G / 2;
+    const Quant k = make_quant(p.sf, p.maxv);
     const int64_t CG = C / G;                       // caller guarantees C % G == 0
     const int64_t total = B * CG * WH;
     bool ovf = false;
@@ -218,7 +223,7 @@ tr_group_kernel(const float *__restrict__ in, Tout *__restrict__ out,
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             uint32_t neg;
-            const uint32_t q = quantize_any<float>(x[j], p.sf, p.maxv, p.relu != 0, neg);
+            const uint32_t q = quantize_any<float, FAST>(x[j], k, p.relu != 0, neg);
             qs[j] = q | (neg << 31);
             uint32_t T, N;
             term_masks(q, p.enc, T, N);
@@ -296,6 +301,7 @@ tr_generic_kernel(const Tin *__restrict__ in, Tout *__restrict__ out,
     const int64_t CG = (C + g - 1) / g;
     const int64_t total = B * CG * WH;
     bool ovf = false;
+    const Quant k = make_quant(p.sf, p.maxv);
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t wh = t % WH;
@@ -309,7 +315,7 @@ tr_generic_kernel(const Tin *__restrict__ in, Tout *__restrict__ out,
         uint32_t negmask = 0u;
         for (int j = 0; j < n; ++j) {
             uint32_t neg;
-            const uint32_t q = quantize_any<Tin>(in[base + (int64_t)j * WH], p.sf, p.maxv, p.relu != 0, neg);
+            const uint32_t q = quantize_any<Tin, false>(in[base + (int64_t)j * WH], k, p.relu != 0, neg);
             negmask |= neg << j;
             term_masks(q, p.enc, T[j], N[j]);
         }
@@ -358,8 +364,12 @@ static int launch_elem(const void *in, void *out, int64_t n, const EncParams &p,
     int grid = (int)(chunks < 1 ? 1 : chunks);
     const int cap = num_sms() * 6;
     if (grid > cap) grid = cap;
-    tr_elem_kernel<Tin, Tout, DEQ><<<grid, ELEM_THREADS, smem, s>>>(
-        (const Tin *)in, (Tout *)out, n, p, use_lut, overflow);
+    if (p.fastdiv)
+        tr_elem_kernel<Tin, Tout, DEQ, true><<<grid, ELEM_THREADS, smem, s>>>(
+            (const Tin *)in, (Tout *)out, n, p, use_lut, overflow);
+    else
+        tr_elem_kernel<Tin, Tout, DEQ, false><<<grid, ELEM_THREADS, smem, s>>>(
+            (const Tin *)in, (Tout *)out, n, p, use_lut, overflow);
     count_launch();
     return check_launch("tr_elem_kernel");
 }
@@ -371,14 +381,13 @@ static int launch_group_f32(const void *in, void *out, int64_t B, int64_t C, int
     const int64_t total = B * (C / g) * WH;
     const int grid = grid_for(total, GROUP_THREADS, 8);
     const bool contig = (WH == 1);
+#define TQ_LAUNCH_GF(GG, CT, FD)                                                                \
+    tr_group_kernel<GG, CT, Tout, DEQ, FD><<<grid, GROUP_THREADS, 0, s>>>(                      \
+        (const float *)in, (Tout *)out, B, C, WH, p, overflow)
 #define TQ_LAUNCH_G(GG)                                                                         \
     case GG:                                                                                    \
-        if (contig)                                                                             \
-            tr_group_kernel<GG, true, Tout, DEQ><<<grid, GROUP_THREADS, 0, s>>>(                \
-                (const float *)in, (Tout *)out, B, C, WH, p, overflow);                         \
-        else                                                                                    \
-            tr_group_kernel<GG, false, Tout, DEQ><<<grid, GROUP_THREADS, 0, s>>>(               \
-                (const float *)in, (Tout *)out, B, C, WH, p, overflow);                         \
+        if (contig) { if (p.fastdiv) TQ_LAUNCH_GF(GG, true, true); else TQ_LAUNCH_GF(GG, true, false); }   \
+        else        { if (p.fastdiv) TQ_LAUNCH_GF(GG, false, true); else TQ_LAUNCH_GF(GG, false, false); } \
         break;
     switch (g) {
         TQ_LAUNCH_G(2)
@@ -389,6 +398,7 @@ static int launch_group_f32(const void *in, void *out, int64_t B, int64_t C, int
         default: return fail(TQ_ERR_INVALID, "internal: group kernel called with g=%d", g);
     }
 #undef TQ_LAUNCH_G
+#undef TQ_LAUNCH_GF
     count_launch();
     return check_launch("tr_group_kernel");
 }
@@ -425,6 +435,8 @@ static int validate(const void *in, const void *out, int64_t B, int64_t C, int64
     p.alpha = alpha;
     p.enc = enc;
     p.relu = (flags & TQ_FLAG_RELU) ? 1 : 0;
+    p.fastdiv = (sf >= 9.313225746154785e-10f && sf <= 1073741824.0f) ? 1 : 0;   // [2^-30, 2^30]
+    if (flags & TQ_FLAG_EXACT_DIV) p.fastdiv = 0;
     return TQ_OK;
 }
 

@@ -1,0 +1,100 @@
+"""Batch-sharded TQ inference: one process per GPU, weights replicated (term-revealed once per
+rank, deterministic), each rank runs its own slice of the batch and the logits are gathered
+with one NCCL all-gather over NVLink.  Replaces the reference's
+``nn.DataParallel(qmodel)`` (evaluate_cnn.py:33), which re-replicates the module on every
+forward and calibrates on GPU 0's shard only; here calibration histograms are summed over
+ranks before the scale-factor sweep.
+
+PyTorch is plumbing (device memory, streams, torch.distributed); the TR kernels come from
+libtq_b200.so.
+"""
+import torch
+import torch.distributed as dist
+
+from . import tr_layer
+
+
+def shard_bounds(n_items, world_size, rank):
+    """Contiguous [lo, hi) slice of rank `rank`; the first n % world ranks hold one extra."""
+    base, extra = divmod(n_items, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def allreduce_histograms(model, group=None):
+    """Sum every LinearQuantize histogram over ranks so that all ranks derive the same scale
+    factors from the whole calibration set (works with gloo on CPU tensors and nccl on CUDA)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return model
+    for m in model.modules():
+        if isinstance(m, tr_layer.LinearQuantize):
+            dist.all_reduce(m.hist_bins, op=dist.ReduceOp.SUM, group=group)
+    return model
+
+
+def calibrate(model, batches, group=None):
+    """Reference protocol (evaluate_cnn.py:36-37): forward the calibration batches in tracking
+    mode, then leave tracking, which runs the fused scale-factor sweep per layer."""
+    tr_layer.set_tr_tracking(model, True)
+    with torch.no_grad():
+        for b in batches:
+            model(b)
+    allreduce_histograms(model, group)
+    tr_layer.set_tr_tracking(model, False)
+    return model
+
+
+class ShardedInference:
+    """Runs `model` on this rank's shard.  `forward(images_dev)` returns the logits of the
+    whole job on every rank (all-gather) or just the local ones when world_size == 1.
+    `forward_host(pinned)` adds the host->device copy of the shard and the device->host read
+    of the gathered logits, double-buffered on a copy stream."""
+
+    def __init__(self, model, device, group=None):
+        self.model = model.eval()
+        self.device = torch.device(device)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._stage = [None, None]
+        self._stage_evt = [None, None]
+        self._slot = 0
+        self._host_out = None
+
+    @torch.no_grad()
+    def forward(self, images_dev):
+        logits = self.model(images_dev)
+        if self.world == 1:
+            return logits
+        out = torch.empty((self.world * logits.shape[0],) + tuple(logits.shape[1:]),
+                          dtype=logits.dtype, device=logits.device)
+        dist.all_gather_into_tensor(out, logits.contiguous(), group=self.group)
+        return out
+
+    def stage(self, pinned):
+        """Start the host->device copy of a pinned shard on the copy stream; returns the slot.
+        Two slots: stage shard i+1, then run(shard i), and the copy overlaps the compute."""
+        s = self._slot
+        self._slot ^= 1
+        if self._stage[s] is None or self._stage[s].shape != pinned.shape:
+            self._stage[s] = torch.empty(pinned.shape, dtype=pinned.dtype, device=self.device)
+        # the slot may still be read by the forward enqueued two steps ago
+        self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.copy_stream):
+            self._stage[s].copy_(pinned, non_blocking=True)
+            evt = torch.cuda.Event()
+            evt.record(self.copy_stream)
+        self._stage_evt[s] = evt
+        return s
+
+    @torch.no_grad()
+    def run(self, slot):
+        """Forward the staged shard and start the device->host read of the gathered logits;
+        returns the pinned host tensor (valid after the current stream is synchronised)."""
+        torch.cuda.current_stream(self.device).wait_event(self._stage_evt[slot])
+        logits = self.forward(self._stage[slot])
+        if self._host_out is None or self._host_out.shape != logits.shape:
+            self._host_out = torch.empty(logits.shape, dtype=logits.dtype, pin_memory=True)
+        self._host_out.copy_(logits, non_blocking=True)
+        return self._host_out

@@ -48,7 +48,8 @@ def _stream_ptr(device):
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def tr(input, sf, bitwidth, group_size, num_keep_terms, *, encoding="hese", relu=False, out=None):
+def tr(input, sf, bitwidth, group_size, num_keep_terms, *, encoding="hese", relu=False, out=None,
+       _exact_div=False):
     """Term Revealing (TR) (CUDA)"""
     _check_input(input)
     B, Cc, WH = _dims(input)
@@ -61,7 +62,9 @@ def tr(input, sf, bitwidth, group_size, num_keep_terms, *, encoding="hese", relu
         rc = _lib.lib().tq_tr_encode(input.data_ptr(), out.data_ptr(), _DTYPES[input.dtype],
                                      B, Cc, WH, float(sf), int(bitwidth), int(group_size),
                                      int(num_keep_terms), _ENCODINGS[encoding],
-                                     _lib.FLAG_RELU if relu else 0, _stream_ptr(input.device))
+                                     (_lib.FLAG_RELU if relu else 0) |
+                                     (_lib.FLAG_EXACT_DIV if _exact_div else 0),
+                                     _stream_ptr(input.device))
     _lib.check(rc)
     return out
 

@@ -216,3 +216,28 @@ def test_argument_errors():
             tr_cuda.tr(x, a["sf"], a["bits"], a["g"], a["alpha"])
     # empty tensors are fine
     assert tr_cuda.tr(torch.zeros(0, 8, device="cuda"), 1.0, 8, 8, 12).shape == (0, 8)
+
+
+def test_hoisted_reciprocal_divide_is_exact():
+    """The stream kernels divide with a per-thread refined reciprocal + Markstein correction
+    instead of a per-element div.rn.f32; on-device comparison over 2^31 pairs, plus an
+    end-to-end comparison of the two kernel variants, plus scale factors outside the fast
+    range (which must take the div.rn.f32 variant)."""
+    from term_quantization_b200 import _lib
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for seed in (1, 2):
+        _lib.check(_lib.lib().tq_selftest_division(1 << 30, seed, bad.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0
+    rng = np.random.default_rng(77)
+    x = (rng.standard_normal((1, (1 << 22) + 5, 1, 1)) * 10).astype(np.float32)
+    for sf in (0.0123, 1.0, 3.3e-7, 999.0):
+        a = _tr(x, sf, 9, 1, 3)
+        b = _tr(x, sf, 9, 1, 3, _exact_div=True)
+        assert bits_equal(a, b)
+    w = x[:, : 1 << 20].reshape(-1, 64, 4, 4)
+    assert bits_equal(_tr(w, 0.05, 8, 8, 12), _tr(w, 0.05, 8, 8, 12, _exact_div=True))
+    small = (rng.standard_normal((1, 5000, 1, 1)) * 1e-11).astype(np.float32)
+    for sf in (1e-12, 1e-38, 3e12):
+        xs = small if sf < 1 else x[:, :5000] * np.float32(1e12)
+        assert bits_equal(_tr(xs, sf, 8, 1, 3), O.tr(xs, sf, 8, 1, 3)), sf
