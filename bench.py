@@ -70,7 +70,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop_evt.wait(0.05)
+            self._stop_evt.wait(0.01)
 
     def finish(self):
         self._stop_evt.set()
@@ -163,11 +163,13 @@ def run_b200(args):
         launches0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        torch.cuda.profiler.start()          # no-op unless ncu runs with --profile-from-start off
         e0.record()
         for i in range(args.steps):
             out = runner.forward(images[i % nbuf])
         e1.record()
         barrier()
+        torch.cuda.profiler.stop()
         launches = _lib.launch_count() - launches0
         trt.on = False
         ms_total = e0.elapsed_time(e1)

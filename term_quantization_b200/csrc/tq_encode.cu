@@ -20,6 +20,7 @@
 //                     pointers): same selection rule, plain loops.
 //
 // HBM traffic is the algorithmic minimum: each element is read once and written once.
+#include <cstdlib>
 #include <type_traits>
 
 #include "tq_common.cuh"
@@ -40,7 +41,6 @@ struct EncParams {
 // g == 1 : elementwise stream
 // =========================================================================================
 constexpr int ELEM_THREADS = 256;
-constexpr int ELEM_UNROLL = 4;
 
 template <typename Tin, typename Tout, bool DEQ, bool FAST>
 __device__ __forceinline__ Tout elem_out_compute(Tin xin, const EncParams &p, const Quant &k, bool &ovf)
@@ -91,7 +91,7 @@ __device__ __forceinline__ Tout lut_decode(uint32_t e)
     return o;
 }
 
-template <typename Tin, typename Tout, bool DEQ, bool FAST>
+template <typename Tin, typename Tout, bool DEQ, bool FAST, int ELEM_UNROLL>
 __global__ void __launch_bounds__(ELEM_THREADS)
 tr_elem_kernel(const Tin *__restrict__ in, Tout *__restrict__ out, int64_t n, EncParams p,
                int use_lut, int *__restrict__ overflow)
@@ -358,18 +358,23 @@ static int launch_elem(const void *in, void *out, int64_t n, const EncParams &p,
                        cudaStream_t s)
 {
     constexpr int VEC = 16 / sizeof(Tin);
+    static const int tune_unroll = getenv("TQ_ELEM_UNROLL") ? atoi(getenv("TQ_ELEM_UNROLL")) : 4;
+    static const int tune_ctas = getenv("TQ_ELEM_CTAS") ? atoi(getenv("TQ_ELEM_CTAS")) : 16;   // > resident: waves balance the two dies
+    const int unroll = tune_unroll == 8 ? 8 : (tune_unroll == 2 ? 2 : 4);
     const int use_lut = (p.bits <= 12 && sizeof(Tout) <= 4 && n >= 4096) ? 1 : 0;
     const size_t smem = use_lut ? (size_t)(2u << p.bits) * sizeof(uint32_t) : 0;
-    const int64_t chunks = (n / VEC + ELEM_THREADS * ELEM_UNROLL - 1) / (ELEM_THREADS * ELEM_UNROLL);
+    const int64_t chunks = (n / VEC + ELEM_THREADS * unroll - 1) / (ELEM_THREADS * unroll);
     int grid = (int)(chunks < 1 ? 1 : chunks);
-    const int cap = num_sms() * 6;
+    const int cap = num_sms() * tune_ctas;
     if (grid > cap) grid = cap;
-    if (p.fastdiv)
-        tr_elem_kernel<Tin, Tout, DEQ, true><<<grid, ELEM_THREADS, smem, s>>>(
-            (const Tin *)in, (Tout *)out, n, p, use_lut, overflow);
-    else
-        tr_elem_kernel<Tin, Tout, DEQ, false><<<grid, ELEM_THREADS, smem, s>>>(
-            (const Tin *)in, (Tout *)out, n, p, use_lut, overflow);
+#define TQ_LAUNCH_E(FD, UN)                                                                     \
+    tr_elem_kernel<Tin, Tout, DEQ, FD, UN><<<grid, ELEM_THREADS, smem, s>>>(                    \
+        (const Tin *)in, (Tout *)out, n, p, use_lut, overflow)
+    if (!p.fastdiv) TQ_LAUNCH_E(false, 4);
+    else if (unroll == 8) TQ_LAUNCH_E(true, 8);
+    else if (unroll == 2) TQ_LAUNCH_E(true, 2);
+    else TQ_LAUNCH_E(true, 4);
+#undef TQ_LAUNCH_E
     count_launch();
     return check_launch("tr_elem_kernel");
 }

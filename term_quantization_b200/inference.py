@@ -32,6 +32,22 @@ def allreduce_histograms(model, group=None):
     return model
 
 
+def gather_logits(logits, group=None):
+    """Logits of the whole job on every rank, rank-major (the one collective of the path)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return logits
+    world = dist.get_world_size(group)
+    logits = logits.contiguous()
+    if logits.is_cuda:
+        out = torch.empty((world * logits.shape[0],) + tuple(logits.shape[1:]), dtype=logits.dtype,
+                          device=logits.device)
+        dist.all_gather_into_tensor(out, logits, group=group)
+        return out
+    parts = [torch.empty_like(logits) for _ in range(world)]
+    dist.all_gather(parts, logits, group=group)
+    return torch.cat(parts, dim=0)
+
+
 def calibrate(model, batches, group=None):
     """Reference protocol (evaluate_cnn.py:36-37): forward the calibration batches in tracking
     mode, then leave tracking, which runs the fused scale-factor sweep per layer."""
@@ -47,8 +63,9 @@ def calibrate(model, batches, group=None):
 class ShardedInference:
     """Runs `model` on this rank's shard.  `forward(images_dev)` returns the logits of the
     whole job on every rank (all-gather) or just the local ones when world_size == 1.
-    `forward_host(pinned)` adds the host->device copy of the shard and the device->host read
-    of the gathered logits, double-buffered on a copy stream."""
+    `stage(pinned)` + `run(slot)` add the host->device copy of the shard (double-buffered on a
+    copy stream, overlapping the previous step's compute) and the device->host read of the
+    gathered logits."""
 
     def __init__(self, model, device, group=None):
         self.model = model.eval()
@@ -64,13 +81,7 @@ class ShardedInference:
 
     @torch.no_grad()
     def forward(self, images_dev):
-        logits = self.model(images_dev)
-        if self.world == 1:
-            return logits
-        out = torch.empty((self.world * logits.shape[0],) + tuple(logits.shape[1:]),
-                          dtype=logits.dtype, device=logits.device)
-        dist.all_gather_into_tensor(out, logits.contiguous(), group=self.group)
-        return out
+        return gather_logits(self.model(images_dev), self.group)
 
     def stage(self, pinned):
         """Start the host->device copy of a pinned shard on the copy stream; returns the slot.

@@ -69,7 +69,21 @@ def main():
     add(wd, float(np.abs(wd).max()) / 128, 8, 8, 12)
     add(np.maximum(rng.standard_normal((1, 1001, 1, 1)), 0), 0.013, 8, 1, 3)
 
-    out = {"n": np.int64(len(cases))}
+    # tr_layer.hese (tr_layer.py:9-41): the module cannot be imported (it JIT-builds the CUDA
+    # extension at import time), so only the text of that one function is executed here.
+    import re
+    src = open("/root/reference/tr_layer.py").read()
+    fn_src = re.search(r"^def hese\(number\):.*?^    return keep_exponents\n", src, re.S | re.M).group(0)
+    ns = {}
+    exec(fn_src, ns)
+    hese_in = np.arange(-700, 701, dtype=np.int64)
+    hese_flat, hese_off = [], [0]
+    for v in hese_in:
+        hese_flat += ns["hese"](int(v))
+        hese_off.append(len(hese_flat))
+
+    out = {"n": np.int64(len(cases)), "hese_in": hese_in, "hese_flat": np.array(hese_flat, dtype=np.int64),
+           "hese_off": np.array(hese_off, dtype=np.int64)}
     for n, (x, sf, bits, g, alpha, y) in enumerate(cases):
         out[f"x{n}"] = x
         out[f"y{n}"] = y

@@ -1,0 +1,186 @@
+"""GPU tests of everything around the TR op: calibration kernels, TR layer wrappers against the
+reference stack on the CPU (oracle/ref_stack.py), op-counter known answers from results/*.json,
+and the evaluate_* drivers end to end on synthetic data."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import ref_stack
+from oracle import tq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _fp32_math():
+    # the float path is compared at 1e-5 relative: keep cuDNN/cuBLAS in true fp32 (no TF32)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_histogram_matches_torch_histc_and_oracle():
+    from term_quantization_b200 import tr_layer
+    g = torch.Generator(device="cuda").manual_seed(3)
+    q = tr_layer.LinearQuantize(8, 3).cuda()
+    total = torch.zeros(8192, device="cuda")
+    oracle_hist = np.zeros(8192, dtype=np.float32)
+    for n, scale in ((100003, 5.0), (7, 1.0), (1 << 20, 30.0), (4096, 0.01)):
+        x = torch.randn(n, device="cuda", generator=g) * scale
+        x[: min(n, 5)] = torch.tensor([-50.0, 50.0, 0.0, 60.0, float("nan")], device="cuda")[: min(n, 5)]
+        q(x.view(-1, 1))                                   # tracking mode: accumulate
+        total += torch.histc(x, 8192, -50, 50)
+        O.hist(x.cpu().numpy(), oracle_hist, -50, 50)
+    assert torch.equal(q.hist_bins, total)
+    assert np.array_equal(q.hist_bins.cpu().numpy(), oracle_hist)
+    xb = (torch.randn(50001, device="cuda", generator=g) * 3).bfloat16()
+    q2 = tr_layer.LinearQuantize(8, 3).cuda()
+    q2(xb)
+    assert torch.equal(q2.hist_bins, torch.histc(xb.float(), 8192, -50, 50))
+
+
+def test_mse_profile_matches_oracle_and_reference_loop():
+    from term_quantization_b200 import tr_cuda, tr_layer
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.relu(torch.randn(200000, device="cuda", generator=g)) * 2.5
+    hist = torch.histc(x, 8192, -50, 50)
+    for bits, terms in ((8, 3), (9, 2), (6, 6)):
+        sf = tr_layer.mse_profile(hist, -50, 50, bits, terms)
+        grid = torch.linspace(-50, 50, 8192)
+        sfs = torch.linspace(1e-8, 50, 2048)
+        idx, errs = O.mse_profile(hist.cpu().numpy(), grid.numpy(), sfs.numpy(), bits, terms)
+        assert sf == sfs.tolist()[idx]
+        # the reference's own loop (tr_layer.py:44-54) over a window around the minimum
+        xg = grid.cuda()
+        lo, hi = max(idx - 8, 0), min(idx + 9, 2048)
+        ref = []
+        for s in sfs.tolist()[lo:hi]:
+            xh = tr_cuda.tr(xg.view(-1, 1, 1, 1), s, bits, 1, terms).view(-1)
+            ref.append((hist * (xg - xh) ** 2).sum())
+        assert lo + int(torch.argmin(torch.Tensor(ref))) == idx
+        np.testing.assert_allclose(torch.Tensor(ref).numpy(), errs[lo:hi], rtol=2e-5)
+
+
+def test_compute_compressed_hese_matches_python_loop():
+    from term_quantization_b200 import tr_cuda, tr_layer
+    g = torch.Generator(device="cuda").manual_seed(7)
+    w = torch.randn(40, 96, device="cuda", generator=g) * 0.1
+    sf = w.abs().max().item() / 128
+    wq = tr_cuda.tr(w, sf, 8, 8, 12)
+    ints = (wq / sf).int().view(-1).tolist()              # exactly tr_layer.py:60 on the device
+    want = (int(np.ceil(np.log2(12))) + 2) * sum(len(tr_layer.hese(v)) for v in ints)
+    assert tr_layer.compute_compressed_hese(wq, sf, 12) == want
+
+
+def _small_cnn():
+    torch.manual_seed(0)
+    return nn.Sequential(
+        nn.Conv2d(3, 16, 3, padding=1), nn.ReLU(),
+        nn.Conv2d(16, 32, 3, padding=1, stride=2), nn.BatchNorm2d(32), nn.ReLU(),
+        nn.Conv2d(32, 32, 3, padding=1, groups=32), nn.ReLU(),         # depthwise -> (16, 1, 16)
+        nn.Conv2d(32, 64, 1), nn.ReLU(), nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(64, 10)).eval()
+
+
+def test_tr_conv_stack_matches_reference_stack_on_cpu():
+    from term_quantization_b200 import cnn_models, tr_layer
+    base = _small_cnn()
+    with torch.no_grad():
+        for m in base.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1)
+                m.running_var.uniform_(0.5, 1.5)
+    cpu = ref_stack.convert_cnn(base, 8, 8, 12, 8, 3)
+    gpu_base = _small_cnn()
+    gpu_base.load_state_dict(base.state_dict())
+    params = cnn_models.static_conv_layer_settings(gpu_base, 8, 8, 12)
+    assert params == [(16, 1, 16), (8, 8, 12), (16, 1, 16), (8, 8, 12)]
+    gpu = cnn_models.convert_model(gpu_base.cuda(), params, 8, 3)
+    # weights: bit-exact
+    cw = [m.conv.weight for m in cpu.modules() if isinstance(m, ref_stack.RefTRConv2d)]
+    gw = [m.conv.weight for m in gpu.modules() if isinstance(m, tr_layer.TRConv2dLayer)]
+    assert len(cw) == len(gw) == 3
+    for a, b in zip(cw, gw):
+        assert torch.equal(a, b.cpu())
+    x = torch.randn(4, 3, 20, 20, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        # calibration on both sides: identical histograms -> identical scale factors
+        cpu(x)
+        gpu(x.cuda())
+        tr_layer.set_tr_tracking(gpu, False)
+        for m in ref_stack.quantizers(cpu):
+            m.finish_tracking()
+        sg = [m.input_quant.sf for m in gpu.modules() if isinstance(m, tr_layer.TRConv2dLayer)]
+        sc = [m.sf for m in ref_stack.quantizers(cpu)]
+        assert sg == sc
+        want = cpu(x)
+        got = gpu(x.cuda()).cpu()
+    # floating-point logits: within 1e-5 relative (north star), fp32 conv on both sides
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-5 * float(want.abs().max()))
+
+
+def test_linear_and_lstm_layers_follow_reference_quirks():
+    from term_quantization_b200 import tr_cuda, tr_layer
+    torch.manual_seed(0)
+    lin = nn.Linear(650, 40).cuda()
+    w0 = lin.weight.detach().clone()
+    layer = tr_layer.TRLinearLayer(lin, 8, 8, 8, 8, 12)
+    sf = w0.abs().max().item() / 128
+    assert layer.w_sf == sf
+    assert torch.equal(layer.linear.weight, tr_cuda.tr(w0, sf, 8, 8, 12))   # 650 % 8 != 0 tail
+    assert np.array_equal(layer.linear.weight.detach().cpu().numpy(), O.tr(w0.cpu().numpy(), sf, 8, 8, 12))
+    x = torch.randn(5, 650, device="cuda")
+    with torch.no_grad():
+        y_track = layer(x)
+        assert float(layer.input_quant.hist_bins.sum()) == x.numel()
+        tr_layer.set_tr_tracking(layer, False)
+        y = layer(x)
+    assert torch.equal(y, y_track) and torch.equal(y, lin(x))     # xq is discarded (tr_layer.py:152-154)
+
+    lstm = nn.LSTM(32, 32, 2).cuda()
+    w_ih1 = lstm.weight_ih_l1.detach().clone()
+    tl = tr_layer.TRLSTMLayer(lstm, 8, 8, 8, 8, 12)
+    assert torch.equal(tl.lstm.weight_ih_l1, w_ih1)               # only layer 0 is term-revealed
+    emb = torch.randn(7, 3, 32, device="cuda")
+    hid = (torch.zeros(2, 3, 32, device="cuda"), torch.zeros(2, 3, 32, device="cuda"))
+    with torch.no_grad():
+        tl(emb, hid)
+        assert float(tl.input_quant.hist_bins.sum()) == emb.numel() + 2 * hid[0].numel()
+        tr_layer.set_tr_tracking(tl, False)
+        out, (h, c) = tl(emb, hid)
+    assert out.shape == (7, 3, 32) and torch.isfinite(out).all()
+
+
+def test_op_counter_known_answers_from_results_json():
+    from term_quantization_b200 import cnn_models, evaluate_mlp, profile_model
+    from term_quantization_b200.train_mlp import MNISTMLP
+    from torchvision.models import resnet18
+    x = (torch.zeros(1, 1, 28, 28, device="cuda"),)
+    # results/mnist-quant.json idx 0 (evaluate_mlp.sh:3): wb=2 wt=2 db=6 dt=6 gs=1
+    m = evaluate_mlp.replace_linear_layers(MNISTMLP().cuda(), [(2, 1, 2)] * 3, 6, 6)
+    assert profile_model.get_model_ops(m, x) == (8024064.0, 1337344.0)
+    # results/mnist-tr.json idx 0 (evaluate_mlp.sh:4): wb=4 wt=6 gs=16
+    m = evaluate_mlp.replace_linear_layers(MNISTMLP().cuda(), [(4, 16, 6)] * 3, 6, 6)
+    tmacs, _ = profile_model.get_model_ops(m, x)
+    assert tmacs == 1504512.0
+    # results/resnet18-group-size-results.json: g=8, avg 1.0 term, data_terms=3 -> 5,086,642,176
+    r = resnet18(weights=None).cuda().eval()
+    q = cnn_models.convert_model(r, cnn_models.static_conv_layer_settings(r, 9, 8, 8), 9, 3)
+    tmacs, params = profile_model.get_model_ops(q, (torch.zeros(1, 3, 224, 224, device="cuda"),))
+    assert tmacs == 5086642176.0 and params == 0.0
+
+
+def test_evaluate_drivers_run_on_synthetic_data(tmp_path):
+    from term_quantization_b200 import evaluate_lstm, evaluate_mlp
+    out = tmp_path / "mlp.json"
+    res = evaluate_mlp.main(["--wb", "4", "8", "--wt", "12", "12", "--db", "6", "8", "--dt", "6", "4",
+                             "--gs", "16", "8", "--out-file", str(out), "--samples", "512"])
+    assert len(res["accs"]) == 2 and out.exists()
+    assert res["tmacs"][0] == float(int(6 * (12 / 16) * 668672))
+    res = evaluate_lstm.main(["--wb", "8", "--wt", "12", "--db", "8", "--dt", "8", "--gs", "8",
+                              "--emsize", "64", "--nhid", "64", "--tokens", "1500"])
+    assert len(res["ppls"]) == 1 and np.isfinite(res["ppls"][0])
+    # decoder term pairs: 8 * (12/8) * (35*10*33278*64) accumulated in float32
+    assert res["tmacs"][0] == float(np.float32(int(8 * 1.5 * 35 * 10 * 33278 * 64)))
