@@ -51,6 +51,8 @@ extern "C" {
 #define TQ_I16   1
 #define TQ_I32   2
 #define TQ_U8    3   /* for ReLU-ed activations, |code| <= 255                 */
+#define TQ_F16C  4   /* integer codes stored as fp16 values (exact for |code| <= 2048):
+                        the operand format of tq_conv2d_codes_f16                 */
 
 /* term encodings.  The reference kernel implements HESE only
  * (kernels/tr_cuda_kernel.cu:29-55); BINARY (bit_utils.py:63-73) and radix-2
@@ -134,6 +136,21 @@ int tq_mse_profile(const float *hist, const float *x, int nbins,
  */
 int tq_hese_term_count(const void *w, int dtype, int64_t n, float sf, unsigned flags,
                        unsigned long long *count, void *stream);
+
+/*
+ * Convolution on term codes with tcgen05 tensor cores (replaces the cuDNN fp32 conv under
+ * TRConv2dLayer.forward, tr_layer.py:124-126, computed on the integer codes instead of the
+ * dequantised values):
+ *     out[n,ho,wo,co] = scale * sum_{r,s,ci} act[n, ho*stride+r-pad, wo*stride+s-pad, ci] * wgt[r*S+s, co, ci]  (+ bias[co])
+ * act  fp16 NHWC [N,H,W,C] holding integer codes (TQ_F16C), C % 8 == 0
+ * wgt  fp16 [R*S][Cout][C] holding integer codes, Cout % 4 == 0
+ * out  fp32 NHWC [N,Ho,Wo,Cout]; bias fp32 [Cout] or NULL; scale = sf_x * sf_w.
+ * The fp32 accumulator equals the exact integer accumulator whenever sum |act*wgt| < 2^24 per
+ * output.  groups = 1, dilation = 1.
+ */
+int tq_conv2d_codes_f16(const void *act, const void *wgt, const float *bias, float *out,
+                        int N, int H, int W, int C, int Cout, int R, int S, int stride, int pad,
+                        float scale, void *stream);
 
 /*
  * Device self-test: quantises n pseudo-random (a, sf) pairs (sf in [2^-30, 2^30], a over all

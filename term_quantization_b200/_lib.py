@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libtq_b200.so")
 
 TQ_OK, TQ_ERR_INVALID, TQ_ERR_UNSUPPORTED, TQ_ERR_CUDA = 0, 1, 2, 3
 TQ_F32, TQ_F64, TQ_BF16, TQ_F16 = 0, 1, 2, 3
-TQ_I8, TQ_I16, TQ_I32, TQ_U8 = 0, 1, 2, 3
+TQ_I8, TQ_I16, TQ_I32, TQ_U8, TQ_F16C = 0, 1, 2, 3, 4
 ENC_HESE, ENC_BINARY, ENC_BOOTH = 0, 1, 2
 FLAG_RELU, FLAG_RECIP_DIV, FLAG_EXACT_DIV = 1, 2, 4
 
@@ -26,6 +26,7 @@ SYMBOLS = {
     "tq_hist_accumulate": (_i, [_p, _i, _i64, _p, _p, _i, _f, _f, _p]),
     "tq_mse_profile": (_i, [_p, _p, _i, _p, _i, _i, _i, _p, _p, _p]),
     "tq_hese_term_count": (_i, [_p, _i, _i64, _f, _u, _p, _p]),
+    "tq_conv2d_codes_f16": (_i, [_p, _p, _p, _p] + [_i] * 9 + [_f, _p]),
     "tq_selftest_division": (_i, [C.c_uint64, C.c_uint32, _p, _p]),
 }
 

@@ -496,6 +496,7 @@ static int encode_codes_t(const void *in, void *codes, int code_dtype, int64_t B
         case TQ_U8:  return dispatch<Tin, uint8_t, false>(in, codes, B, C, WH, g, p, overflow, s);
         case TQ_I16: return dispatch<Tin, int16_t, false>(in, codes, B, C, WH, g, p, overflow, s);
         case TQ_I32: return dispatch<Tin, int32_t, false>(in, codes, B, C, WH, g, p, overflow, s);
+        case TQ_F16C: return dispatch<Tin, __half, false>(in, codes, B, C, WH, g, p, overflow, s);
         default: return fail(TQ_ERR_INVALID, "unknown code dtype %d", code_dtype);
     }
 }

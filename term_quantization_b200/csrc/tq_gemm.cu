@@ -1,0 +1,384 @@
+// tq_gemm.cu -- the contraction that consumes term-revealed operands, on tcgen05 tensor cores.
+//
+// Reference: tr_layer.py:126 / :154 feed the DEQUANTISED fp32 activations and weights to cuDNN /
+// cuBLAS.  Here the operands are the integer term codes themselves (tq_tr_encode_codes), held as
+// fp16 (every |code| <= 2048 is exact in an 11-bit significand), multiplied with
+// tcgen05.mma kind::f16 into an fp32 accumulator in TMEM, and the scale sf_x * sf_w is applied
+// once in the epilogue.  All products (<= 2^17) and all partial sums below 2^24 are exact
+// integers in fp32, so the accumulator equals the int32 accumulator of an integer conv as long as
+// sum_k |a_k w_k| < 2^24 for every output (DESIGN.md section 6 explains how that is checked).
+//
+// Implicit GEMM, NHWC activations, [R*S][Cout][Cin] weights:
+//   M tile  = a box of  nbox x hbox x wbox  output pixels (<= 128 rows), fetched per filter tap
+//             (r, s) by ONE tiled 4-D TMA load at offset (h0*stride + r - pad, w0*stride + s - pad)
+//             with element strides = conv stride; out-of-image pixels arrive as zeros (padding
+//             is free), so there is no im2col buffer and no index arithmetic on the SMs.
+//   K loop  = taps x 64-channel blocks; each stage holds a 128x64 A tile and a BLOCK_N x 64 B
+//             tile, both K-major with the 128-byte swizzle TMA and UMMA agree on.
+//   N tile  = BLOCK_N output channels; two accumulator stages in TMEM so the epilogue of tile i
+//             overlaps the MMAs of tile i+1.
+// Warp roles (256 threads, persistent CTAs, one per SM): warp 0 TMA producer, warp 1 MMA
+// issuer (one thread), warp 2 TMEM allocator, warps 4-7 epilogue (TMEM -> registers -> global).
+#include <cuda.h>
+
+#include <mutex>
+
+#include "tq_common.cuh"
+
+namespace tq {
+
+constexpr int GM_BLOCK_M = 128;
+constexpr int GM_BLOCK_K = 64;                  // fp16 elements = 128 bytes = one swizzle row
+constexpr int GM_THREADS = 256;
+constexpr int GM_A_BYTES = GM_BLOCK_M * GM_BLOCK_K * 2;
+
+struct ConvGeom {
+    int N, H, W, C, Cout, R, S, stride, pad, Ho, Wo;
+    int wbox, hbox, nbox;                       // output pixels per M tile
+    int tiles_w, tiles_h, tiles_n;              // M tiles along w, h, image
+    int m_tiles, n_tiles, kc_blocks;
+    int a_tx_bytes;                             // bytes one A box deposits
+    float scale;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzle: rows of 128 B, 8-row atoms 1024 B apart (SBO), LBO unused,
+// descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int BLOCK_N, int STAGES>
+struct GemmSmem {
+    static constexpr int B_BYTES = BLOCK_N * GM_BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = GM_A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;   // + alignment slack
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(GM_THREADS, 1)
+conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const float *__restrict__ bias, float *__restrict__ out, const ConvGeom g)
+{
+    using L = GemmSmem<BLOCK_N, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::BAR_OFFSET);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tfull_bar = empty_bar + STAGES;       // [2] accumulator ready
+    uint64_t *tempty_bar = tfull_bar + 2;           // [2] accumulator drained
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = g.m_tiles * g.n_tiles;
+    const int kblocks = g.R * g.S * g.kc_blocks;
+    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;     // power of two >= 32 for BLOCK_N in {64, 128}
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ================= TMA producer =================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int n_tile = tile % g.n_tiles, m_tile = tile / g.n_tiles;
+            const int tw = m_tile % g.tiles_w, th = (m_tile / g.tiles_w) % g.tiles_h, tn = m_tile / (g.tiles_w * g.tiles_h);
+            const int w_in0 = tw * g.wbox * g.stride - g.pad, h_in0 = th * g.hbox * g.stride - g.pad, n0 = tn * g.nbox;
+            for (int tap = 0; tap < g.R * g.S; ++tap) {
+                const int r = tap / g.S, s = tap % g.S;
+                for (int kc = 0; kc < g.kc_blocks; ++kc) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    uint8_t *sa = smem + stage * L::STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], (uint32_t)(g.a_tx_bytes + L::B_BYTES));
+                    tma_load_4d(&tmA, &full_bar[stage], sa, kc * GM_BLOCK_K, w_in0 + s, h_in0 + r, n0);
+                    tma_load_3d(&tmB, &full_bar[stage], sa + GM_A_BYTES, kc * GM_BLOCK_K, n_tile * BLOCK_N, tap);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ================= MMA issuer (one thread) =================
+        // instruction descriptor: D = F32, A = B = F16, both K-major, N = BLOCK_N, M = 128
+        constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(GM_BLOCK_M >> 4) << 24);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+                const uint64_t da = smem_desc_sw128(sa), db = smem_desc_sw128(sa + GM_A_BYTES);
+#pragma unroll
+                for (int k = 0; k < GM_BLOCK_K / 16; ++k)      // UMMA_K = 16 fp16 = 32 bytes = +2 in the address field
+                    umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+                umma_commit(&empty_bar[stage]);                 // frees the smem stage when the MMAs retire
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+            umma_commit(&tfull_bar[acc]);                       // accumulator complete
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue: TMEM -> registers -> global (fp32 NHWC) =================
+        const int ew = warp - 4;                                // TMEM lanes 32*ew .. 32*ew+31
+        const int row = ew * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int n_tile = tile % g.n_tiles, m_tile = tile / g.n_tiles;
+            const int tw = m_tile % g.tiles_w, th = (m_tile / g.tiles_w) % g.tiles_h, tn = m_tile / (g.tiles_w * g.tiles_h);
+            const int wl = row % g.wbox, hl = (row / g.wbox) % g.hbox, nl = row / (g.wbox * g.hbox);
+            const int wo = tw * g.wbox + wl, ho = th * g.hbox + hl, n = tn * g.nbox + nl;
+            const bool valid = nl < g.nbox && n < g.N && ho < g.Ho && wo < g.Wo;
+            const int c0 = n_tile * BLOCK_N;
+            float *dst = out + (((int64_t)n * g.Ho + ho) * g.Wo + wo) * g.Cout + c0;
+
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < BLOCK_N / 32; ++cc) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BLOCK_N + cc * 32), v);
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const int c = c0 + cc * 32 + j;
+                        if (c < g.Cout) {                        // Cout % 4 == 0 is required by the host
+                            float4 o;
+                            // acc * scale, then + bias: two roundings (no FMA), like mul followed by add
+                            o.x = __fmul_rn(__uint_as_float(v[j + 0]), g.scale);
+                            o.y = __fmul_rn(__uint_as_float(v[j + 1]), g.scale);
+                            o.z = __fmul_rn(__uint_as_float(v[j + 2]), g.scale);
+                            o.w = __fmul_rn(__uint_as_float(v[j + 3]), g.scale);
+                            if (bias) {
+                                const float4 b = *reinterpret_cast<const float4 *>(bias + c);
+                                o.x = __fadd_rn(o.x, b.x); o.y = __fadd_rn(o.y, b.y);
+                                o.z = __fadd_rn(o.z, b.z); o.w = __fadd_rn(o.w, b.w);
+                            }
+                            *reinterpret_cast<float4 *>(dst + cc * 32 + j) = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+// choose the pixel box (wbox, hbox, nbox), product <= 128, that needs the fewest M tiles
+static void pick_box(ConvGeom &g)
+{
+    long best = -1;
+    for (int wb = 1; wb <= g.Wo && wb <= 128; ++wb) {
+        if (wb * g.stride > 256) break;
+        for (int hb = 1; hb <= g.Ho && wb * hb <= 128; ++hb) {
+            if (hb * g.stride > 256) break;
+            int nb = 1;
+            if (wb == g.Wo && hb == g.Ho) nb = 128 / (wb * hb) < g.N ? 128 / (wb * hb) : g.N;
+            if (nb < 1) nb = 1;
+            const long tiles = (long)((g.Wo + wb - 1) / wb) * ((g.Ho + hb - 1) / hb) * ((g.N + nb - 1) / nb);
+            if (best < 0 || tiles < best || (tiles == best && wb > g.wbox)) {
+                best = tiles;
+                g.wbox = wb; g.hbox = hb; g.nbox = nb;
+            }
+        }
+    }
+    g.tiles_w = (g.Wo + g.wbox - 1) / g.wbox;
+    g.tiles_h = (g.Ho + g.hbox - 1) / g.hbox;
+    g.tiles_n = (g.N + g.nbox - 1) / g.nbox;
+    g.m_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
+    g.a_tx_bytes = g.wbox * g.hbox * g.nbox * GM_BLOCK_K * 2;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_conv(const CUtensorMap &tmA, const CUtensorMap &tmB, const float *bias, float *out,
+                       const ConvGeom &g, cudaStream_t s)
+{
+    using L = GemmSmem<BLOCK_N, STAGES>;
+    auto kern = conv_igemm_f16_kernel<BLOCK_N, STAGES>;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess)
+            return check_launch("cudaFuncSetAttribute(conv_igemm_f16_kernel)");
+        attr_set[dev] = true;
+    }
+    const int total = g.m_tiles * g.n_tiles;
+    const int grid = total < num_sms() ? total : num_sms();
+    kern<<<grid, GM_THREADS, L::TOTAL, s>>>(tmA, tmB, bias, out, g);
+    count_launch();
+    return check_launch("conv_igemm_f16_kernel");
+}
+
+}  // namespace tq
+
+using namespace tq;
+
+extern "C" int tq_conv2d_codes_f16(const void *act, const void *wgt, const float *bias, float *out,
+                                   int N, int H, int W, int C, int Cout, int R, int S, int stride, int pad,
+                                   float scale, void *stream)
+{
+    if (!act || !wgt || !out) return fail(TQ_ERR_INVALID, "NULL pointer");
+    if (N < 1 || H < 1 || W < 1 || C < 1 || Cout < 1 || R < 1 || S < 1 || stride < 1 || pad < 0)
+        return fail(TQ_ERR_INVALID, "bad convolution geometry");
+    if (C % 8 != 0) return fail(TQ_ERR_UNSUPPORTED, "input channels must be a multiple of 8 (16-byte TMA rows), got %d", C);
+    if (Cout % 4 != 0) return fail(TQ_ERR_UNSUPPORTED, "output channels must be a multiple of 4, got %d", Cout);
+    if ((((uintptr_t)act | (uintptr_t)wgt | (uintptr_t)out | (uintptr_t)bias) & 15u) != 0)
+        return fail(TQ_ERR_INVALID, "pointers must be 16-byte aligned");
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return fail(TQ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+
+    ConvGeom g{};
+    g.N = N; g.H = H; g.W = W; g.C = C; g.Cout = Cout; g.R = R; g.S = S; g.stride = stride; g.pad = pad;
+    g.Ho = (H + 2 * pad - R) / stride + 1;
+    g.Wo = (W + 2 * pad - S) / stride + 1;
+    if (g.Ho < 1 || g.Wo < 1) return fail(TQ_ERR_INVALID, "empty output");
+    g.scale = scale;
+    g.kc_blocks = (C + GM_BLOCK_K - 1) / GM_BLOCK_K;
+    pick_box(g);
+    const int block_n = Cout <= 64 ? 64 : 128;
+    g.n_tiles = (Cout + block_n - 1) / block_n;
+
+    // activations: (C, W, H, N) fp16, box (64, wbox*stride, hbox*stride, nbox), element strides (1, s, s, 1)
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+        cuuint32_t box[4] = {(cuuint32_t)GM_BLOCK_K, (cuuint32_t)(g.wbox * stride), (cuuint32_t)(g.hbox * stride), (cuuint32_t)g.nbox};
+        cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(act), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(TQ_ERR_CUDA, "cuTensorMapEncodeTiled(activations) failed: %d", (int)r);
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Cout, (cuuint64_t)(R * S)};
+        cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)Cout * C * 2};
+        cuuint32_t box[3] = {(cuuint32_t)GM_BLOCK_K, (cuuint32_t)block_n, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(wgt), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(TQ_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (block_n == 64) return launch_conv<64, 6>(tmA, tmB, bias, out, g, s);
+    return launch_conv<128, 6>(tmA, tmB, bias, out, g, s);
+}
