@@ -94,34 +94,46 @@ def build_tq_resnet18(device):
     return qmodel.eval()
 
 
-class TRTimer:
-    """Wraps tr_cuda.tr so that every launch inside the timed region is bracketed by CUDA events
-    on the launching stream: per-launch durations for the roofline object."""
+class KernelTimer:
+    """Wraps the Python entry points of this repo's kernels so that every launch inside the
+    timed region is bracketed by CUDA events on the launching stream: per-launch durations and
+    algorithmic bytes / flops for the roofline objects."""
 
     def __init__(self):
-        from term_quantization_b200 import tr_cuda
-        self.mod, self.orig, self.records, self.on = tr_cuda, tr_cuda.tr, [], False
+        from term_quantization_b200 import conv_codes, tr_cuda
+        self.on = False
+        self.records = {"tr_encode": [], "conv": []}
+        self.targets = [(tr_cuda, "tr", "tr_encode", lambda a, k, out: a[0].numel() * a[0].element_size() * 2),
+                        (tr_cuda, "tr_codes", "tr_encode",
+                         lambda a, k, out: a[0].numel() * (a[0].element_size() + out.element_size())),
+                        (conv_codes, "conv2d_codes", "conv",
+                         lambda a, k, out: 2 * out.numel() * a[1].shape[0] * a[1].shape[2])]
+        self.saved = []
 
     def __enter__(self):
-        def timed(input, *a, **k):
-            if not self.on:
-                return self.orig(input, *a, **k)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            out = self.orig(input, *a, **k)
-            e1.record()
-            self.records.append((e0, e1, input.numel() * input.element_size() * 2))
-            return out
-        self.mod.tr = timed
+        for mod, attr, key, work in self.targets:
+            orig = getattr(mod, attr)
+            self.saved.append((mod, attr, orig))
+
+            def timed(*a, _orig=orig, _key=key, _work=work, **k):
+                if not self.on:
+                    return _orig(*a, **k)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = _orig(*a, **k)
+                e1.record()
+                self.records[_key].append((e0, e1, _work(a, k, out)))
+                return out
+            setattr(mod, attr, timed)
         return self
 
     def __exit__(self, *exc):
-        self.mod.tr = self.orig
+        for mod, attr, orig in self.saved:
+            setattr(mod, attr, orig)
 
-    def summary(self):
-        ms = sum(a.elapsed_time(b) for a, b, _ in self.records)
-        by = sum(n for _, _, n in self.records)
-        return len(self.records), by, ms
+    def summary(self, key):
+        rec = self.records[key]
+        return len(rec), sum(w for _, _, w in rec), sum(a.elapsed_time(b) for a, b, _ in rec)
 
 
 def run_b200(args):
@@ -145,6 +157,12 @@ def run_b200(args):
     nbuf = 2
     images = [torch.randn(BATCH, 3, 224, 224, device=dev, generator=gen) for _ in range(nbuf)]
     inference.calibrate(model, [images[0][:64]])          # untimed: histograms + fused sweep
+    if args.conv_backend == "tcgen05":
+        from term_quantization_b200 import tr_layer
+        model = model.to(memory_format=torch.channels_last)
+        images = [im.contiguous(memory_format=torch.channels_last) for im in images]
+        switched, skipped = tr_layer.use_tensor_cores(model)
+        assert len(switched) == 19 and not skipped, (switched, skipped)
     runner = inference.ShardedInference(model, dev)
 
     def barrier():
@@ -158,7 +176,7 @@ def run_b200(args):
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    with TRTimer() as trt:
+    with KernelTimer() as trt:
         trt.on = True
         launches0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -173,7 +191,8 @@ def run_b200(args):
         launches = _lib.launch_count() - launches0
         trt.on = False
         ms_total = e0.elapsed_time(e1)
-        n_tr, tr_bytes, tr_ms = trt.summary()
+        n_tr, tr_bytes, tr_ms = trt.summary("tr_encode")
+        n_cv, cv_flops, cv_ms = trt.summary("conv")
     clocks = sampler.finish()
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -182,7 +201,10 @@ def run_b200(args):
     assert out.shape == (BATCH * world, 1000) and bool(torch.isfinite(out).all())
 
     # ---- e2e: pinned host images -> H2D -> forward -> all-gather -> logits D2H -------------
-    host = [torch.randn(BATCH, 3, 224, 224).pin_memory() for _ in range(2)]
+    host = [torch.randn(BATCH, 3, 224, 224) for _ in range(2)]
+    if args.conv_backend == "tcgen05":
+        host = [h.contiguous(memory_format=torch.channels_last) for h in host]
+    host = [h.pin_memory() for h in host]
     slot = runner.stage(host[0])
     for i in range(max(args.warmup, 1)):
         nxt = runner.stage(host[(i + 1) % 2])
@@ -207,11 +229,32 @@ def run_b200(args):
     if rank == 0:
         peak, peak_src = peaks()
         ach = tr_bytes / (tr_ms * 1e-3) / 1e9 if tr_ms > 0 else 0.0
+        tr_roof = {"kernel": "tq::tr_elem_kernel (g=1 TR encode of every wrapped conv's input, 19 launches "
+                             "per forward; fp32 in, " + ("fp16 codes out: 6 B/elem" if args.conv_backend == "tcgen05"
+                                                         else "fp32 out: 8 B/elem") + ")",
+                   "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                   "traffic": None, "peak_source": peak_src, "launches_timed": n_tr,
+                   "algorithmic_bytes": tr_bytes, "kernel_ms_total": tr_ms, "share_of_step": tr_ms / ms_total}
+        conv_roof = None
+        if n_cv:
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                    tpeak, tsrc = float(json.load(f)["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained; f16 runs at the bf16 rate)"
+            except Exception:
+                tpeak, tsrc = 1400.0, "fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)"
+            tach = cv_flops / (cv_ms * 1e-3) / 1e12
+            conv_roof = {"kernel": "tq::conv_igemm_f16_kernel (tcgen05 kind::f16 implicit GEMM on term codes, "
+                                   "19 launches per forward)",
+                         "bound": "tensor", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s", "frac": tach / tpeak,
+                         "traffic": None, "peak_source": tsrc, "launches_timed": n_cv,
+                         "algorithmic_flops": cv_flops, "kernel_ms_total": cv_ms, "share_of_step": cv_ms / ms_total}
+        dominant, other = (conv_roof, tr_roof) if (conv_roof and cv_ms > tr_ms) else (tr_roof, conv_roof)
         line = {
             "metric": METRIC, "value": BATCH * world * args.steps / (ms_total * 1e-3),
             "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 values / int32 term codes (TR encode); f32 conv",
+            "vs_baseline": None, "dtype": ("int term codes (TR encode) held in f16, f32 accumulate (exact integers) on tcgen05"
+                                       if args.conv_backend == "tcgen05" else "f32 values (TR encode); f32 conv"),
             "data": "synthetic (randn images, random-init torchvision resnet18, seed 0)",
             "config": {"workload": "ResNet-18 TQ inference, batch 256 per GPU at 3x224x224 "
                                    "(BASELINE.json configs[1])", **SETTING,
@@ -226,12 +269,8 @@ def run_b200(args):
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "tq::tr_elem_kernel<float,float> (g=1 TR encode of every wrapped "
-                                   "conv's input, 19 launches per forward)",
-                         "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                         "launches_timed": n_tr, "algorithmic_bytes": tr_bytes,
-                         "kernel_ms_total": tr_ms, "share_of_step": tr_ms / ms_total},
+            "roofline": dominant,
+            "roofline_other": other,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_images_per_sec(sample_batch=args.cpu_batch, steps=1)
@@ -310,7 +349,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--conv-backend", default="cudnn_fp32")
+    ap.add_argument("--conv-backend", default="tcgen05", choices=["tcgen05", "cudnn_fp32"],
+                    help="tcgen05: code-domain conv on tensor cores (csrc/tq_gemm.cu); "
+                         "cudnn_fp32: the reference's float path")
     ap.add_argument("--cpu-batch", type=int, default=16, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -30,7 +30,7 @@ from . import tr_cuda
 
 STRICT_REFERENCE = True
 
-__all__ = ["hese", "mse_profile", "compute_compressed_hese", "set_tr_tracking", "LinearQuantize",
+__all__ = ["hese", "mse_profile", "compute_compressed_hese", "set_tr_tracking", "use_tensor_cores", "LinearQuantize",
            "TRConv2dLayer", "TRLinearLayer", "TRLSTMLayer", "tr_cuda", "STRICT_REFERENCE"]
 
 
@@ -95,6 +95,21 @@ def compute_compressed_hese(w, sf, weight_terms):
                                            torch.cuda.current_stream(w.device).cuda_stream)
     _lib.check(rc)
     return bit_width * int(count.item())
+
+
+def use_tensor_cores(model, enable=True):
+    """Switch every supported TRConv2dLayer of `model` to the tcgen05 code-domain conv.
+    Returns (switched, skipped) where skipped is a list of (module name, reason)."""
+    switched, skipped = [], []
+    for name, layer in model.named_modules():
+        if isinstance(layer, TRConv2dLayer):
+            why = layer.tensor_core_blocker() if enable else None
+            if why is None:
+                layer.use_tensor_cores(enable)
+                switched.append(name)
+            else:
+                skipped.append((name, why))
+    return switched, skipped
 
 
 def set_tr_tracking(model, tracking):
@@ -176,7 +191,14 @@ class _TRBase(nn.Module):
 
 
 class TRConv2dLayer(_TRBase):
-    """Conv2d on term-revealed weights and activations (tr_layer.py:106-132)."""
+    """Conv2d on term-revealed weights and activations (tr_layer.py:106-132).
+
+    Default forward = the reference's: dequantised activations into the stock fp32 conv.
+    After ``use_tensor_cores()`` the same layer computes on the integer term codes with the
+    tcgen05 kernel (csrc/tq_gemm.cu): activations are encoded to fp16 codes in NHWC, weights
+    are the packed codes of the already term-revealed ``conv.weight``, the exact integer
+    accumulator is scaled by ``sf_x * w_sf`` (+ bias) in the epilogue, and the result comes
+    back as a channels_last fp32 tensor."""
 
     def __init__(self, conv_layer, data_bits=8, data_terms=4, weight_bits=8, group_size=1,
                  num_terms=8):
@@ -185,8 +207,62 @@ class TRConv2dLayer(_TRBase):
                     num_terms)
         conv_layer.weight = self._reveal_weight(conv_layer.weight)
         self.conv = conv_layer
+        self._tc_weight = None
+
+    def tensor_core_blocker(self):
+        """None if the tcgen05 path supports this layer, else the reason it does not."""
+        c = self.conv
+        if not isinstance(c, nn.Conv2d) or type(c) is not nn.Conv2d:
+            return "not a plain nn.Conv2d"
+        if c.groups != 1:
+            return "grouped/depthwise conv"
+        if c.dilation != (1, 1):
+            return "dilated conv"
+        if c.stride[0] != c.stride[1] or c.padding[0] != c.padding[1] or isinstance(c.padding, str):
+            return "asymmetric stride/padding"
+        if c.padding_mode != "zeros":
+            return "non-zero padding mode"
+        if c.in_channels % 8 or c.out_channels % 4:
+            return "channel counts must be multiples of 8 (in) and 4 (out)"
+        if self.weight_bits > 11 or self.data_bits > 11:
+            return "codes above 2^11 are not exact in fp16"
+        if c.weight.dtype != torch.float32:
+            return "fp32 weights only"
+        return None
+
+    def use_tensor_cores(self, enable=True):
+        if not enable:
+            self._tc_weight = None
+            return self
+        why = self.tensor_core_blocker()
+        if why is not None:
+            raise NotImplementedError(f"tcgen05 conv path: {why}")
+        w = self.conv.weight.detach()
+        sf32 = torch.tensor(self.w_sf, dtype=torch.float32).item()       # what the binding saw
+        codes = torch.round(w / sf32)
+        if not torch.equal(codes * sf32, w):
+            raise RuntimeError("conv.weight is not an integer multiple of w_sf any more")
+        O, I, kh, kw = codes.shape
+        self._tc_weight = codes.permute(2, 3, 0, 1).reshape(kh * kw, O, I).to(torch.float16).contiguous()
+        self._tc_wsf32 = sf32
+        return self
+
+    def _forward_tensor_cores(self, x):
+        from . import conv_codes
+        c = self.conv
+        q = self.input_quant
+        x_nhwc = x.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)   # physical NHWC view
+        codes = tr_cuda.tr_codes(x_nhwc.view(1, -1, 1, 1), q.sf, q.data_bits, 1, q.data_terms,
+                                 dtype=torch.float16).view(x_nhwc.shape)
+        sfx32 = torch.tensor(float(q.sf), dtype=torch.float32)
+        scale = (sfx32 * torch.tensor(self._tc_wsf32, dtype=torch.float32)).item()   # fp32 product
+        out = conv_codes.conv2d_codes(codes, self._tc_weight, c.bias, c.kernel_size, c.stride[0],
+                                      c.padding[0], scale)
+        return out.permute(0, 3, 1, 2)                                   # NCHW shape, channels_last memory
 
     def forward(self, x):
+        if self._tc_weight is not None and not self.input_quant.tracking:
+            return self._forward_tensor_cores(x)
         return self.conv(self.input_quant(x))
 
 

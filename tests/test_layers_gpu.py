@@ -184,3 +184,37 @@ def test_evaluate_drivers_run_on_synthetic_data(tmp_path):
     assert len(res["ppls"]) == 1 and np.isfinite(res["ppls"][0])
     # decoder term pairs: 8 * (12/8) * (35*10*33278*64) accumulated in float32
     assert res["tmacs"][0] == float(np.float32(int(8 * 1.5 * 35 * 10 * 33278 * 64)))
+
+
+def test_tensor_core_conv_layer_matches_float_path():
+    """TRConv2dLayer.use_tensor_cores(): same layer, computed on integer codes by the tcgen05
+    kernel.  Integer accumulators are exact (tests/test_conv_gpu.py); here the layer output is
+    compared with the reference float path (fp32 cuDNN conv of the dequantised operands)."""
+    from term_quantization_b200 import cnn_models, tr_layer
+    base = _small_cnn().cuda()
+    params = cnn_models.static_conv_layer_settings(base, 9, 8, 12)
+    q = cnn_models.convert_model(base, params, 9, 3)
+    x = torch.randn(6, 3, 40, 40, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+    with torch.no_grad():
+        q(x)
+        tr_layer.set_tr_tracking(q, False)
+        want = q(x)
+        layers = [m for m in q.modules() if isinstance(m, tr_layer.TRConv2dLayer)]
+        feats = {}
+        hooks = [m.register_forward_hook(lambda mod, i, o, k=k: feats.__setitem__(k, (i[0], o)))
+                 for k, m in enumerate(layers)]
+        q(x)
+        ref_feats = dict(feats)
+        switched, skipped = tr_layer.use_tensor_cores(q)
+        assert len(switched) == 2 and len(skipped) == 1 and "grouped" in skipped[0][1]
+        got = q(x)
+        for k in (0, 2):
+            xin, yref = ref_feats[k]
+            yin, ytc = feats[k]
+            assert torch.equal(xin, yin)                      # same inputs up to that layer
+            assert ytc.is_contiguous(memory_format=torch.channels_last)
+            tol = 2e-6 * float(yref.abs().max()) * (layers[k].conv.in_channels * 9) ** 0.5
+            assert float((ytc - yref).abs().max()) <= tol
+        for h in hooks:
+            h.remove()
+    assert torch.allclose(got, want, rtol=1e-4, atol=1e-4 * float(want.abs().max()))
