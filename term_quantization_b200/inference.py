@@ -88,8 +88,10 @@ class ShardedInference:
         Two slots: stage shard i+1, then run(shard i), and the copy overlaps the compute."""
         s = self._slot
         self._slot ^= 1
-        if self._stage[s] is None or self._stage[s].shape != pinned.shape:
-            self._stage[s] = torch.empty(pinned.shape, dtype=pinned.dtype, device=self.device)
+        if self._stage[s] is None or self._stage[s].shape != pinned.shape or \
+                self._stage[s].stride() != pinned.stride():
+            # same strides as the host tensor (e.g. channels_last): the copy is one plain DMA
+            self._stage[s] = torch.empty_like(pinned, device=self.device)
         # the slot may still be read by the forward enqueued two steps ago
         self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.copy_stream):
