@@ -153,6 +153,23 @@ int tq_conv2d_codes_f16(const void *act, const void *wgt, const float *bias, flo
                         float scale, void *stream);
 
 /*
+ * Same contraction with the layer's whole tail fused into the epilogue (verilog/systolic_dla_top.v
+ * pipeline order: accumulate -> ReLU/requantise -> encode -> truncate; tr_layer.py:124-126 plus the
+ * BatchNorm / residual / ReLU that follow a conv in the CNNs of cnn_models/):
+ *     t = acc * scale (+ bias[co]);  t = fma(t, bn_a[co], bn_b[co]);  t += residual[n,ho,wo,co];
+ *     t = max(t, 0) if relu;  out_f32 = t;  out_codes = term code of t under the consumer's quantiser
+ *     (next_sf, next_bits <= 10, next_terms; g = 1, HESE) stored as fp16 NHWC.
+ * Every step is optional (NULL pointer / relu = 0); at least one of out_f32, out_codes is given.
+ * Outputs are written with TMA stores from swizzled shared memory (fully coalesced, clipped at
+ * the tensor edge).
+ */
+int tq_conv2d_codes_fused(const void *act, const void *wgt, float *out_f32, void *out_codes,
+                          const float *bias, const float *bn_a, const float *bn_b, const float *residual,
+                          int N, int H, int W, int C, int Cout, int R, int S, int stride, int pad,
+                          float scale, int relu, float next_sf, int next_bits, int next_terms,
+                          void *stream);
+
+/*
  * Device self-test: quantises n pseudo-random (a, sf) pairs (sf in [2^-30, 2^30], a over all
  * non-negative floats and the quantiser's rounding boundaries) with the hoisted-reciprocal
  * divide and with div.rn.f32 and adds the number of disagreements to *mismatch (device).

@@ -39,3 +39,34 @@ def conv2d_codes(act, wgt, bias, kernel_size, stride, pad, scale, out=None):
             torch.cuda.current_stream(act.device).cuda_stream)
     _lib.check(rc)
     return out
+
+
+def conv2d_codes_fused(act, wgt, kernel_size, stride, pad, scale, *, bias=None, bn=None, residual=None,
+                       relu=False, want_f32=True, next_quant=None):
+    """Conv on codes with the fused tail (see tq_conv2d_codes_fused in include/tq_b200.h).
+
+    bn = (a, b) fp32 [Cout] per-channel affine applied as fma(t, a, b); residual fp32
+    [N, Ho, Wo, Cout]; next_quant = (sf, bits, terms) of the consumer's LinearQuantize.
+    Returns (out_f32 or None, out_codes or None)."""
+    N, H, W, C = act.shape
+    R, S = kernel_size
+    RS, Cout, C2 = wgt.shape
+    if act.dtype != torch.float16 or wgt.dtype != torch.float16 or RS != R * S or C2 != C:
+        raise RuntimeError("conv2d_codes_fused: bad operands")
+    Ho = (H + 2 * pad - R) // stride + 1
+    Wo = (W + 2 * pad - S) // stride + 1
+    out = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=act.device) if want_f32 else None
+    codes = torch.empty((N, Ho, Wo, Cout), dtype=torch.float16, device=act.device) if next_quant else None
+    if residual is not None and (residual.shape != (N, Ho, Wo, Cout) or not residual.is_contiguous()
+                                 or residual.dtype != torch.float32):
+        raise RuntimeError("residual must be a contiguous fp32 [N, Ho, Wo, Cout] tensor")
+    sf, bits, terms = next_quant if next_quant else (1.0, 1, 0)
+    ptr = lambda t: t.data_ptr() if t is not None else None   # noqa: E731
+    with torch.cuda.device(act.device):
+        rc = _lib.lib().tq_conv2d_codes_fused(
+            act.data_ptr(), wgt.data_ptr(), ptr(out), ptr(codes), ptr(bias),
+            ptr(bn[0]) if bn else None, ptr(bn[1]) if bn else None, ptr(residual),
+            N, H, W, C, Cout, R, S, stride, pad, float(scale), int(bool(relu)), float(sf), int(bits),
+            int(terms), torch.cuda.current_stream(act.device).cuda_stream)
+    _lib.check(rc)
+    return out, codes

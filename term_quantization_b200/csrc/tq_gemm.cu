@@ -17,8 +17,9 @@
 //             tile, both K-major with the 128-byte swizzle TMA and UMMA agree on.
 //   N tile  = BLOCK_N output channels; two accumulator stages in TMEM so the epilogue of tile i
 //             overlaps the MMAs of tile i+1.
-// Warp roles (256 threads, persistent CTAs, one per SM): warp 0 TMA producer, warp 1 MMA
-// issuer (one thread), warp 2 TMEM allocator, warps 4-7 epilogue (TMEM -> registers -> global).
+// Warp roles (384 threads, persistent CTAs, one per SM): warp 0 TMA producer, warp 1 MMA
+// issuer (one thread), warp 2 TMEM allocator, warps 4-7 / 8-11 two epilogue groups, one per
+// accumulator stage (TMEM -> registers -> fused tail -> swizzled smem -> TMA store).
 #include <cuda.h>
 
 #include <mutex>
@@ -29,7 +30,7 @@ namespace tq {
 
 constexpr int GM_BLOCK_M = 128;
 constexpr int GM_BLOCK_K = 64;                  // fp16 elements = 128 bytes = one swizzle row
-constexpr int GM_THREADS = 256;
+constexpr int GM_THREADS = 384;                 // 4 control warps + 2 epilogue groups of 4 warps
 constexpr int GM_A_BYTES = GM_BLOCK_M * GM_BLOCK_K * 2;
 
 struct ConvGeom {
@@ -39,6 +40,12 @@ struct ConvGeom {
     int m_tiles, n_tiles, kc_blocks;
     int a_tx_bytes;                             // bytes one A box deposits
     float scale;
+    // fused epilogue (all optional):  t = acc*scale (+bias) ; t = fma(t, bn_a, bn_b) ; t += residual ;
+    // t = max(t, 0) ; fp32 tile out (TMA store) ; fp16 term codes of t for the next layer (TMA store)
+    const float *bias, *bn_a, *bn_b, *residual;
+    int relu, write_f32, write_codes;
+    float next_sf;
+    int next_bits, next_terms, next_fastdiv;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -109,6 +116,22 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *src, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // K-major, 128-byte swizzle: rows of 128 B, 8-row atoms 1024 B apart (SBO), LBO unused,
 // descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B)
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr)
@@ -116,18 +139,25 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr)
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+constexpr int GM_LUT_MAX_BITS = 10;             // fused next-layer encode: 2^(bits+1) fp16 entries in smem
+
 template <int BLOCK_N, int STAGES>
 struct GemmSmem {
     static constexpr int B_BYTES = BLOCK_N * GM_BLOCK_K * 2;
     static constexpr int STAGE_BYTES = GM_A_BYTES + B_BYTES;
-    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    // per epilogue group: [128 rows][128 B] fp32 (32 columns) + [128 rows][64 B] fp16 codes
+    static constexpr int EPI_BYTES = 16384 + 8192;
+    static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int LUT_OFFSET = EPI_OFFSET + 2 * EPI_BYTES;
+    static constexpr int BAR_OFFSET = LUT_OFFSET + (2 << GM_LUT_MAX_BITS) * 2;
     static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;   // + alignment slack
 };
 
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const float *__restrict__ bias, float *__restrict__ out, const ConvGeom g)
+                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD,
+                      const ConvGeom g)
 {
     using L = GemmSmem<BLOCK_N, STAGES>;
     extern __shared__ uint8_t smem_raw[];
@@ -146,10 +176,20 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        if (g.write_f32) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+        if (g.write_codes) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
+    }
+    __half *lut = reinterpret_cast<__half *>(smem + L::LUT_OFFSET);
+    if (g.write_codes) {
+        // (q, sign) -> fp16 term code of the consumer's quantiser, as in tr_elem_kernel
+        for (uint32_t i = threadIdx.x; i < (2u << g.next_bits); i += GM_THREADS) {
+            int code = elem_code(i & ((1u << g.next_bits) - 1u), TQ_ENC_HESE, g.next_terms);
+            lut[i] = __int2half_rn((i >> g.next_bits) ? -code : code);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }   // 128 = one epilogue group
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -208,51 +248,116 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     } else if (warp >= 4) {
-        // ================= epilogue: TMEM -> registers -> global (fp32 NHWC) =================
-        const int ew = warp - 4;                                // TMEM lanes 32*ew .. 32*ew+31
+        // ============ epilogue: TMEM -> registers -> swizzled smem -> TMA store ============
+        // Two groups of four warps; group `grp` drains accumulator stage `grp` (every second tile
+        // of this CTA), so one group's staging/TMA-store latency overlaps the other's arithmetic.
+        const int grp = (warp - 4) >> 2;
+        const int ew = (warp - 4) & 3;                          // TMEM lanes 32*ew .. 32*ew+31
         const int row = ew * 32 + lane;
-        int acc = 0;
+        const bool store_thread = (ew == 0 && lane == 0);
+        uint8_t *st_f32 = smem + L::EPI_OFFSET + grp * L::EPI_BYTES;    // [128][32] fp32, 128B swizzle
+        uint8_t *st_codes = st_f32 + 16384;                             // [128][32] fp16,  64B swizzle
+        const uint32_t sw128 = (uint32_t)(row & 7);             // 16B piece index ^= row % 8
+        const uint32_t sw64 = (uint32_t)((row >> 1) & 3);       // 16B piece index ^= (row / 2) % 4
+        const Quant nq = make_quant(g.write_codes ? g.next_sf : 1.0f, (float)((1u << g.next_bits) - 1u));
+        const bool has_res = g.residual != nullptr;
+        const int acc = grp;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            if ((it & 1) != grp) continue;
             const int n_tile = tile % g.n_tiles, m_tile = tile / g.n_tiles;
             const int tw = m_tile % g.tiles_w, th = (m_tile / g.tiles_w) % g.tiles_h, tn = m_tile / (g.tiles_w * g.tiles_h);
             const int wl = row % g.wbox, hl = (row / g.wbox) % g.hbox, nl = row / (g.wbox * g.hbox);
             const int wo = tw * g.wbox + wl, ho = th * g.hbox + hl, n = tn * g.nbox + nl;
             const bool valid = nl < g.nbox && n < g.N && ho < g.Ho && wo < g.Wo;
-            const int c0 = n_tile * BLOCK_N;
-            float *dst = out + (((int64_t)n * g.Ho + ho) * g.Wo + wo) * g.Cout + c0;
+            const int64_t pix = ((int64_t)n * g.Ho + ho) * g.Wo + wo;
 
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
 #pragma unroll 1
             for (int cc = 0; cc < BLOCK_N / 32; ++cc) {
+                const int c0 = n_tile * BLOCK_N + cc * 32;
+                // (a) this group's previous TMA stores must have finished reading the staging tiles
+                if (store_thread) bulk_wait_read0();
+                epi_bar_sync(1 + grp);
+                // (b) residual row lands in the fp32 staging tile (own row only), asynchronously
+                if (has_res && valid) {
+                    const float *src = g.residual + pix * g.Cout + c0;
+#pragma unroll
+                    for (int p = 0; p < 8; ++p)
+                        if (c0 + p * 4 < g.Cout) cp_async16(st_f32 + row * 128 + (((uint32_t)p ^ sw128) << 4), src + p * 4);
+                }
+                if (cc == 0) {
+                    mbar_wait(&tfull_bar[acc], acc_phase);
+                    tc_fence_after();
+                }
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BLOCK_N + cc * 32), v);
-                if (valid) {
+                if (cc == BLOCK_N / 32 - 1) {                    // accumulator fully drained into registers
+                    tc_fence_before();
+                    mbar_arrive(&tempty_bar[acc]);
+                }
+                if (has_res) cp_async_wait_all();
+                uint32_t cw[4];                                   // 8 codes = one 16-byte piece
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const int c = c0 + cc * 32 + j;
-                        if (c < g.Cout) {                        // Cout % 4 == 0 is required by the host
-                            float4 o;
-                            // acc * scale, then + bias: two roundings (no FMA), like mul followed by add
-                            o.x = __fmul_rn(__uint_as_float(v[j + 0]), g.scale);
-                            o.y = __fmul_rn(__uint_as_float(v[j + 1]), g.scale);
-                            o.z = __fmul_rn(__uint_as_float(v[j + 2]), g.scale);
-                            o.w = __fmul_rn(__uint_as_float(v[j + 3]), g.scale);
-                            if (bias) {
-                                const float4 b = *reinterpret_cast<const float4 *>(bias + c);
-                                o.x = __fadd_rn(o.x, b.x); o.y = __fadd_rn(o.y, b.y);
-                                o.z = __fadd_rn(o.z, b.z); o.w = __fadd_rn(o.w, b.w);
-                            }
-                            *reinterpret_cast<float4 *>(dst + cc * 32 + j) = o;
+                for (int j = 0; j < 32; j += 4) {
+                    const int c = c0 + j;
+                    const bool cvalid = c < g.Cout;               // Cout % 4 == 0
+                    float t[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) t[e] = __fmul_rn(__uint_as_float(v[j + e]), g.scale);
+                    if (g.bias && cvalid) {
+                        const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bias + c));
+                        t[0] = __fadd_rn(t[0], b.x); t[1] = __fadd_rn(t[1], b.y);
+                        t[2] = __fadd_rn(t[2], b.z); t[3] = __fadd_rn(t[3], b.w);
+                    }
+                    if (g.bn_a && cvalid) {
+                        const float4 a = __ldg(reinterpret_cast<const float4 *>(g.bn_a + c));
+                        const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bn_b + c));
+                        t[0] = __fmaf_rn(t[0], a.x, b.x); t[1] = __fmaf_rn(t[1], a.y, b.y);
+                        t[2] = __fmaf_rn(t[2], a.z, b.z); t[3] = __fmaf_rn(t[3], a.w, b.w);
+                    }
+                    float4 *slot = reinterpret_cast<float4 *>(st_f32 + row * 128 + (((uint32_t)(j >> 2) ^ sw128) << 4));
+                    if (has_res && valid && cvalid) {
+                        const float4 r = *slot;
+                        t[0] = __fadd_rn(t[0], r.x); t[1] = __fadd_rn(t[1], r.y);
+                        t[2] = __fadd_rn(t[2], r.z); t[3] = __fadd_rn(t[3], r.w);
+                    }
+                    if (g.relu) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) t[e] = fmaxf(t[e], 0.0f);
+                    }
+                    if (g.write_f32) *slot = make_float4(t[0], t[1], t[2], t[3]);
+                    if (g.write_codes) {
+                        uint32_t hc[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const uint32_t neg = __float_as_uint(t[e]) >> 31;
+                            const uint32_t q = g.next_fastdiv ? quantize_f32<true>(t[e], nq) : quantize_f32<false>(t[e], nq);
+                            hc[e] = __half_as_ushort(lut[q | (neg << g.next_bits)]);
+                        }
+                        const int hi = (j >> 2) & 1;
+                        cw[2 * hi] = hc[0] | (hc[1] << 16);
+                        cw[2 * hi + 1] = hc[2] | (hc[3] << 16);
+                        if (hi) {
+                            const uint32_t piece = (uint32_t)(j >> 3);
+                            *reinterpret_cast<uint4 *>(st_codes + row * 64 + ((piece ^ sw64) << 4)) =
+                                make_uint4(cw[0], cw[1], cw[2], cw[3]);
                         }
                     }
                 }
+                // (c) staging complete: hand it to the async proxy and store
+                fence_proxy_async();
+                epi_bar_sync(1 + grp);
+                if (store_thread && c0 < g.Cout) {
+                    const int w0 = tw * g.wbox, h0 = th * g.hbox, n0 = tn * g.nbox;
+                    if (g.write_f32) tma_store_4d(&tmC, st_f32, c0, w0, h0, n0);
+                    if (g.write_codes) tma_store_4d(&tmD, st_codes, c0, w0, h0, n0);
+                    bulk_commit();
+                }
             }
-            tc_fence_before();
-            mbar_arrive(&tempty_bar[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            acc_phase ^= 1u;
         }
+        if (store_thread) bulk_wait0();
     }
 
     tc_fence_before();
@@ -307,10 +412,11 @@ static void pick_box(ConvGeom &g)
 }
 
 template <int BLOCK_N, int STAGES>
-static int launch_conv(const CUtensorMap &tmA, const CUtensorMap &tmB, const float *bias, float *out,
-                       const ConvGeom &g, cudaStream_t s)
+static int launch_conv(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
+                       const CUtensorMap &tmD, const ConvGeom &g, cudaStream_t s)
 {
     using L = GemmSmem<BLOCK_N, STAGES>;
+    static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
     auto kern = conv_igemm_f16_kernel<BLOCK_N, STAGES>;
     static bool attr_set[64] = {false};
     int dev = 0;
@@ -322,26 +428,50 @@ static int launch_conv(const CUtensorMap &tmA, const CUtensorMap &tmB, const flo
     }
     const int total = g.m_tiles * g.n_tiles;
     const int grid = total < num_sms() ? total : num_sms();
-    kern<<<grid, GM_THREADS, L::TOTAL, s>>>(tmA, tmB, bias, out, g);
+    kern<<<grid, GM_THREADS, L::TOTAL, s>>>(tmA, tmB, tmC, tmD, g);
     count_launch();
     return check_launch("conv_igemm_f16_kernel");
+}
+
+static int encode_map(EncodeTiledFn enc, CUtensorMap *tm, CUtensorMapDataType dt, int esize, const void *base,
+                      int rank, const cuuint64_t *dims, const cuuint32_t *box, const cuuint32_t *estr, const char *what,
+                      CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B)
+{
+    cuuint64_t strides[4];
+    cuuint64_t acc = (cuuint64_t)esize;
+    for (int i = 0; i < rank - 1; ++i) { acc *= dims[i]; strides[i] = acc; }
+    CUresult r = enc(tm, dt, (cuuint32_t)rank, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(TQ_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed: %d", what, (int)r);
+    return TQ_OK;
 }
 
 }  // namespace tq
 
 using namespace tq;
 
-extern "C" int tq_conv2d_codes_f16(const void *act, const void *wgt, const float *bias, float *out,
-                                   int N, int H, int W, int C, int Cout, int R, int S, int stride, int pad,
-                                   float scale, void *stream)
+extern "C" int tq_conv2d_codes_fused(const void *act, const void *wgt, float *out_f32, void *out_codes,
+                                     const float *bias, const float *bn_a, const float *bn_b,
+                                     const float *residual, int N, int H, int W, int C, int Cout, int R, int S,
+                                     int stride, int pad, float scale, int relu, float next_sf, int next_bits,
+                                     int next_terms, void *stream)
 {
-    if (!act || !wgt || !out) return fail(TQ_ERR_INVALID, "NULL pointer");
+    if (!act || !wgt || (!out_f32 && !out_codes)) return fail(TQ_ERR_INVALID, "NULL pointer");
     if (N < 1 || H < 1 || W < 1 || C < 1 || Cout < 1 || R < 1 || S < 1 || stride < 1 || pad < 0)
         return fail(TQ_ERR_INVALID, "bad convolution geometry");
     if (C % 8 != 0) return fail(TQ_ERR_UNSUPPORTED, "input channels must be a multiple of 8 (16-byte TMA rows), got %d", C);
     if (Cout % 4 != 0) return fail(TQ_ERR_UNSUPPORTED, "output channels must be a multiple of 4, got %d", Cout);
-    if ((((uintptr_t)act | (uintptr_t)wgt | (uintptr_t)out | (uintptr_t)bias) & 15u) != 0)
+    if (out_codes && Cout % 8 != 0) return fail(TQ_ERR_UNSUPPORTED, "code output needs Cout %% 8 == 0, got %d", Cout);
+    if ((bn_a == nullptr) != (bn_b == nullptr)) return fail(TQ_ERR_INVALID, "bn_a and bn_b go together");
+    if ((((uintptr_t)act | (uintptr_t)wgt | (uintptr_t)out_f32 | (uintptr_t)out_codes | (uintptr_t)bias |
+          (uintptr_t)bn_a | (uintptr_t)bn_b | (uintptr_t)residual) & 15u) != 0)
         return fail(TQ_ERR_INVALID, "pointers must be 16-byte aligned");
+    if (out_codes) {
+        if (!(next_sf > 0.0f) || !(next_sf < INFINITY)) return fail(TQ_ERR_INVALID, "next_sf must be positive and finite");
+        if (next_bits < 1 || next_bits > GM_LUT_MAX_BITS) return fail(TQ_ERR_UNSUPPORTED, "fused encode supports 1..%d bits", GM_LUT_MAX_BITS);
+        if (next_terms < 0) return fail(TQ_ERR_INVALID, "next_terms must be >= 0");
+    }
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return fail(TQ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
 
@@ -355,30 +485,52 @@ extern "C" int tq_conv2d_codes_f16(const void *act, const void *wgt, const float
     pick_box(g);
     const int block_n = Cout <= 64 ? 64 : 128;
     g.n_tiles = (Cout + block_n - 1) / block_n;
+    g.bias = bias; g.bn_a = bn_a; g.bn_b = bn_b; g.residual = residual;
+    g.relu = relu ? 1 : 0;
+    g.write_f32 = out_f32 ? 1 : 0;
+    g.write_codes = out_codes ? 1 : 0;
+    g.next_sf = out_codes ? next_sf : 1.0f;
+    g.next_bits = out_codes ? next_bits : 1;
+    g.next_terms = next_terms;
+    g.next_fastdiv = (g.next_sf >= 9.313225746154785e-10f && g.next_sf <= 1073741824.0f) ? 1 : 0;
 
-    // activations: (C, W, H, N) fp16, box (64, wbox*stride, hbox*stride, nbox), element strides (1, s, s, 1)
-    CUtensorMap tmA, tmB;
-    {
+    CUtensorMap tmA, tmB, tmC, tmD;
+    int rc;
+    {   // activations: (C, W, H, N) fp16; box spans wbox*stride x hbox*stride pixels, element strides = conv stride
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
         cuuint32_t box[4] = {(cuuint32_t)GM_BLOCK_K, (cuuint32_t)(g.wbox * stride), (cuuint32_t)(g.hbox * stride), (cuuint32_t)g.nbox};
         cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(act), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(TQ_ERR_CUDA, "cuTensorMapEncodeTiled(activations) failed: %d", (int)r);
+        if ((rc = encode_map(enc, &tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, act, 4, dims, box, estr, "activations")) != TQ_OK) return rc;
     }
-    {
+    {   // weights: (C, Cout, R*S) fp16
         cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Cout, (cuuint64_t)(R * S)};
-        cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)Cout * C * 2};
         cuuint32_t box[3] = {(cuuint32_t)GM_BLOCK_K, (cuuint32_t)block_n, 1};
         cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(wgt), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(TQ_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+        if ((rc = encode_map(enc, &tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wgt, 3, dims, box, estr, "weights")) != TQ_OK) return rc;
+    }
+    cuuint64_t odims[4] = {(cuuint64_t)Cout, (cuuint64_t)g.Wo, (cuuint64_t)g.Ho, (cuuint64_t)N};
+    cuuint32_t one[4] = {1, 1, 1, 1};
+    {   // fp32 output tile: 32 channels (128 B) x pixel box
+        cuuint32_t box[4] = {32, (cuuint32_t)g.wbox, (cuuint32_t)g.hbox, (cuuint32_t)g.nbox};
+        const void *base = out_f32 ? (const void *)out_f32 : act;      // unused map still has to be valid
+        if (out_f32) { if ((rc = encode_map(enc, &tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, 4, odims, box, one, "fp32 output")) != TQ_OK) return rc; }
+        else tmC = tmA;
+    }
+    {   // fp16 code output tile: 32 channels (64 B, 64-byte swizzle) x pixel box
+        cuuint32_t box[4] = {32, (cuuint32_t)g.wbox, (cuuint32_t)g.hbox, (cuuint32_t)g.nbox};
+        if (out_codes) { if ((rc = encode_map(enc, &tmD, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, out_codes, 4, odims, box, one, "code output", CU_TENSOR_MAP_SWIZZLE_64B)) != TQ_OK) return rc; }
+        else tmD = tmA;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    if (block_n == 64) return launch_conv<64, 6>(tmA, tmB, bias, out, g, s);
-    return launch_conv<128, 6>(tmA, tmB, bias, out, g, s);
+    if (block_n == 64) return launch_conv<64, 7>(tmA, tmB, tmC, tmD, g, s);
+    return launch_conv<128, 5>(tmA, tmB, tmC, tmD, g, s);
+}
+
+extern "C" int tq_conv2d_codes_f16(const void *act, const void *wgt, const float *bias, float *out,
+                                   int N, int H, int W, int C, int Cout, int R, int S, int stride, int pad,
+                                   float scale, void *stream)
+{
+    if (!out) return fail(TQ_ERR_INVALID, "NULL pointer");
+    return tq_conv2d_codes_fused(act, wgt, out, nullptr, bias, nullptr, nullptr, nullptr, N, H, W, C, Cout, R, S,
+                                 stride, pad, scale, 0, 1.0f, 1, 0, stream);
 }

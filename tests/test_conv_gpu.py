@@ -41,3 +41,49 @@ def test_conv_codes_exact_accumulators(case):
     out2 = conv_codes.conv2d_codes(act.half(), wgt.half(), bias, (k, k), stride, pad, 0.00123)
     want2 = (want.float() * np.float32(0.00123) + bias).float()
     assert torch.equal(out2, want2)
+
+
+FUSED = [(2, 56, 56, 64, 64, 3, 1, 1), (3, 28, 28, 128, 128, 3, 1, 1), (2, 56, 56, 64, 128, 1, 2, 0),
+         (5, 7, 7, 512, 512, 3, 1, 1), (1, 9, 13, 72, 72, 3, 1, 1), (3, 14, 14, 256, 256, 3, 1, 1)]
+
+
+@pytest.mark.parametrize("case", FUSED)
+def test_conv_fused_epilogue(case):
+    """scale -> fma(BN) -> + residual -> ReLU -> fp32 out + fp16 term codes of the result, each
+    step against plain torch / the CPU oracle."""
+    from oracle import tq_oracle as O
+    from term_quantization_b200 import conv_codes
+    N, H, W, C, Cout, k, stride, pad = case
+    g = torch.Generator(device="cuda").manual_seed(7 + sum(case))
+    act = (torch.randint(0, 513, (N, H, W, C), device="cuda", generator=g) *
+           (torch.rand(N, H, W, C, device="cuda", generator=g) < 0.5)).half()
+    wgt = torch.randint(-256, 257, (k * k, Cout, C), device="cuda", generator=g).half()
+    w_oihw = wgt.view(k, k, Cout, C).permute(2, 3, 0, 1).double()
+    acc = F.conv2d(act.permute(0, 3, 1, 2).double(), w_oihw, None, stride, pad).permute(0, 2, 3, 1).float()
+    scale = np.float32(3.1e-6)
+    a = torch.rand(Cout, device="cuda", generator=g) + 0.5
+    b = torch.randn(Cout, device="cuda", generator=g)
+    res = torch.randn(acc.shape, device="cuda", generator=g)
+    t0 = acc * scale
+    t1 = (t0.double() * a.double() + b.double()).float()          # fma(t, a, b), one rounding
+    t2 = t1 + res
+    t3 = torch.relu(t2)
+    nq = (float(t3.max()) / 512, 9, 3)
+
+    out, codes = conv_codes.conv2d_codes_fused(act, wgt, (k, k), stride, pad, scale)
+    assert codes is None and torch.equal(out, t0)
+    out, _ = conv_codes.conv2d_codes_fused(act, wgt, (k, k), stride, pad, scale, bn=(a, b))
+    assert torch.equal(out, t1)
+    out, _ = conv_codes.conv2d_codes_fused(act, wgt, (k, k), stride, pad, scale, bn=(a, b), residual=res)
+    assert torch.equal(out, t2)
+    out, codes = conv_codes.conv2d_codes_fused(act, wgt, (k, k), stride, pad, scale, bn=(a, b), residual=res,
+                                               relu=True, next_quant=nq)
+    assert torch.equal(out, t3)
+    _, want = O.tr(t3.cpu().numpy().reshape(1, -1, 1, 1), nq[0], nq[1], 1, nq[2], return_codes=True)
+    assert np.array_equal(codes.cpu().numpy().astype(np.int32).reshape(-1), want.reshape(-1))
+    # codes only (no fp32 tile), signed values (no ReLU)
+    none, codes = conv_codes.conv2d_codes_fused(act, wgt, (k, k), stride, pad, scale, bn=(a, b), want_f32=False,
+                                                next_quant=(float(t1.abs().max()) / 256, 8, 2))
+    assert none is None
+    _, want = O.tr(t1.cpu().numpy().reshape(1, -1, 1, 1), float(t1.abs().max()) / 256, 8, 1, 2, return_codes=True)
+    assert np.array_equal(codes.cpu().numpy().astype(np.int32).reshape(-1), want.reshape(-1))
