@@ -107,7 +107,10 @@ class KernelTimer:
                         (tr_cuda, "tr_codes", "tr_encode",
                          lambda a, k, out: a[0].numel() * (a[0].element_size() + out.element_size())),
                         (conv_codes, "conv2d_codes", "conv",
-                         lambda a, k, out: 2 * out.numel() * a[1].shape[0] * a[1].shape[2])]
+                         lambda a, k, out: 2 * out.numel() * a[1].shape[0] * a[1].shape[2]),
+                        (conv_codes, "conv2d_codes_fused", "conv",
+                         lambda a, k, out: 2 * (out[0] if out[0] is not None else out[1]).numel()
+                         * a[1].shape[0] * a[1].shape[2])]
         self.saved = []
 
     def __enter__(self):
@@ -157,12 +160,14 @@ def run_b200(args):
     nbuf = 2
     images = [torch.randn(BATCH, 3, 224, 224, device=dev, generator=gen) for _ in range(nbuf)]
     inference.calibrate(model, [images[0][:64]])          # untimed: histograms + fused sweep
-    if args.conv_backend == "tcgen05":
-        from term_quantization_b200 import tr_layer
+    if args.conv_backend in ("tcgen05", "fused"):
+        from term_quantization_b200 import fused, tr_layer
         model = model.to(memory_format=torch.channels_last)
         images = [im.contiguous(memory_format=torch.channels_last) for im in images]
         switched, skipped = tr_layer.use_tensor_cores(model)
         assert len(switched) == 19 and not skipped, (switched, skipped)
+        if args.conv_backend == "fused":
+            model = fused.FusedResNet(model)
     runner = inference.ShardedInference(model, dev)
 
     def barrier():
@@ -202,7 +207,7 @@ def run_b200(args):
 
     # ---- e2e: pinned host images -> H2D -> forward -> all-gather -> logits D2H -------------
     host = [torch.randn(BATCH, 3, 224, 224) for _ in range(2)]
-    if args.conv_backend == "tcgen05":
+    if args.conv_backend in ("tcgen05", "fused"):
         host = [h.contiguous(memory_format=torch.channels_last) for h in host]
     host = [h.pin_memory() for h in host]
     slot = runner.stage(host[0])
@@ -229,8 +234,8 @@ def run_b200(args):
     if rank == 0:
         peak, peak_src = peaks()
         ach = tr_bytes / (tr_ms * 1e-3) / 1e9 if tr_ms > 0 else 0.0
-        tr_roof = {"kernel": "tq::tr_elem_kernel (g=1 TR encode of every wrapped conv's input, 19 launches "
-                             "per forward; fp32 in, " + ("fp16 codes out: 6 B/elem" if args.conv_backend == "tcgen05"
+        tr_roof = {"kernel": "tq::tr_elem_kernel (g=1 TR encode; standalone launches only -- in the fused "
+                             "engine all but the first encode run inside the conv epilogue; fp32 in, " + ("fp16 codes out: 6 B/elem" if args.conv_backend != "cudnn_fp32"
                                                          else "fp32 out: 8 B/elem") + ")",
                    "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                    "traffic": None, "peak_source": peak_src, "launches_timed": n_tr,
@@ -243,8 +248,8 @@ def run_b200(args):
             except Exception:
                 tpeak, tsrc = 1400.0, "fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)"
             tach = cv_flops / (cv_ms * 1e-3) / 1e12
-            conv_roof = {"kernel": "tq::conv_igemm_f16_kernel (tcgen05 kind::f16 implicit GEMM on term codes, "
-                                   "19 launches per forward)",
+            conv_roof = {"kernel": "tq::conv_igemm_f16_kernel (tcgen05 kind::f16 implicit GEMM on term codes with "
+                                   "fused BN/residual/ReLU/encode epilogue, 19 launches per forward)",
                          "bound": "tensor", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s", "frac": tach / tpeak,
                          "traffic": None, "peak_source": tsrc, "launches_timed": n_cv,
                          "algorithmic_flops": cv_flops, "kernel_ms_total": cv_ms, "share_of_step": cv_ms / ms_total}
@@ -254,7 +259,7 @@ def run_b200(args):
             "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": ("int term codes (TR encode) held in f16, f32 accumulate (exact integers) on tcgen05"
-                                       if args.conv_backend == "tcgen05" else "f32 values (TR encode); f32 conv"),
+                                       if args.conv_backend != "cudnn_fp32" else "f32 values (TR encode); f32 conv"),
             "data": "synthetic (randn images, random-init torchvision resnet18, seed 0)",
             "config": {"workload": "ResNet-18 TQ inference, batch 256 per GPU at 3x224x224 "
                                    "(BASELINE.json configs[1])", **SETTING,
@@ -349,9 +354,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--conv-backend", default="tcgen05", choices=["tcgen05", "cudnn_fp32"],
-                    help="tcgen05: code-domain conv on tensor cores (csrc/tq_gemm.cu); "
-                         "cudnn_fp32: the reference's float path")
+    ap.add_argument("--conv-backend", default="fused", choices=["fused", "tcgen05", "cudnn_fp32"],
+                    help="fused: code-domain tcgen05 convs with BN/residual/ReLU/next-layer encode in the "
+                         "epilogue (fused.FusedResNet); tcgen05: same kernel layer by layer under the "
+                         "unchanged torchvision graph; cudnn_fp32: the reference's float path")
     ap.add_argument("--cpu-batch", type=int, default=16, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -1,0 +1,105 @@
+"""Fused execution of a TQ-converted ResNet (torchvision BasicBlock topology).
+
+The reference runs, per wrapped conv: TR encode -> cuDNN conv -> BatchNorm -> ReLU (-> add) as
+separate passes over fp32 activations (tr_layer.py:124-126 inside torchvision's BasicBlock).
+Here each conv is ONE launch of the tcgen05 kernel whose epilogue applies the BatchNorm affine,
+the residual add and the ReLU, and emits the fp16 term codes the *next* conv consumes
+(the accumulate -> ReLU/requantise -> encode -> truncate order of verilog/systolic_dla_top.v).
+fp32 activations are materialised only where the graph needs them (block outputs, which feed
+the next residual add).  The stem (first conv, never wrapped: cnn_models/__init__.py:34-36),
+max-pool, global average pool and the classifier stay on PyTorch.
+
+Numerics: integer accumulators are exact; the BatchNorm affine is evaluated as
+fma(t, a, b) with a = weight * rsqrt(var + eps), b = fma(-mean, a, bias), which is within 1-2 ulp
+of cuDNN's inference BatchNorm but not bit-identical (tools/bn_probe*.py), so a value sitting on
+a quantisation boundary can round differently than in the unfused path.
+"""
+import torch
+import torch.nn as nn
+
+from . import conv_codes, tr_cuda, tr_layer
+
+
+def _bn_affine(bn):
+    with torch.no_grad():
+        a = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+        b = torch.addcmul(bn.bias, -bn.running_mean, a)
+    return a.float().contiguous(), b.float().contiguous()
+
+
+def _quant_key(layer):
+    q = layer.input_quant
+    return (float(q.sf), int(q.data_bits), int(q.data_terms))
+
+
+class _Conv:
+    """Packed operands of one TRConv2dLayer + the BatchNorm that follows it."""
+
+    def __init__(self, layer, bn):
+        why = layer.tensor_core_blocker()
+        if why is not None:
+            raise NotImplementedError(f"fused path: {why}")
+        if layer.input_quant.tracking:
+            raise RuntimeError("calibrate the model (set_tr_tracking(model, False)) before fusing")
+        if layer._tc_weight is None:
+            layer.use_tensor_cores()
+        self.layer = layer
+        self.w = layer._tc_weight
+        self.quant = _quant_key(layer)
+        sfx32 = torch.tensor(self.quant[0], dtype=torch.float32)
+        self.scale = (sfx32 * torch.tensor(layer._tc_wsf32, dtype=torch.float32)).item()
+        self.bias = layer.conv.bias
+        self.bn = _bn_affine(bn) if bn is not None else None
+        c = layer.conv
+        self.ks, self.stride, self.pad = c.kernel_size, c.stride[0], c.padding[0]
+
+    def __call__(self, codes, residual=None, relu=False, want_f32=True, next_quant=None):
+        return conv_codes.conv2d_codes_fused(codes, self.w, self.ks, self.stride, self.pad, self.scale,
+                                             bias=self.bias, bn=self.bn, residual=residual, relu=relu,
+                                             want_f32=want_f32, next_quant=next_quant)
+
+
+class FusedResNet(nn.Module):
+    """Wraps a calibrated, TQ-converted torchvision ResNet built from BasicBlocks."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.model = model.to(memory_format=torch.channels_last).eval()
+        self.blocks = []
+        for stage in (model.layer1, model.layer2, model.layer3, model.layer4):
+            for blk in stage:
+                if not (isinstance(blk.conv1, tr_layer.TRConv2dLayer) and isinstance(blk.conv2, tr_layer.TRConv2dLayer)
+                        and hasattr(blk, "bn2") and not hasattr(blk, "conv3")):
+                    raise NotImplementedError("FusedResNet expects TQ-converted BasicBlocks")
+                down = None
+                if blk.downsample is not None:
+                    if not isinstance(blk.downsample[0], tr_layer.TRConv2dLayer):
+                        raise NotImplementedError("downsample conv must be a TRConv2dLayer")
+                    down = _Conv(blk.downsample[0], blk.downsample[1])
+                self.blocks.append((_Conv(blk.conv1, blk.bn1), _Conv(blk.conv2, blk.bn2), down))
+
+    @staticmethod
+    def _encode(x_nhwc, quant):
+        sf, bits, terms = quant
+        return tr_cuda.tr_codes(x_nhwc.view(1, -1, 1, 1), sf, bits, 1, terms,
+                                dtype=torch.float16).view(x_nhwc.shape)
+
+    @torch.no_grad()
+    def forward(self, x):
+        m = self.model
+        x = x.contiguous(memory_format=torch.channels_last)
+        x = m.maxpool(m.relu(m.bn1(m.conv1(x))))
+        cur = x.permute(0, 2, 3, 1)                      # fp32 [N, H, W, C], contiguous
+        codes = {}                                       # quantiser -> fp16 codes of `cur`
+        for i, (c1, c2, down) in enumerate(self.blocks):
+            def get(q):
+                if q not in codes:
+                    codes[q] = self._encode(cur, q)
+                return codes[q]
+            identity = cur if down is None else down(get(down.quant), want_f32=True)[0]
+            _, mid = c1(get(c1.quant), relu=True, want_f32=False, next_quant=c2.quant)
+            nxt = self.blocks[i + 1][0].quant if i + 1 < len(self.blocks) else None
+            cur, out_codes = c2(mid, residual=identity, relu=True, want_f32=True, next_quant=nxt)
+            codes = {nxt: out_codes} if nxt is not None else {}
+        y = cur.permute(0, 3, 1, 2)                      # NCHW shape, channels_last memory
+        return m.fc(torch.flatten(m.avgpool(y), 1))

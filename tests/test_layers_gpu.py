@@ -218,3 +218,40 @@ def test_tensor_core_conv_layer_matches_float_path():
         for h in hooks:
             h.remove()
     assert torch.allclose(got, want, rtol=1e-4, atol=1e-4 * float(want.abs().max()))
+
+
+def test_fused_resnet_matches_unfused_tensor_core_path():
+    """FusedResNet (BN / residual / ReLU / next-layer encode in the conv epilogue) against the
+    same model run layer by layer (use_tensor_cores) and against the float reference path."""
+    from torchvision.models import resnet18
+    from term_quantization_b200 import cnn_models, fused, inference, tr_layer
+    torch.manual_seed(0)
+    base = resnet18(weights=None).cuda().eval()
+    with torch.no_grad():
+        for mod in base.modules():
+            if isinstance(mod, nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.2)
+                mod.running_var.uniform_(0.5, 1.5)
+                mod.weight.uniform_(0.5, 1.5)
+                mod.bias.normal_(0, 0.2)
+    q = cnn_models.convert_model(base, cnn_models.static_conv_layer_settings(base, 9, 8, 12), 9, 3)
+    x = torch.randn(8, 3, 224, 224, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    inference.calibrate(q, [x])
+    with torch.no_grad():
+        ref = q(x)                                              # float path (fp32 cuDNN conv)
+        q = q.to(memory_format=torch.channels_last)
+        switched, skipped = tr_layer.use_tensor_cores(q)
+        assert len(switched) == 19 and not skipped
+        unfused = q(x.contiguous(memory_format=torch.channels_last))
+        f = fused.FusedResNet(q)
+        got = f(x)
+    scale = float(ref.abs().max())
+    d_unfused = float((unfused - ref).abs().max()) / scale
+    d_fused = float((got - unfused).abs().max()) / scale
+    print(f"rel diff: tensor-core vs float path {d_unfused:.3e}; fused vs unfused {d_fused:.3e}")
+    # The float path is cuDNN fp32 (Winograd / FFT algorithms under cudnn.benchmark): its own
+    # rounding noise, amplified by 19 re-quantisations, is what separates it from the exact
+    # integer path (tools/numerics_probe.py measures both against an fp64 run).
+    assert d_unfused < 2e-2
+    assert d_fused < 1e-3
+    assert torch.equal(got.argmax(1), ref.argmax(1))
