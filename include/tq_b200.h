@@ -170,6 +170,16 @@ int tq_conv2d_codes_fused(const void *act, const void *wgt, float *out_f32, void
                           void *stream);
 
 /*
+ * Fused tail of the unquantised stem (torchvision ResNet: bn1 -> relu -> maxpool(3, 2, 1), then
+ * the first wrapped conv's LinearQuantize, tr_layer.py:96-99): x fp32 NHWC [N,H,W,C] ->
+ * out fp32 NHWC [N,Ho,Wo,C] = maxpool3x3s2p1(relu(fma(x, bn_a, bn_b))) and, if out_codes != NULL,
+ * the fp16 term codes of `out` under (next_sf, next_bits <= 12, next_terms).  C % 4 == 0.
+ */
+int tq_bn_relu_maxpool_encode(const float *x, const float *bn_a, const float *bn_b, float *out,
+                              void *out_codes, int N, int H, int W, int C, int relu,
+                              float next_sf, int next_bits, int next_terms, void *stream);
+
+/*
  * Device self-test: quantises n pseudo-random (a, sf) pairs (sf in [2^-30, 2^30], a over all
  * non-negative floats and the quantiser's rounding boundaries) with the hoisted-reciprocal
  * divide and with div.rn.f32 and adds the number of disagreements to *mismatch (device).

@@ -70,3 +70,22 @@ def conv2d_codes_fused(act, wgt, kernel_size, stride, pad, scale, *, bias=None, 
             int(terms), torch.cuda.current_stream(act.device).cuda_stream)
     _lib.check(rc)
     return out, codes
+
+
+def bn_relu_maxpool_encode(x_nhwc, bn, relu=True, next_quant=None):
+    """maxpool3x3/s2/p1(relu(fma(x, a, b))) on an fp32 [N, H, W, C] tensor, plus the fp16 term
+    codes of the result for the first wrapped conv.  Returns (out [N, Ho, Wo, C], codes or None)."""
+    if x_nhwc.dtype != torch.float32 or not x_nhwc.is_contiguous() or not x_nhwc.is_cuda:
+        raise RuntimeError("bn_relu_maxpool_encode expects a contiguous fp32 CUDA [N, H, W, C] tensor")
+    N, H, W, C = x_nhwc.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty((N, Ho, Wo, C), dtype=torch.float32, device=x_nhwc.device)
+    codes = torch.empty((N, Ho, Wo, C), dtype=torch.float16, device=x_nhwc.device) if next_quant else None
+    sf, bits, terms = next_quant if next_quant else (1.0, 1, 0)
+    with torch.cuda.device(x_nhwc.device):
+        rc = _lib.lib().tq_bn_relu_maxpool_encode(
+            x_nhwc.data_ptr(), bn[0].data_ptr(), bn[1].data_ptr(), out.data_ptr(),
+            codes.data_ptr() if codes is not None else None, N, H, W, C, int(bool(relu)),
+            float(sf), int(bits), int(terms), torch.cuda.current_stream(x_nhwc.device).cuda_stream)
+    _lib.check(rc)
+    return out, codes

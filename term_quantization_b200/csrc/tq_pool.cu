@@ -1,0 +1,108 @@
+// tq_pool.cu -- fused tail of the (unquantised) stem of the CNNs in cnn_models/:
+//   BatchNorm (per-channel affine) -> ReLU -> MaxPool 3x3 / stride 2 / pad 1 -> fp32 NHWC output
+//   + fp16 term codes of that output for the first wrapped conv (tr_layer.py:96-99 fused in).
+// torchvision's ResNet runs these as three passes over the largest activation of the network
+// (N x 64 x 112 x 112 fp32 = 822 MB at batch 256) plus a TR-encode pass over the pooled tensor; here
+// the conv output is read once and the pooled tensor / its codes are written once.
+// Memory-bound: algorithmic bytes = 4*N*H*W*C (read) + 4*N*Ho*Wo*C (write) + 2*N*Ho*Wo*C (codes).
+#include "tq_common.cuh"
+
+namespace tq {
+
+struct PoolParams {
+    int N, H, W, C, Ho, Wo;
+    int relu;
+    float next_sf;
+    int next_bits, next_terms, next_fastdiv, write_codes;
+};
+
+__global__ void __launch_bounds__(256)
+bn_relu_maxpool3x3s2_kernel(const float *__restrict__ x, const float *__restrict__ bn_a,
+                            const float *__restrict__ bn_b, float *__restrict__ out,
+                            __half *__restrict__ codes, PoolParams p)
+{
+    extern __shared__ __half lut[];
+    if (p.write_codes) {
+        for (uint32_t i = threadIdx.x; i < (2u << p.next_bits); i += blockDim.x) {
+            const int code = elem_code(i & ((1u << p.next_bits) - 1u), TQ_ENC_HESE, p.next_terms);
+            lut[i] = __int2half_rn((i >> p.next_bits) ? -code : code);
+        }
+        __syncthreads();
+    }
+    const Quant nq = make_quant(p.write_codes ? p.next_sf : 1.0f, (float)((1u << p.next_bits) - 1u));
+    const int c4n = p.C >> 2;
+    const int64_t total = (int64_t)p.N * p.Ho * p.Wo * c4n;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(t % c4n);
+        const int64_t pix = t / c4n;
+        const int wo = (int)(pix % p.Wo), ho = (int)((pix / p.Wo) % p.Ho), n = (int)(pix / ((int64_t)p.Wo * p.Ho));
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(bn_a) + c4);
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(bn_b) + c4);
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int h = ho * 2 - 1 + dy;
+            if (h < 0 || h >= p.H) continue;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const int w = wo * 2 - 1 + dx;
+                if (w < 0 || w >= p.W) continue;
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(x + (((int64_t)n * p.H + h) * p.W + w) * p.C) + c4);
+                m.x = fmaxf(m.x, __fmaf_rn(v.x, a.x, b.x));
+                m.y = fmaxf(m.y, __fmaf_rn(v.y, a.y, b.y));
+                m.z = fmaxf(m.z, __fmaf_rn(v.z, a.z, b.z));
+                m.w = fmaxf(m.w, __fmaf_rn(v.w, a.w, b.w));
+            }
+        }
+        if (p.relu) { m.x = fmaxf(m.x, 0.f); m.y = fmaxf(m.y, 0.f); m.z = fmaxf(m.z, 0.f); m.w = fmaxf(m.w, 0.f); }
+        reinterpret_cast<float4 *>(out)[t] = m;
+        if (p.write_codes) {
+            const float vv[4] = {m.x, m.y, m.z, m.w};
+            uint32_t hc[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t neg = __float_as_uint(vv[e]) >> 31;
+                const uint32_t q = p.next_fastdiv ? quantize_f32<true>(vv[e], nq) : quantize_f32<false>(vv[e], nq);
+                hc[e] = __half_as_ushort(lut[q | (neg << p.next_bits)]);
+            }
+            reinterpret_cast<uint2 *>(codes)[t] = make_uint2(hc[0] | (hc[1] << 16), hc[2] | (hc[3] << 16));
+        }
+    }
+}
+
+}  // namespace tq
+
+using namespace tq;
+
+extern "C" int tq_bn_relu_maxpool_encode(const float *x, const float *bn_a, const float *bn_b, float *out,
+                                         void *out_codes, int N, int H, int W, int C, int relu,
+                                         float next_sf, int next_bits, int next_terms, void *stream)
+{
+    if (!x || !bn_a || !bn_b || !out) return fail(TQ_ERR_INVALID, "NULL pointer");
+    if (N < 1 || H < 1 || W < 1 || C < 4 || C % 4) return fail(TQ_ERR_INVALID, "bad shape (C must be a multiple of 4)");
+    if ((((uintptr_t)x | (uintptr_t)bn_a | (uintptr_t)bn_b | (uintptr_t)out | (uintptr_t)out_codes) & 15u) != 0)
+        return fail(TQ_ERR_INVALID, "pointers must be 16-byte aligned");
+    PoolParams p{};
+    p.N = N; p.H = H; p.W = W; p.C = C;
+    p.Ho = (H + 2 - 3) / 2 + 1;
+    p.Wo = (W + 2 - 3) / 2 + 1;
+    p.relu = relu ? 1 : 0;
+    p.write_codes = out_codes ? 1 : 0;
+    p.next_sf = out_codes ? next_sf : 1.0f;
+    p.next_bits = out_codes ? next_bits : 1;
+    p.next_terms = next_terms;
+    if (out_codes) {
+        if (!(next_sf > 0.0f) || !(next_sf < INFINITY)) return fail(TQ_ERR_INVALID, "next_sf must be positive and finite");
+        if (next_bits < 1 || next_bits > 12 || next_terms < 0) return fail(TQ_ERR_UNSUPPORTED, "fused encode supports 1..12 bits");
+    }
+    p.next_fastdiv = (p.next_sf >= 9.313225746154785e-10f && p.next_sf <= 1073741824.0f) ? 1 : 0;
+    const int64_t total = (int64_t)N * p.Ho * p.Wo * (C / 4);
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    const size_t smem = out_codes ? (size_t)(2u << p.next_bits) * sizeof(__half) : 0;
+    bn_relu_maxpool3x3s2_kernel<<<(int)blocks, 256, smem, (cudaStream_t)stream>>>(
+        x, bn_a, bn_b, out, (__half *)out_codes, p);
+    count_launch();
+    return check_launch("bn_relu_maxpool3x3s2_kernel");
+}

@@ -77,6 +77,11 @@ class FusedResNet(nn.Module):
                         raise NotImplementedError("downsample conv must be a TRConv2dLayer")
                     down = _Conv(blk.downsample[0], blk.downsample[1])
                 self.blocks.append((_Conv(blk.conv1, blk.bn1), _Conv(blk.conv2, blk.bn2), down))
+        mp = model.maxpool
+        self.fuse_stem = (isinstance(mp, nn.MaxPool2d) and mp.kernel_size in (3, (3, 3)) and mp.stride in (2, (2, 2))
+                          and mp.padding in (1, (1, 1)) and mp.dilation in (1, (1, 1)) and not mp.ceil_mode
+                          and model.conv1.out_channels % 4 == 0 and self.blocks[0][0].quant[1] <= 12)
+        self.stem_bn = _bn_affine(model.bn1)
 
     @staticmethod
     def _encode(x_nhwc, quant):
@@ -88,9 +93,16 @@ class FusedResNet(nn.Module):
     def forward(self, x):
         m = self.model
         x = x.contiguous(memory_format=torch.channels_last)
-        x = m.maxpool(m.relu(m.bn1(m.conv1(x))))
-        cur = x.permute(0, 2, 3, 1)                      # fp32 [N, H, W, C], contiguous
-        codes = {}                                       # quantiser -> fp16 codes of `cur`
+        if self.fuse_stem:
+            # stem conv on cuDNN (never wrapped), then bn1 + relu + maxpool + first encode in one pass
+            q0 = self.blocks[0][0].quant
+            cur, c0 = conv_codes.bn_relu_maxpool_encode(m.conv1(x).permute(0, 2, 3, 1), self.stem_bn,
+                                                        relu=True, next_quant=q0)
+            codes = {q0: c0}                             # quantiser -> fp16 codes of `cur`
+        else:
+            x = m.maxpool(m.relu(m.bn1(m.conv1(x))))
+            cur = x.permute(0, 2, 3, 1)                  # fp32 [N, H, W, C], contiguous
+            codes = {}
         for i, (c1, c2, down) in enumerate(self.blocks):
             def get(q):
                 if q not in codes:

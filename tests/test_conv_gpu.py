@@ -87,3 +87,23 @@ def test_conv_fused_epilogue(case):
     assert none is None
     _, want = O.tr(t1.cpu().numpy().reshape(1, -1, 1, 1), float(t1.abs().max()) / 256, 8, 1, 2, return_codes=True)
     assert np.array_equal(codes.cpu().numpy().astype(np.int32).reshape(-1), want.reshape(-1))
+
+
+def test_bn_relu_maxpool_encode():
+    from oracle import tq_oracle as O
+    from term_quantization_b200 import conv_codes
+    g = torch.Generator(device="cuda").manual_seed(11)
+    for (N, H, W, C) in ((2, 112, 112, 64), (3, 17, 9, 8), (1, 7, 7, 20)):
+        x = torch.randn(N, H, W, C, device="cuda", generator=g) * 2
+        a = torch.randn(C, device="cuda", generator=g)            # negative slopes included
+        b = torch.randn(C, device="cuda", generator=g)
+        y = (x.double() * a.double() + b.double()).float()        # fma, one rounding
+        want = F.max_pool2d(torch.relu(y).permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous()
+        nq = (float(want.max()) / 512, 9, 3)
+        out, codes = conv_codes.bn_relu_maxpool_encode(x, (a, b), relu=True, next_quant=nq)
+        assert torch.equal(out, want)
+        _, wc = O.tr(want.cpu().numpy().reshape(1, -1, 1, 1), nq[0], nq[1], 1, nq[2], return_codes=True)
+        assert np.array_equal(codes.cpu().numpy().astype(np.int32).reshape(-1), wc.reshape(-1))
+        out2, none = conv_codes.bn_relu_maxpool_encode(x, (a, b), relu=False)
+        assert none is None
+        assert torch.equal(out2, F.max_pool2d(y.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1))
