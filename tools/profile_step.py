@@ -16,10 +16,13 @@ backend = sys.argv[1] if len(sys.argv) > 1 else "tcgen05"
 model = bench.build_tq_resnet18(dev)
 x = torch.randn(256, 3, 224, 224, device=dev)
 inference.calibrate(model, [x[:64]])
-if backend == "tcgen05":
+if backend in ("tcgen05", "fused"):
     model = model.to(memory_format=torch.channels_last)
     x = x.contiguous(memory_format=torch.channels_last)
     tr_layer.use_tensor_cores(model)
+    if backend == "fused":
+        from term_quantization_b200 import fused
+        model = fused.FusedResNet(model)
 with torch.no_grad():
     for _ in range(3):
         model(x)
