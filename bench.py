@@ -139,6 +139,36 @@ class KernelTimer:
         return len(rec), sum(w for _, _, w in rec), sum(a.elapsed_time(b) for a, b, _ in rec)
 
 
+def tr_encode_roofline(dev, peak, peak_src, iters=20):
+    """BASELINE metric 1: TR-encode GB/s at the largest ResNet-18 activation (256x64x56x56 fp32,
+    g=1, 9-bit, 3 terms, drop-in fp32 -> fp32 contract: 8 B/element).  Two 205 MB inputs rotate
+    (> 126 MB L2); every launch is timed with CUDA events on its stream."""
+    from term_quantization_b200 import tr_cuda
+    n = 256 * 64 * 56 * 56
+    g = torch.Generator(device=dev).manual_seed(7)
+    xs = [torch.relu(torch.randn(1, n, 1, 1, device=dev, generator=g)) for _ in range(2)]
+    out = torch.empty_like(xs[0])
+    sf = float(xs[0].max()) / 512
+    for i in range(3):
+        tr_cuda.tr(xs[i % 2], sf, 9, 1, 3, out=out)
+    torch.cuda.synchronize()
+    evs = []
+    for i in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        tr_cuda.tr(xs[i % 2], sf, 9, 1, 3, out=out)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs) / iters
+    ach = n * 8 / (ms * 1e-3) / 1e9
+    return {"kernel": "tq::tr_elem_kernel<float,float> on 51,380,224 elements (ResNet-18 layer1 activation at "
+                      "batch 256), g=1, 9-bit, 3 terms", "bound": "hbm", "achieved": ach, "peak": peak,
+            "unit": "GB/s", "frac": ach / peak, "frac_of_nominal_8000": ach / 8000.0, "traffic": None,
+            "peak_source": peak_src, "launches_timed": iters, "algorithmic_bytes_per_launch": n * 8,
+            "ms_per_launch": ms}
+
+
 def run_b200(args):
     from term_quantization_b200 import _lib, inference
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -276,6 +306,7 @@ def run_b200(args):
             "clocks": clocks,
             "roofline": dominant,
             "roofline_other": other,
+            "tr_encode": tr_encode_roofline(dev, peak, peak_src),
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_images_per_sec(sample_batch=args.cpu_batch, steps=1)
