@@ -180,6 +180,19 @@ int tq_bn_relu_maxpool_encode(const float *x, const float *bn_a, const float *bn
                               float next_sf, int next_bits, int next_terms, void *stream);
 
 /*
+ * The unquantised stem conv of the CNNs (7x7, stride 2, pad 3, 3 input channels, no bias;
+ * torchvision resnet `conv1`, left in fp32 by the reference: cnn_models/__init__.py:34-36) on the
+ * tensor-core kernel with fp32-level accuracy (hi/lo fp16 operand pairs, fp32 accumulation).
+ *   x          fp32 NHWC [N, H, W, 3] (H, W even)
+ *   x2_scratch 2 * N * (H/2+3) * (W/2+3) * 16 fp16 of scratch (folded hi / lo image planes)
+ *   w2         fp16 [8][Cout][64]: rows R = 0..3 of the 8x8-padded kernel folded 2x2, as
+ *              (hi, lo) planes (conv_codes.pack_stem_weight builds it); Cout <= 64
+ *   out        fp32 NHWC [N, H/2, W/2, Cout]
+ */
+int tq_stem_conv7x7s2(const float *x, void *x2_scratch, const void *w2, float *out,
+                      int N, int H, int W, int Cout, void *stream);
+
+/*
  * Device self-test: quantises n pseudo-random (a, sf) pairs (sf in [2^-30, 2^30], a over all
  * non-negative floats and the quantiser's rounding boundaries) with the hoisted-reciprocal
  * divide and with div.rn.f32 and adds the number of disagreements to *mismatch (device).

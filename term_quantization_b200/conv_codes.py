@@ -89,3 +89,36 @@ def bn_relu_maxpool_encode(x_nhwc, bn, relu=True, next_quant=None):
             float(sf), int(bits), int(terms), torch.cuda.current_stream(x_nhwc.device).cuda_stream)
     _lib.check(rc)
     return out, codes
+
+
+def pack_stem_weight(w):
+    """(Cout, 3, 7, 7) fp32 -> fp16 [8][Cout][64] for tq_stem_conv7x7s2: the kernel padded to 8x8 and
+    folded 2x2 (r = 2R + dr, s = 2S + ds), row R holding (S, dr, ds, c) with c padded to 4, as the
+    two operand planes (w_hi, w_lo) with w = w_hi + w_lo in fp16 pairs."""
+    Cout, Cin, kh, kw = w.shape
+    if (Cin, kh, kw) != (3, 7, 7):
+        raise NotImplementedError("stem conv packing expects a (Cout, 3, 7, 7) weight")
+    w8 = torch.zeros(Cout, 4, 8, 8, dtype=torch.float32, device=w.device)
+    w8[:, :3, :7, :7] = w.detach().float()
+    # [co, c, R, dr, S, ds] -> [R, co, S, dr, ds, c]
+    w2 = w8.view(Cout, 4, 4, 2, 4, 2).permute(2, 0, 4, 3, 5, 1).reshape(4, Cout, 64)
+    hi = w2.half()
+    lo = (w2 - hi.float()).half()
+    return torch.cat([hi, lo], dim=0).contiguous()
+
+
+def stem_conv7x7s2(x_nhwc, w2, scratch=None):
+    """fp32 [N, H, W, 3] -> fp32 [N, H/2, W/2, Cout] (7x7 / stride 2 / pad 3, no bias)."""
+    if x_nhwc.dtype != torch.float32 or not x_nhwc.is_contiguous() or x_nhwc.shape[-1] != 3:
+        raise RuntimeError("stem_conv7x7s2 expects a contiguous fp32 [N, H, W, 3] tensor")
+    N, H, W, _ = x_nhwc.shape
+    Cout = w2.shape[1]
+    need = 2 * N * (H // 2 + 3) * (W // 2 + 3) * 16
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty(need, dtype=torch.float16, device=x_nhwc.device)
+    out = torch.empty((N, H // 2, W // 2, Cout), dtype=torch.float32, device=x_nhwc.device)
+    with torch.cuda.device(x_nhwc.device):
+        rc = _lib.lib().tq_stem_conv7x7s2(x_nhwc.data_ptr(), scratch.data_ptr(), w2.data_ptr(), out.data_ptr(),
+                                          N, H, W, Cout, torch.cuda.current_stream(x_nhwc.device).cuda_stream)
+    _lib.check(rc)
+    return out, scratch

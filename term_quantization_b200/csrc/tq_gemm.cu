@@ -22,6 +22,7 @@
 // accumulator stage (TMEM -> registers -> fused tail -> swizzled smem -> TMA store).
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "tq_common.cuh"
@@ -40,6 +41,18 @@ struct ConvGeom {
     int m_tiles, n_tiles, kc_blocks;
     int a_tx_bytes;                             // bytes one A box deposits
     float scale;
+    // shared-memory carve-up (runtime, 1024-byte aligned regions)
+    int stages, stage_bytes, ring_off, bstat_off, epi_off, lut_off, bar_off, smem_total;
+    // "program" mode for small layers (Cout <= BLOCK_N, all weights resident in shared memory): the K loop is
+    // a table of A loads, each followed by 1-2 MMAs against stationary B tiles into an accumulator group
+    int prog_steps, nb_tiles, n_groups;
+    int dbg_skip_epilogue;      // profiling aid (TQ_CONV_SKIP_EPI=1): drain accumulators without storing
+    struct KStep {
+        int8_t dw, dh;          // offset of the A box relative to the tile origin (filter tap)
+        int8_t kc;              // 64-channel block
+        int8_t plane;           // A plane (stacked along N): coordinate n0 + plane * N
+        uint8_t n_mma, b_tile[2], group[2];
+    } prog[16];
     // fused epilogue (all optional):  t = acc*scale (+bias) ; t = fma(t, bn_a, bn_b) ; t += residual ;
     // t = max(t, 0) ; fp32 tile out (TMA store) ; fp16 term codes of t for the next layer (TMA store)
     const float *bias, *bn_a, *bn_b, *residual;
@@ -86,6 +99,18 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *ba
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// one lane of a converged warp (the rest of the warp stays converged around the asm that follows)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -140,38 +165,36 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr)
 }
 
 constexpr int GM_LUT_MAX_BITS = 10;             // fused next-layer encode: 2^(bits+1) fp16 entries in smem
+constexpr int GM_MAX_STAGES = 8;
+constexpr int GM_EPI_BYTES = 16384 + 8192;      // per epilogue group: [128][32] fp32 + [128][32] fp16 staging
+constexpr int GM_SMEM_BUDGET = 227 * 1024;
 
-template <int BLOCK_N, int STAGES>
-struct GemmSmem {
-    static constexpr int B_BYTES = BLOCK_N * GM_BLOCK_K * 2;
-    static constexpr int STAGE_BYTES = GM_A_BYTES + B_BYTES;
-    // per epilogue group: [128 rows][128 B] fp32 (32 columns) + [128 rows][64 B] fp16 codes
-    static constexpr int EPI_BYTES = 16384 + 8192;
-    static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int LUT_OFFSET = EPI_OFFSET + 2 * EPI_BYTES;
-    static constexpr int BAR_OFFSET = LUT_OFFSET + (2 << GM_LUT_MAX_BITS) * 2;
-    static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;   // + alignment slack
-};
-
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD,
-                      const ConvGeom g)
+                      const __grid_constant__ ConvGeom g)
 {
-    using L = GemmSmem<BLOCK_N, STAGES>;
+    constexpr int B_BYTES = BLOCK_N * GM_BLOCK_K * 2;
+    const int STAGES = g.stages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::BAR_OFFSET);
-    uint64_t *empty_bar = full_bar + STAGES;
-    uint64_t *tfull_bar = empty_bar + STAGES;       // [2] accumulator ready
-    uint64_t *tempty_bar = tfull_bar + 2;           // [2] accumulator drained
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+    uint8_t *ring = smem + g.ring_off;              // STAGES x (A tile [+ B tile when streaming])
+    uint8_t *bstat = smem + g.bstat_off;            // stationary B tiles (program mode)
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + g.bar_off);
+    uint64_t *empty_bar = full_bar + GM_MAX_STAGES;
+    uint64_t *tfull_bar = empty_bar + GM_MAX_STAGES;    // [2] accumulator ready
+    uint64_t *tempty_bar = tfull_bar + 2;               // [2] accumulator drained
+    uint64_t *bfull_bar = tempty_bar + 2;               // stationary weights landed
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bfull_bar + 1);
+    const bool prog = g.prog_steps > 0;
+    const int acc_cols = g.n_groups * BLOCK_N;          // TMEM columns of one accumulator stage
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = g.m_tiles * g.n_tiles;
     const int kblocks = g.R * g.S * g.kc_blocks;
-    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;     // power of two >= 32 for BLOCK_N in {64, 128}
+    uint32_t TMEM_COLS = 32;                            // power of two >= 2 accumulator stages
+    while (TMEM_COLS < (uint32_t)(2 * acc_cols)) TMEM_COLS <<= 1;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -179,7 +202,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (g.write_f32) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
         if (g.write_codes) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
     }
-    __half *lut = reinterpret_cast<__half *>(smem + L::LUT_OFFSET);
+    __half *lut = reinterpret_cast<__half *>(smem + g.lut_off);
     if (g.write_codes) {
         // (q, sign) -> fp16 term code of the consumer's quantiser, as in tr_elem_kernel
         for (uint32_t i = threadIdx.x; i < (2u << g.next_bits); i += GM_THREADS) {
@@ -189,6 +212,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(bfull_bar, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }   // 128 = one epilogue group
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -201,50 +225,112 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
         // ================= TMA producer =================
+        // converged warp, one elected lane issues (same reason as the MMA warp below)
         int stage = 0;
         uint32_t phase = 0;
+        if (prog) {                                     // all weights once: they stay resident
+            if (elect_one()) {
+                mbar_expect_tx(bfull_bar, (uint32_t)(g.nb_tiles * B_BYTES));
+                for (int t = 0; t < g.nb_tiles; ++t) tma_load_3d(&tmB, bfull_bar, bstat + t * B_BYTES, 0, 0, t);
+            }
+            __syncwarp();
+        }
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int n_tile = tile % g.n_tiles, m_tile = tile / g.n_tiles;
             const int tw = m_tile % g.tiles_w, th = (m_tile / g.tiles_w) % g.tiles_h, tn = m_tile / (g.tiles_w * g.tiles_h);
             const int w_in0 = tw * g.wbox * g.stride - g.pad, h_in0 = th * g.hbox * g.stride - g.pad, n0 = tn * g.nbox;
+            if (prog) {
+                for (int st = 0; st < g.prog_steps; ++st) {
+                    const int cw = w_in0 + g.prog[st].dw, ch = h_in0 + g.prog[st].dh;
+                    const int cc = g.prog[st].kc * GM_BLOCK_K, cn = n0 + g.prog[st].plane * g.N;
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    if (elect_one()) {
+                        mbar_expect_tx(&full_bar[stage], (uint32_t)g.a_tx_bytes);
+                        tma_load_4d(&tmA, &full_bar[stage], ring + stage * g.stage_bytes, cc, cw, ch, cn);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                continue;
+            }
             for (int tap = 0; tap < g.R * g.S; ++tap) {
                 const int r = tap / g.S, s = tap % g.S;
                 for (int kc = 0; kc < g.kc_blocks; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    uint8_t *sa = smem + stage * L::STAGE_BYTES;
-                    mbar_expect_tx(&full_bar[stage], (uint32_t)(g.a_tx_bytes + L::B_BYTES));
-                    tma_load_4d(&tmA, &full_bar[stage], sa, kc * GM_BLOCK_K, w_in0 + s, h_in0 + r, n0);
-                    tma_load_3d(&tmB, &full_bar[stage], sa + GM_A_BYTES, kc * GM_BLOCK_K, n_tile * BLOCK_N, tap);
+                    if (elect_one()) {
+                        uint8_t *sa = ring + stage * g.stage_bytes;
+                        mbar_expect_tx(&full_bar[stage], (uint32_t)(g.a_tx_bytes + B_BYTES));
+                        tma_load_4d(&tmA, &full_bar[stage], sa, kc * GM_BLOCK_K, w_in0 + s, h_in0 + r, n0);
+                        tma_load_3d(&tmB, &full_bar[stage], sa + GM_A_BYTES, kc * GM_BLOCK_K, n_tile * BLOCK_N, tap);
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ================= MMA issuer (one thread) =================
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        // The whole warp walks the loop converged (descriptors stay in uniform registers, no per-operand
+        // broadcasts); one elected lane issues tcgen05.mma / tcgen05.commit.
         // instruction descriptor: D = F32, A = B = F16, both K-major, N = BLOCK_N, M = 128
         constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(GM_BLOCK_M >> 4) << 24);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
+        const uint32_t ring_addr = smem_u32(ring), bstat_addr = smem_u32(bstat);
+        if (prog) {
+            mbar_wait(bfull_bar, 0);
+            tc_fence_after();
+        }
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
             tc_fence_after();
-            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
-            for (int kb = 0; kb < kblocks; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-                const uint64_t da = smem_desc_sw128(sa), db = smem_desc_sw128(sa + GM_A_BYTES);
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
+            if (prog) {
+                uint32_t started = 0;                           // accumulator groups already written in this tile
+                for (int st = 0; st < g.prog_steps; ++st) {
+                    const int n_mma = g.prog[st].n_mma;
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = smem_desc_sw128(ring_addr + (uint32_t)(stage * g.stage_bytes));
+                    for (int m = 0; m < n_mma; ++m) {
+                        const uint64_t db = smem_desc_sw128(bstat_addr + (uint32_t)(g.prog[st].b_tile[m] * B_BYTES));
+                        const uint32_t grp = g.prog[st].group[m];
+                        const uint32_t first = ((started >> grp) & 1u) ^ 1u;
+                        if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < GM_BLOCK_K / 16; ++k)      // UMMA_K = 16 fp16 = 32 bytes = +2 in the address field
-                    umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
-                umma_commit(&empty_bar[stage]);                 // frees the smem stage when the MMAs retire
-                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                            for (int k = 0; k < GM_BLOCK_K / 16; ++k)
+                                umma_f16(tmem_d + grp * BLOCK_N, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC,
+                                         (k != 0 || !first) ? 1u : 0u);
+                        }
+                        __syncwarp();
+                        started |= 1u << grp;
+                    }
+                    if (elect_one()) umma_commit(&empty_bar[stage]);
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            } else {
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = ring_addr + (uint32_t)(stage * g.stage_bytes);
+                    const uint64_t da = smem_desc_sw128(sa), db = smem_desc_sw128(sa + GM_A_BYTES);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < GM_BLOCK_K / 16; ++k)   // UMMA_K = 16 fp16 = 32 bytes = +2 in the address field
+                            umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+                        umma_commit(&empty_bar[stage]);             // frees the smem stage when the MMAs retire
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
             }
-            umma_commit(&tfull_bar[acc]);                       // accumulator complete
+            if (elect_one()) umma_commit(&tfull_bar[acc]);      // accumulator complete
+            __syncwarp();
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     } else if (warp >= 4) {
@@ -255,7 +341,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int ew = (warp - 4) & 3;                          // TMEM lanes 32*ew .. 32*ew+31
         const int row = ew * 32 + lane;
         const bool store_thread = (ew == 0 && lane == 0);
-        uint8_t *st_f32 = smem + L::EPI_OFFSET + grp * L::EPI_BYTES;    // [128][32] fp32, 128B swizzle
+        uint8_t *st_f32 = smem + g.epi_off + grp * GM_EPI_BYTES;        // [128][32] fp32, 128B swizzle
         uint8_t *st_codes = st_f32 + 16384;                             // [128][32] fp16,  64B swizzle
         const uint32_t sw128 = (uint32_t)(row & 7);             // 16B piece index ^= row % 8
         const uint32_t sw64 = (uint32_t)((row >> 1) & 3);       // 16B piece index ^= (row / 2) % 4
@@ -273,6 +359,14 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const bool valid = nl < g.nbox && n < g.N && ho < g.Ho && wo < g.Wo;
             const int64_t pix = ((int64_t)n * g.Ho + ho) * g.Wo + wo;
 
+            if (g.dbg_skip_epilogue) {
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[acc]);
+                acc_phase ^= 1u;
+                continue;
+            }
 #pragma unroll 1
             for (int cc = 0; cc < BLOCK_N / 32; ++cc) {
                 const int c0 = n_tile * BLOCK_N + cc * 32;
@@ -291,7 +385,14 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     tc_fence_after();
                 }
                 uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BLOCK_N + cc * 32), v);
+                const uint32_t tcol = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * acc_cols + cc * 32);
+                tmem_ld_32x32b_x32(tcol, v);
+                for (int gi = 1; gi < g.n_groups; ++gi) {        // accumulator groups are summed here, in fp32 RN
+                    uint32_t u[32];
+                    tmem_ld_32x32b_x32(tcol + (uint32_t)(gi * BLOCK_N), u);
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__fadd_rn(__uint_as_float(v[e]), __uint_as_float(u[e])));
+                }
                 if (cc == BLOCK_N / 32 - 1) {                    // accumulator fully drained into registers
                     tc_fence_before();
                     mbar_arrive(&tempty_bar[acc]);
@@ -411,24 +512,50 @@ static void pick_box(ConvGeom &g)
     g.a_tx_bytes = g.wbox * g.hbox * g.nbox * GM_BLOCK_K * 2;
 }
 
-template <int BLOCK_N, int STAGES>
-static int launch_conv(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
-                       const CUtensorMap &tmD, const ConvGeom &g, cudaStream_t s)
+// carve shared memory: [stationary B][stage ring][2 x epilogue staging][LUT][barriers]
+static int plan_smem(ConvGeom &g, int block_n)
 {
-    using L = GemmSmem<BLOCK_N, STAGES>;
-    static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
-    auto kern = conv_igemm_f16_kernel<BLOCK_N, STAGES>;
+    const int b_bytes = block_n * GM_BLOCK_K * 2;
+    const bool prog = g.prog_steps > 0;
+    g.stage_bytes = GM_A_BYTES + (prog ? 0 : b_bytes);
+    g.bstat_off = 0;
+    g.ring_off = prog ? g.nb_tiles * b_bytes : 0;
+    const int fixed = g.ring_off + 2 * GM_EPI_BYTES + (2 << GM_LUT_MAX_BITS) * 2 + 1024 /* barriers */ + 1024 /* align */;
+    int stages = (GM_SMEM_BUDGET - fixed) / g.stage_bytes;
+    if (stages > GM_MAX_STAGES) stages = GM_MAX_STAGES;
+    static const int cap = getenv("TQ_CONV_STAGES") ? atoi(getenv("TQ_CONV_STAGES")) : GM_MAX_STAGES;
+    if (stages > cap && cap >= 2) stages = cap;
+    if (stages < 2) return fail(TQ_ERR_UNSUPPORTED, "shared memory budget: %d resident weight tiles do not fit", g.nb_tiles);
+    g.stages = stages;
+    g.epi_off = g.ring_off + stages * g.stage_bytes;
+    g.lut_off = g.epi_off + 2 * GM_EPI_BYTES;
+    g.bar_off = g.lut_off + (2 << GM_LUT_MAX_BITS) * 2;
+    g.smem_total = g.bar_off + 1024 + 1024;
+    return TQ_OK;
+}
+
+template <int BLOCK_N>
+static int launch_conv(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
+                       const CUtensorMap &tmD, ConvGeom &g, cudaStream_t s)
+{
+    if (g.n_groups < 1) g.n_groups = 1;
+    static const bool skip_epi = getenv("TQ_CONV_SKIP_EPI") != nullptr;
+    g.dbg_skip_epilogue = skip_epi ? 1 : 0;
+    if (2 * g.n_groups * BLOCK_N > 512) return fail(TQ_ERR_UNSUPPORTED, "accumulator groups exceed tensor memory");
+    int rc = plan_smem(g, BLOCK_N);
+    if (rc != TQ_OK) return rc;
+    auto kern = conv_igemm_f16_kernel<BLOCK_N>;
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess)
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_BUDGET) != cudaSuccess)
             return check_launch("cudaFuncSetAttribute(conv_igemm_f16_kernel)");
         attr_set[dev] = true;
     }
     const int total = g.m_tiles * g.n_tiles;
     const int grid = total < num_sms() ? total : num_sms();
-    kern<<<grid, GM_THREADS, L::TOTAL, s>>>(tmA, tmB, tmC, tmD, g);
+    kern<<<grid, GM_THREADS, g.smem_total, s>>>(tmA, tmB, tmC, tmD, g);
     count_launch();
     return check_launch("conv_igemm_f16_kernel");
 }
@@ -493,6 +620,20 @@ extern "C" int tq_conv2d_codes_fused(const void *act, const void *wgt, float *ou
     g.next_bits = out_codes ? next_bits : 1;
     g.next_terms = next_terms;
     g.next_fastdiv = (g.next_sf >= 9.313225746154785e-10f && g.next_sf <= 1073741824.0f) ? 1 : 0;
+    g.n_groups = 1;
+    // small layers: every weight tile stays resident in shared memory and the K loop is a table of A loads
+    const int taps = R * S * g.kc_blocks;
+    static const bool no_prog = getenv("TQ_CONV_NO_PROG") != nullptr;
+    if (!no_prog && Cout <= 64 && taps <= 12) {
+        g.prog_steps = taps;
+        g.nb_tiles = taps;
+        for (int t = 0; t < taps; ++t) {
+            const int tap = t / g.kc_blocks, kc = t % g.kc_blocks;
+            ConvGeom::KStep &k = g.prog[t];
+            k.dw = (int8_t)(tap % S); k.dh = (int8_t)(tap / S); k.kc = (int8_t)kc; k.plane = 0;
+            k.n_mma = 1; k.b_tile[0] = (uint8_t)t; k.group[0] = 0;
+        }
+    }
 
     CUtensorMap tmA, tmB, tmC, tmD;
     int rc;
@@ -502,7 +643,15 @@ extern "C" int tq_conv2d_codes_fused(const void *act, const void *wgt, float *ou
         cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
         if ((rc = encode_map(enc, &tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, act, 4, dims, box, estr, "activations")) != TQ_OK) return rc;
     }
-    {   // weights: (C, Cout, R*S) fp16
+    if (g.prog_steps > 0 && g.kc_blocks == 1) {
+        // resident weights are fetched as tile t = tap: (C, Cout, R*S) with one 64-channel block per tap
+        cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Cout, (cuuint64_t)(R * S)};
+        cuuint32_t box[3] = {(cuuint32_t)GM_BLOCK_K, (cuuint32_t)block_n, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        if ((rc = encode_map(enc, &tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wgt, 3, dims, box, estr, "weights")) != TQ_OK) return rc;
+    } else {   // weights: (C, Cout, R*S) fp16
+        g.prog_steps = 0;                                  // (program mode needs one channel block per tap)
+        g.nb_tiles = 0;
         cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Cout, (cuuint64_t)(R * S)};
         cuuint32_t box[3] = {(cuuint32_t)GM_BLOCK_K, (cuuint32_t)block_n, 1};
         cuuint32_t estr[3] = {1, 1, 1};
@@ -522,8 +671,8 @@ extern "C" int tq_conv2d_codes_fused(const void *act, const void *wgt, float *ou
         else tmD = tmA;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    if (block_n == 64) return launch_conv<64, 7>(tmA, tmB, tmC, tmD, g, s);
-    return launch_conv<128, 5>(tmA, tmB, tmC, tmD, g, s);
+    if (block_n == 64) return launch_conv<64>(tmA, tmB, tmC, tmD, g, s);
+    return launch_conv<128>(tmA, tmB, tmC, tmD, g, s);
 }
 
 extern "C" int tq_conv2d_codes_f16(const void *act, const void *wgt, const float *bias, float *out,
@@ -533,4 +682,129 @@ extern "C" int tq_conv2d_codes_f16(const void *act, const void *wgt, const float
     if (!out) return fail(TQ_ERR_INVALID, "NULL pointer");
     return tq_conv2d_codes_fused(act, wgt, out, nullptr, bias, nullptr, nullptr, nullptr, N, H, W, C, Cout, R, S,
                                  stride, pad, scale, 0, 1.0f, 1, 0, stream);
+}
+
+
+// =============================================================================================
+// Unquantised stem conv (7x7 / stride 2 / pad 3 on 3 channels -- the first conv of the CNNs in
+// cnn_models/, never wrapped: cnn_models/__init__.py:34-36) on the same tensor-core kernel.
+//
+//   * space-to-depth: with the image padded by 3 and folded 2x2 into 16 channels ((dr, ds, c), c
+//     padded 3 -> 4) the conv is a 4x4 / stride-1 conv without padding:  r = 2R + dr, s = 2S + ds.
+//   * for one filter row R the four taps S = 0..3 x 16 channels are 64 CONTIGUOUS fp16 of the
+//     folded image, so the A operand of a k-block is a tensor map whose inner dimension is that
+//     64-element window and whose next dimension (output column) advances by 16 elements: the
+//     windows overlap, TMA does the im2col.
+//   * fp32 accuracy from fp16 tensor cores: x = x_hi + x_lo, w = w_hi + w_lo (fp16 each) and
+//     acc = x_hi*w_hi + x_hi*w_lo + x_lo*w_hi in the fp32 TMEM accumulator (the dropped lo*lo
+//     term is 2^-22 relative, below the rounding noise of an fp32 FMA chain of length 147).
+// =============================================================================================
+namespace tq {
+
+__global__ void __launch_bounds__(256)
+stem_prepare_kernel(const float *__restrict__ x, __half *__restrict__ x2, int N, int H, int W, int Hs, int Ws)
+{
+    // one thread per folded pixel (n, hs, ws): 16 halves hi + 16 halves lo
+    const int64_t total = (int64_t)N * Hs * Ws;
+    const int64_t plane = total * 16;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int ws = (int)(t % Ws), hs = (int)((t / Ws) % Hs), n = (int)(t / ((int64_t)Ws * Hs));
+        __align__(16) __half hi[16], lo[16];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const int h = 2 * hs + (d >> 1) - 3, w = 2 * ws + (d & 1) - 3;
+            const bool in = h >= 0 && h < H && w >= 0 && w < W;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float v = 0.0f;
+                if (in && c < 3) v = __ldg(x + (((int64_t)n * H + h) * W + w) * 3 + c);
+                const __half vh = __float2half_rn(v);
+                hi[d * 4 + c] = vh;
+                lo[d * 4 + c] = __float2half_rn(v - __half2float(vh));
+            }
+        }
+        uint4 *dh = reinterpret_cast<uint4 *>(x2 + t * 16);
+        uint4 *dl = reinterpret_cast<uint4 *>(x2 + plane + t * 16);
+        dh[0] = reinterpret_cast<const uint4 *>(hi)[0]; dh[1] = reinterpret_cast<const uint4 *>(hi)[1];
+        dl[0] = reinterpret_cast<const uint4 *>(lo)[0]; dl[1] = reinterpret_cast<const uint4 *>(lo)[1];
+    }
+}
+
+}  // namespace tq
+
+extern "C" int tq_stem_conv7x7s2(const float *x, void *x2_scratch, const void *w2, float *out,
+                                 int N, int H, int W, int Cout, void *stream)
+{
+    if (!x || !x2_scratch || !w2 || !out) return fail(TQ_ERR_INVALID, "NULL pointer");
+    if (N < 1 || H < 2 || W < 2 || (H & 1) || (W & 1)) return fail(TQ_ERR_INVALID, "H and W must be even");
+    if (Cout < 4 || Cout % 4) return fail(TQ_ERR_UNSUPPORTED, "Cout must be a multiple of 4");
+    if ((((uintptr_t)x2_scratch | (uintptr_t)w2 | (uintptr_t)out) & 15u) != 0)
+        return fail(TQ_ERR_INVALID, "pointers must be 16-byte aligned");
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return fail(TQ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int Ho = H / 2, Wo = W / 2, Hs = Ho + 3, Ws = Wo + 3;
+
+    {   // fold + split the image: fp32 NHWC3 -> fp16 [2][N][Hs][Ws][16]
+        const int64_t total = (int64_t)N * Hs * Ws;
+        int64_t blocks = (total + 255) / 256;
+        if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
+        stem_prepare_kernel<<<(int)blocks, 256, 0, s>>>(x, (__half *)x2_scratch, N, H, W, Hs, Ws);
+        count_launch();
+        int rc = check_launch("stem_prepare_kernel");
+        if (rc != TQ_OK) return rc;
+    }
+
+    ConvGeom g{};
+    g.N = N; g.H = Hs; g.W = Wo; g.C = 64; g.Cout = Cout; g.R = 4; g.S = 1; g.stride = 1; g.pad = 0;
+    g.Ho = Ho; g.Wo = Wo;
+    g.scale = 1.0f;
+    g.kc_blocks = 1;
+    pick_box(g);
+    const int block_n = Cout <= 64 ? 64 : 128;
+    g.n_tiles = (Cout + block_n - 1) / block_n;
+    g.write_f32 = 1;
+    g.next_sf = 1.0f; g.next_bits = 1;
+    // program: per filter row R one load of x_hi (MMAs against w_hi -> main accumulator, w_lo -> cross
+    // accumulator) and one of x_lo (w_hi -> cross).  The main accumulator is split in two (rows 0-1 / 2-3):
+    // tensor-core accumulation truncates, so fewer steps per accumulator = less bias; the small cross terms
+    // live apart from the large ones and everything is summed once, in fp32 RN, in the epilogue.
+    g.prog_steps = 8; g.nb_tiles = 8; g.n_groups = 3;
+    for (int R = 0; R < 4; ++R) {
+        ConvGeom::KStep &a = g.prog[R];
+        a.dw = 0; a.dh = (int8_t)R; a.kc = 0; a.plane = 0; a.n_mma = 2;
+        a.b_tile[0] = (uint8_t)R; a.group[0] = (uint8_t)(R < 2 ? 0 : 1);
+        a.b_tile[1] = (uint8_t)(4 + R); a.group[1] = 2;
+        ConvGeom::KStep &b = g.prog[4 + R];
+        b.dw = 0; b.dh = (int8_t)R; b.kc = 0; b.plane = 1; b.n_mma = 1;
+        b.b_tile[0] = (uint8_t)R; b.group[0] = 2;
+    }
+
+    CUtensorMap tmA, tmB, tmC;
+    int rc;
+    {   // overlapping windows: inner 64 elements, output column advances by one folded pixel (16 elements)
+        cuuint64_t dims[4] = {64, (cuuint64_t)Wo, (cuuint64_t)Hs, (cuuint64_t)(2 * N)};
+        cuuint64_t strides[3] = {32, (cuuint64_t)Ws * 32, (cuuint64_t)Hs * Ws * 32};
+        cuuint32_t box[4] = {64, (cuuint32_t)g.wbox, (cuuint32_t)g.hbox, (cuuint32_t)g.nbox};
+        cuuint32_t one[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x2_scratch, dims, strides, box, one,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(TQ_ERR_CUDA, "cuTensorMapEncodeTiled(stem windows) failed: %d", (int)r);
+    }
+    {
+        cuuint64_t dims[3] = {64, (cuuint64_t)Cout, 8};
+        cuuint32_t box[3] = {64, (cuuint32_t)block_n, 1};
+        cuuint32_t one[3] = {1, 1, 1};
+        if ((rc = encode_map(enc, &tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w2, 3, dims, box, one, "stem weights")) != TQ_OK) return rc;
+    }
+    {
+        cuuint64_t odims[4] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
+        cuuint32_t box[4] = {32, (cuuint32_t)g.wbox, (cuuint32_t)g.hbox, (cuuint32_t)g.nbox};
+        cuuint32_t one[4] = {1, 1, 1, 1};
+        if ((rc = encode_map(enc, &tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, 4, odims, box, one, "stem output")) != TQ_OK) return rc;
+    }
+    if (g.nbox != 1) return fail(TQ_ERR_UNSUPPORTED, "stem conv expects images of at least 128 output pixels");
+    if (block_n != 64) return fail(TQ_ERR_UNSUPPORTED, "stem conv supports Cout <= 64");
+    return launch_conv<64>(tmA, tmB, tmC, tmA, g, s);
 }

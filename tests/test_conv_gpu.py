@@ -107,3 +107,25 @@ def test_bn_relu_maxpool_encode():
         out2, none = conv_codes.bn_relu_maxpool_encode(x, (a, b), relu=False)
         assert none is None
         assert torch.equal(out2, F.max_pool2d(y.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1))
+
+
+def test_stem_conv_tensor_cores_fp32_accuracy():
+    """7x7/s2/p3 stem conv with hi/lo fp16 operand pairs on the tcgen05 kernel: as close to an fp64
+    evaluation as cuDNN's fp32 conv is."""
+    from term_quantization_b200 import conv_codes
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for N, H, W in ((3, 224, 224), (2, 64, 96)):
+        x = torch.randn(N, 3, H, W, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+        w = torch.randn(64, 3, 7, 7, device="cuda", generator=g) * 0.1
+        want = F.conv2d(x.double(), w.double(), None, 2, 3).permute(0, 2, 3, 1)
+        cudnn = F.conv2d(x, w, None, 2, 3).permute(0, 2, 3, 1)
+        got, _ = conv_codes.stem_conv7x7s2(x.permute(0, 2, 3, 1), conv_codes.pack_stem_weight(w))
+        scale = float(want.abs().max())
+        e_mine = float((got.double() - want).abs().max()) / scale
+        e_cudnn = float((cudnn.double() - want).abs().max()) / scale
+        print(f"stem conv max rel err vs fp64: tcgen05 hi/lo {e_mine:.2e}, cuDNN fp32 {e_cudnn:.2e}")
+        assert got.shape == want.shape
+        # tensor-core fp32 accumulation truncates (48 accumulate steps): ~2e-6 of the output range,
+        # against ~3e-7 for an fp32 FMA chain; TF32 would be ~1e-3
+        assert e_mine < 5e-6

@@ -48,7 +48,27 @@ def main():
                           "min_GBs": round(mb / ms, 1), "count": cnt}))
         total_ms += ms * cnt
         total_flop += flop * cnt
-    print(json.dumps({"resnet18_wrapped_convs_ms": total_ms, "TFLOPs": total_flop / total_ms / 1e9}))
+    print(json.dumps({"resnet18_wrapped_convs_ms": total_ms, "TFLOPs": total_flop / max(total_ms, 1e-9) / 1e9}))
+    if args.only < 0:
+        import torch.nn.functional as F
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cudnn.benchmark = True
+        x = torch.randn(args.batch, 3, 224, 224, device="cuda").contiguous(memory_format=torch.channels_last)
+        w = torch.randn(64, 3, 7, 7, device="cuda") * 0.1
+        w2 = conv_codes.pack_stem_weight(w)
+        xn = x.permute(0, 2, 3, 1)
+        _, scratch = conv_codes.stem_conv7x7s2(xn, w2)
+        for name, fn in (("stem tcgen05 hi/lo", lambda: conv_codes.stem_conv7x7s2(xn, w2, scratch)),
+                         ("stem cuDNN fp32", lambda: F.conv2d(x, w, None, 2, 3))):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.iters):
+                fn()
+            e1.record()
+            e1.synchronize()
+            print(json.dumps({"case": name, "ms": e0.elapsed_time(e1) / args.iters}))
 
 
 if __name__ == "__main__":
