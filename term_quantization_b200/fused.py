@@ -6,8 +6,10 @@ Here each conv is ONE launch of the tcgen05 kernel whose epilogue applies the Ba
 the residual add and the ReLU, and emits the fp16 term codes the *next* conv consumes
 (the accumulate -> ReLU/requantise -> encode -> truncate order of verilog/systolic_dla_top.v).
 fp32 activations are materialised only where the graph needs them (block outputs, which feed
-the next residual add).  The stem (first conv, never wrapped: cnn_models/__init__.py:34-36),
-max-pool, global average pool and the classifier stay on PyTorch.
+the next residual add).  The stem (first conv, never wrapped: cnn_models/__init__.py:34-36) stays
+unquantised fp32 arithmetic but also runs on the tensor cores (hi/lo fp16 operand pairs, fp32
+accumulate: conv_codes.stem_conv7x7s2; `stem="cudnn"` keeps cuDNN's fp32 conv); its BatchNorm + ReLU +
+max-pool + first encode are one pass.  Global average pool and the classifier stay on PyTorch.
 
 Numerics: integer accumulators are exact; the BatchNorm affine is evaluated as
 fma(t, a, b) with a = weight * rsqrt(var + eps), b = fma(-mean, a, bias), which is within 1-2 ulp
@@ -62,8 +64,10 @@ class _Conv:
 class FusedResNet(nn.Module):
     """Wraps a calibrated, TQ-converted torchvision ResNet built from BasicBlocks."""
 
-    def __init__(self, model):
+    def __init__(self, model, stem="tcgen05"):
         super().__init__()
+        if stem not in ("tcgen05", "cudnn"):
+            raise ValueError("stem must be 'tcgen05' or 'cudnn'")
         self.model = model.to(memory_format=torch.channels_last).eval()
         self.blocks = []
         for stage in (model.layer1, model.layer2, model.layer3, model.layer4):
@@ -82,6 +86,13 @@ class FusedResNet(nn.Module):
                           and mp.padding in (1, (1, 1)) and mp.dilation in (1, (1, 1)) and not mp.ceil_mode
                           and model.conv1.out_channels % 4 == 0 and self.blocks[0][0].quant[1] <= 12)
         self.stem_bn = _bn_affine(model.bn1)
+        c1 = model.conv1
+        self.stem_w = None
+        if (stem == "tcgen05" and self.fuse_stem and tuple(c1.weight.shape[1:]) == (3, 7, 7) and c1.stride == (2, 2)
+                and c1.padding == (3, 3) and c1.dilation == (1, 1) and c1.groups == 1 and c1.bias is None
+                and c1.out_channels <= 64):
+            self.stem_w = conv_codes.pack_stem_weight(c1.weight)
+        self._stem_scratch = None
 
     @staticmethod
     def _encode(x_nhwc, quant):
@@ -94,10 +105,15 @@ class FusedResNet(nn.Module):
         m = self.model
         x = x.contiguous(memory_format=torch.channels_last)
         if self.fuse_stem:
-            # stem conv on cuDNN (never wrapped), then bn1 + relu + maxpool + first encode in one pass
+            # stem conv (never wrapped, fp32 arithmetic), then bn1 + relu + maxpool + first encode in one pass
             q0 = self.blocks[0][0].quant
-            cur, c0 = conv_codes.bn_relu_maxpool_encode(m.conv1(x).permute(0, 2, 3, 1), self.stem_bn,
-                                                        relu=True, next_quant=q0)
+            if self.stem_w is not None and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0 \
+                    and (x.shape[2] // 2) * (x.shape[3] // 2) >= 128:
+                y, self._stem_scratch = conv_codes.stem_conv7x7s2(x.permute(0, 2, 3, 1), self.stem_w,
+                                                                  self._stem_scratch)
+            else:
+                y = m.conv1(x).permute(0, 2, 3, 1)
+            cur, c0 = conv_codes.bn_relu_maxpool_encode(y, self.stem_bn, relu=True, next_quant=q0)
             codes = {q0: c0}                             # quantiser -> fp16 codes of `cur`
         else:
             x = m.maxpool(m.relu(m.bn1(m.conv1(x))))

@@ -243,12 +243,18 @@ def test_fused_resnet_matches_unfused_tensor_core_path():
         switched, skipped = tr_layer.use_tensor_cores(q)
         assert len(switched) == 19 and not skipped
         unfused = q(x.contiguous(memory_format=torch.channels_last))
-        f = fused.FusedResNet(q)
-        got = f(x)
+        got = fused.FusedResNet(q, stem="cudnn")(x)
+        f = fused.FusedResNet(q)                                # stem conv on the tensor cores too
+        assert f.stem_w is not None
+        got_tc_stem = f(x)
     scale = float(ref.abs().max())
     d_unfused = float((unfused - ref).abs().max()) / scale
     d_fused = float((got - unfused).abs().max()) / scale
-    print(f"rel diff: tensor-core vs float path {d_unfused:.3e}; fused vs unfused {d_fused:.3e}")
+    d_stem = float((got_tc_stem - got).abs().max()) / scale
+    print(f"rel diff: tensor-core vs float path {d_unfused:.3e}; fused vs unfused {d_fused:.3e}; "
+          f"tcgen05 stem vs cuDNN stem {d_stem:.3e}")
+    assert d_stem < 2e-2
+    assert float((got_tc_stem.argmax(1) == ref.argmax(1)).float().mean()) >= 0.75
     # The float path is cuDNN fp32 (Winograd / FFT algorithms under cudnn.benchmark): its own
     # rounding noise, amplified by 19 re-quantisations, is what separates it from the exact
     # integer path (tools/numerics_probe.py measures both against an fp64 run).
