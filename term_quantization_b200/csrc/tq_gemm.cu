@@ -47,12 +47,12 @@ struct ConvGeom {
     // a table of A loads, each followed by 1-2 MMAs against stationary B tiles into an accumulator group
     int prog_steps, nb_tiles, n_groups;
     int dbg_skip_epilogue;      // profiling aid (TQ_CONV_SKIP_EPI=1): drain accumulators without storing
-    struct KStep {
-        int8_t dw, dh;          // offset of the A box relative to the tile origin (filter tap)
-        int8_t kc;              // 64-channel block
-        int8_t plane;           // A plane (stacked along N): coordinate n0 + plane * N
-        uint8_t n_mma, b_tile[2], group[2];
-    } prog[16];
+    int dbg_skip_mma, dbg_skip_tma;   // TQ_CONV_SKIP_MMA / TQ_CONV_SKIP_TMA: isolate the load and the MMA pipelines
+    // one packed word per step for each of the two control warps (a single indexed constant load per step):
+    //   prog_ld : dw | dh << 8 | kc << 16 | plane << 24   (A box offset = filter tap, 64-channel block, A plane
+    //             stacked along N: coordinate n0 + plane * N)
+    //   prog_mma: n_mma | b_tile0 << 4 | group0 << 8 | b_tile1 << 12 | group1 << 16
+    uint32_t prog_ld[16], prog_mma[16];
     // fused epilogue (all optional):  t = acc*scale (+bias) ; t = fma(t, bn_a, bn_b) ; t += residual ;
     // t = max(t, 0) ; fp32 tile out (TMA store) ; fp16 term codes of t for the next layer (TMA store)
     const float *bias, *bn_a, *bn_b, *residual;
@@ -169,7 +169,10 @@ constexpr int GM_MAX_STAGES = 8;
 constexpr int GM_EPI_BYTES = 16384 + 8192;      // per epilogue group: [128][32] fp32 + [128][32] fp16 staging
 constexpr int GM_SMEM_BUDGET = 227 * 1024;
 
-template <int BLOCK_N>
+// MODE 0: A and B tiles stream through the stage ring.  MODE 1: all weight tiles resident in shared memory
+// (tile = filter tap, one 64-channel block), only A streams.  MODE 2: resident weights + the general step
+// table (several MMA groups / accumulator groups / A planes per step: the hi/lo stem conv).
+template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD,
@@ -187,7 +190,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint64_t *tempty_bar = tfull_bar + 2;               // [2] accumulator drained
     uint64_t *bfull_bar = tempty_bar + 2;               // stationary weights landed
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bfull_bar + 1);
-    const bool prog = g.prog_steps > 0;
+    constexpr bool prog = MODE != 0;
     const int acc_cols = g.n_groups * BLOCK_N;          // TMEM columns of one accumulator stage
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -230,6 +233,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         // converged warp, one elected lane issues (same reason as the MMA warp below)
         int stage = 0;
         uint32_t phase = 0;
+        uint8_t *sdst = ring;
         if (prog) {                                     // all weights once: they stay resident
             if (elect_one()) {
                 mbar_expect_tx(bfull_bar, (uint32_t)(g.nb_tiles * B_BYTES));
@@ -237,51 +241,61 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             }
             __syncwarp();
         }
+        const int steps = prog ? g.prog_steps : kblocks;
+        uint32_t pw = MODE == 2 ? g.prog_ld[0] : 0u;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int n_tile = tile % g.n_tiles, m_tile = tile / g.n_tiles;
             const int tw = m_tile % g.tiles_w, th = (m_tile / g.tiles_w) % g.tiles_h, tn = m_tile / (g.tiles_w * g.tiles_h);
             const int w_in0 = tw * g.wbox * g.stride - g.pad, h_in0 = th * g.hbox * g.stride - g.pad, n0 = tn * g.nbox;
-            if (prog) {
-                for (int st = 0; st < g.prog_steps; ++st) {
-                    const int cw = w_in0 + g.prog[st].dw, ch = h_in0 + g.prog[st].dh;
-                    const int cc = g.prog[st].kc * GM_BLOCK_K, cn = n0 + g.prog[st].plane * g.N;
-                    mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    if (elect_one()) {
+            int r = 0, sx = 0, kc = 0;                  // streaming mode: tap (r, sx), channel block kc
+            for (int st = 0; st < steps; ++st) {
+                int cc, cw, ch, cn;
+                if constexpr (MODE == 2) {
+                    const uint32_t cur = pw;
+                    pw = g.prog_ld[st + 1 < steps ? st + 1 : 0];        // next step's word while this one is issued
+                    cw = w_in0 + (int)(cur & 0xFFu); ch = h_in0 + (int)((cur >> 8) & 0xFFu);
+                    cc = (int)((cur >> 16) & 0xFFu) * GM_BLOCK_K; cn = n0 + (int)(cur >> 24) * g.N;
+                } else {
+                    cw = w_in0 + sx; ch = h_in0 + r; cc = kc * GM_BLOCK_K; cn = n0;
+                }
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                if (elect_one()) {
+                    if (g.dbg_skip_tma) mbar_arrive(&full_bar[stage]);
+                    else if constexpr (prog) {
                         mbar_expect_tx(&full_bar[stage], (uint32_t)g.a_tx_bytes);
-                        tma_load_4d(&tmA, &full_bar[stage], ring + stage * g.stage_bytes, cc, cw, ch, cn);
-                    }
-                    __syncwarp();
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-                }
-                continue;
-            }
-            for (int tap = 0; tap < g.R * g.S; ++tap) {
-                const int r = tap / g.S, s = tap % g.S;
-                for (int kc = 0; kc < g.kc_blocks; ++kc) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    if (elect_one()) {
-                        uint8_t *sa = ring + stage * g.stage_bytes;
+                        tma_load_4d(&tmA, &full_bar[stage], sdst, cc, cw, ch, cn);
+                    } else {
                         mbar_expect_tx(&full_bar[stage], (uint32_t)(g.a_tx_bytes + B_BYTES));
-                        tma_load_4d(&tmA, &full_bar[stage], sa, kc * GM_BLOCK_K, w_in0 + s, h_in0 + r, n0);
-                        tma_load_3d(&tmB, &full_bar[stage], sa + GM_A_BYTES, kc * GM_BLOCK_K, n_tile * BLOCK_N, tap);
+                        tma_load_4d(&tmA, &full_bar[stage], sdst, cc, cw, ch, cn);
+                        tma_load_3d(&tmB, &full_bar[stage], sdst + GM_A_BYTES, cc, n_tile * BLOCK_N, r * g.S + sx);
                     }
-                    __syncwarp();
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
+                __syncwarp();
+                sdst += g.stage_bytes;
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; sdst = ring; }
+                if (++kc == g.kc_blocks) { kc = 0; if (++sx == g.S) { sx = 0; ++r; } }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        // The whole warp walks the loop converged (descriptors stay in uniform registers, no per-operand
-        // broadcasts); one elected lane issues tcgen05.mma / tcgen05.commit.
+        // The whole warp walks the loop converged; one elected lane issues tcgen05.mma / tcgen05.commit.
+        // The loop body is kept to a handful of instructions per stage: a single warp executes dependent
+        // scalar code at one instruction every few cycles, and 4 MMAs of N = 64 retire in ~230 cycles
+        // (tools/umma_issue_probe.cu), so descriptor arithmetic or table lookups here would pace the tensor pipe.
         // instruction descriptor: D = F32, A = B = F16, both K-major, N = BLOCK_N, M = 128
         constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(GM_BLOCK_M >> 4) << 24);
+        constexpr uint64_t DESC_HI = ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        const uint32_t ring_addr = smem_u32(ring), bstat_addr = smem_u32(bstat);
-        if (prog) {
+        const uint32_t a_lo0 = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (1u << 16);      // descriptor low words
+        const uint32_t b_lo0 = ((smem_u32(bstat) & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t a_step = (uint32_t)g.stage_bytes >> 4;
+        uint32_t a_lo = a_lo0;
+        const int steps = prog ? g.prog_steps : kblocks;
+        uint32_t pw = MODE == 2 ? g.prog_mma[0] : 0u;
+        if constexpr (prog) {
             mbar_wait(bfull_bar, 0);
             tc_fence_after();
         }
@@ -289,44 +303,60 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
-            if (prog) {
-                uint32_t started = 0;                           // accumulator groups already written in this tile
-                for (int st = 0; st < g.prog_steps; ++st) {
-                    const int n_mma = g.prog[st].n_mma;
+            if constexpr (MODE != 2) {
+                uint32_t b_lo = b_lo0;                              // MODE 1: resident tile of this step
+                for (int st = 0; st < steps; ++st) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint64_t da = smem_desc_sw128(ring_addr + (uint32_t)(stage * g.stage_bytes));
-                    for (int m = 0; m < n_mma; ++m) {
-                        const uint64_t db = smem_desc_sw128(bstat_addr + (uint32_t)(g.prog[st].b_tile[m] * B_BYTES));
-                        const uint32_t grp = g.prog[st].group[m];
-                        const uint32_t first = ((started >> grp) & 1u) ^ 1u;
-                        if (elect_one()) {
-#pragma unroll
-                            for (int k = 0; k < GM_BLOCK_K / 16; ++k)
-                                umma_f16(tmem_d + grp * BLOCK_N, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC,
-                                         (k != 0 || !first) ? 1u : 0u);
-                        }
-                        __syncwarp();
-                        started |= 1u << grp;
-                    }
-                    if (elect_one()) umma_commit(&empty_bar[stage]);
-                    __syncwarp();
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-                }
-            } else {
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sa = ring_addr + (uint32_t)(stage * g.stage_bytes);
-                    const uint64_t da = smem_desc_sw128(sa), db = smem_desc_sw128(sa + GM_A_BYTES);
                     if (elect_one()) {
+                        const uint64_t da = DESC_HI | a_lo;
+                        const uint64_t db = DESC_HI | (MODE == 1 ? b_lo : a_lo + (uint32_t)(GM_A_BYTES >> 4));
+                        if (!g.dbg_skip_mma) {
 #pragma unroll
-                        for (int k = 0; k < GM_BLOCK_K / 16; ++k)   // UMMA_K = 16 fp16 = 32 bytes = +2 in the address field
-                            umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < GM_BLOCK_K / 16; ++k)   // UMMA_K = 16 fp16 = 32 bytes = +2 in the address field
+                                umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (st | k) != 0 ? 1u : 0u);
+                        }
                         umma_commit(&empty_bar[stage]);             // frees the smem stage when the MMAs retire
                     }
                     __syncwarp();
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    a_lo += a_step;
+                    b_lo += (uint32_t)(B_BYTES >> 4);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; a_lo = a_lo0; }
+                }
+            } else {
+                uint32_t started = 0;                               // accumulator groups already written in this tile
+                for (int st = 0; st < steps; ++st) {
+                    const uint32_t cur = pw;
+                    pw = g.prog_mma[st + 1 < steps ? st + 1 : 0];
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t da = DESC_HI | a_lo;
+                        const uint32_t g0 = (cur >> 8) & 0xFu;
+                        const uint64_t db = DESC_HI | (b_lo0 + ((cur >> 4) & 0xFu) * (uint32_t)(B_BYTES >> 4));
+                        const uint32_t first = ((started >> g0) & 1u) ^ 1u;
+                        if (!g.dbg_skip_mma) {
+#pragma unroll
+                            for (int k = 0; k < GM_BLOCK_K / 16; ++k)
+                                umma_f16(tmem_d + g0 * BLOCK_N, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC,
+                                         (k != 0 || !first) ? 1u : 0u);
+                            if ((cur & 0xFu) == 2u) {
+                                const uint32_t g1 = (cur >> 16) & 0xFu;
+                                const uint64_t db1 = DESC_HI | (b_lo0 + ((cur >> 12) & 0xFu) * (uint32_t)(B_BYTES >> 4));
+                                const uint32_t first1 = (((started | (1u << g0)) >> g1) & 1u) ^ 1u;
+#pragma unroll
+                                for (int k = 0; k < GM_BLOCK_K / 16; ++k)
+                                    umma_f16(tmem_d + g1 * BLOCK_N, da + (uint64_t)(2 * k), db1 + (uint64_t)(2 * k), IDESC,
+                                             (k != 0 || !first1) ? 1u : 0u);
+                            }
+                        }
+                        umma_commit(&empty_bar[stage]);
+                    }
+                    __syncwarp();
+                    started |= 1u << ((cur >> 8) & 0xFu);
+                    if ((cur & 0xFu) == 2u) started |= 1u << ((cur >> 16) & 0xFu);
+                    a_lo += a_step;
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; a_lo = a_lo0; }
                 }
             }
             if (elect_one()) umma_commit(&tfull_bar[acc]);      // accumulator complete
@@ -491,10 +521,14 @@ static EncodeTiledFn encode_tiled()
 static void pick_box(ConvGeom &g)
 {
     long best = -1;
+    static const int force_w = getenv("TQ_CONV_WBOX") ? atoi(getenv("TQ_CONV_WBOX")) : 0;
+    static const int force_h = getenv("TQ_CONV_HBOX") ? atoi(getenv("TQ_CONV_HBOX")) : 0;
     for (int wb = 1; wb <= g.Wo && wb <= 128; ++wb) {
         if (wb * g.stride > 256) break;
+        if (force_w && wb != force_w && force_w <= g.Wo) continue;
         for (int hb = 1; hb <= g.Ho && wb * hb <= 128; ++hb) {
             if (hb * g.stride > 256) break;
+            if (force_h && hb != force_h && force_h <= g.Ho && force_w * force_h <= 128) continue;
             int nb = 1;
             if (wb == g.Wo && hb == g.Ho) nb = 128 / (wb * hb) < g.N ? 128 / (wb * hb) : g.N;
             if (nb < 1) nb = 1;
@@ -534,17 +568,16 @@ static int plan_smem(ConvGeom &g, int block_n)
     return TQ_OK;
 }
 
-template <int BLOCK_N>
-static int launch_conv(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
+template <int BLOCK_N, int MODE>
+static int launch_conv_mode(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
                        const CUtensorMap &tmD, ConvGeom &g, cudaStream_t s)
 {
-    if (g.n_groups < 1) g.n_groups = 1;
     static const bool skip_epi = getenv("TQ_CONV_SKIP_EPI") != nullptr;
     g.dbg_skip_epilogue = skip_epi ? 1 : 0;
-    if (2 * g.n_groups * BLOCK_N > 512) return fail(TQ_ERR_UNSUPPORTED, "accumulator groups exceed tensor memory");
-    int rc = plan_smem(g, BLOCK_N);
-    if (rc != TQ_OK) return rc;
-    auto kern = conv_igemm_f16_kernel<BLOCK_N>;
+    static const bool skip_mma = getenv("TQ_CONV_SKIP_MMA") != nullptr, skip_tma = getenv("TQ_CONV_SKIP_TMA") != nullptr;
+    g.dbg_skip_mma = skip_mma ? 1 : 0;
+    g.dbg_skip_tma = skip_tma ? 1 : 0;
+    auto kern = conv_igemm_f16_kernel<BLOCK_N, MODE>;
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -558,6 +591,23 @@ static int launch_conv(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUt
     kern<<<grid, GM_THREADS, g.smem_total, s>>>(tmA, tmB, tmC, tmD, g);
     count_launch();
     return check_launch("conv_igemm_f16_kernel");
+}
+
+// general_prog: the step table (prog_ld / prog_mma) is in use; otherwise resident weights are tile = tap
+template <int BLOCK_N>
+static int launch_conv(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
+                       const CUtensorMap &tmD, ConvGeom &g, cudaStream_t s, bool general_prog = false)
+{
+    if (g.n_groups < 1) g.n_groups = 1;
+    if (2 * g.n_groups * BLOCK_N > 512) return fail(TQ_ERR_UNSUPPORTED, "accumulator groups exceed tensor memory");
+    int rc = plan_smem(g, BLOCK_N);
+    if (rc != TQ_OK) return rc;
+    if (g.prog_steps == 0) return launch_conv_mode<BLOCK_N, 0>(tmA, tmB, tmC, tmD, g, s);
+    if constexpr (BLOCK_N == 64) {
+        if (general_prog) return launch_conv_mode<64, 2>(tmA, tmB, tmC, tmD, g, s);
+        return launch_conv_mode<64, 1>(tmA, tmB, tmC, tmD, g, s);
+    }
+    return fail(TQ_ERR_UNSUPPORTED, "resident-weight mode is built for BLOCK_N = 64 only");
 }
 
 static int encode_map(EncodeTiledFn enc, CUtensorMap *tm, CUtensorMapDataType dt, int esize, const void *base,
@@ -627,12 +677,6 @@ extern "C" int tq_conv2d_codes_fused(const void *act, const void *wgt, float *ou
     if (!no_prog && Cout <= 64 && taps <= 12) {
         g.prog_steps = taps;
         g.nb_tiles = taps;
-        for (int t = 0; t < taps; ++t) {
-            const int tap = t / g.kc_blocks, kc = t % g.kc_blocks;
-            ConvGeom::KStep &k = g.prog[t];
-            k.dw = (int8_t)(tap % S); k.dh = (int8_t)(tap / S); k.kc = (int8_t)kc; k.plane = 0;
-            k.n_mma = 1; k.b_tile[0] = (uint8_t)t; k.group[0] = 0;
-        }
     }
 
     CUtensorMap tmA, tmB, tmC, tmD;
@@ -770,14 +814,11 @@ extern "C" int tq_stem_conv7x7s2(const float *x, void *x2_scratch, const void *w
     // tensor-core accumulation truncates, so fewer steps per accumulator = less bias; the small cross terms
     // live apart from the large ones and everything is summed once, in fp32 RN, in the epilogue.
     g.prog_steps = 8; g.nb_tiles = 8; g.n_groups = 3;
-    for (int R = 0; R < 4; ++R) {
-        ConvGeom::KStep &a = g.prog[R];
-        a.dw = 0; a.dh = (int8_t)R; a.kc = 0; a.plane = 0; a.n_mma = 2;
-        a.b_tile[0] = (uint8_t)R; a.group[0] = (uint8_t)(R < 2 ? 0 : 1);
-        a.b_tile[1] = (uint8_t)(4 + R); a.group[1] = 2;
-        ConvGeom::KStep &b = g.prog[4 + R];
-        b.dw = 0; b.dh = (int8_t)R; b.kc = 0; b.plane = 1; b.n_mma = 1;
-        b.b_tile[0] = (uint8_t)R; b.group[0] = 2;
+    for (uint32_t R = 0; R < 4; ++R) {
+        g.prog_ld[R] = R << 8;                                              // x_hi, filter row R
+        g.prog_mma[R] = 2u | (R << 4) | ((R < 2 ? 0u : 1u) << 8) | ((4u + R) << 12) | (2u << 16);
+        g.prog_ld[4 + R] = (R << 8) | (1u << 24);                           // x_lo (plane 1), filter row R
+        g.prog_mma[4 + R] = 1u | (R << 4) | (2u << 8);
     }
 
     CUtensorMap tmA, tmB, tmC;
@@ -806,5 +847,5 @@ extern "C" int tq_stem_conv7x7s2(const float *x, void *x2_scratch, const void *w
     }
     if (g.nbox != 1) return fail(TQ_ERR_UNSUPPORTED, "stem conv expects images of at least 128 output pixels");
     if (block_n != 64) return fail(TQ_ERR_UNSUPPORTED, "stem conv supports Cout <= 64");
-    return launch_conv<64>(tmA, tmB, tmC, tmA, g, s);
+    return launch_conv<64>(tmA, tmB, tmC, tmA, g, s, true);
 }
