@@ -31,7 +31,7 @@ namespace tq {
 
 constexpr int GM_BLOCK_M = 128;
 constexpr int GM_BLOCK_K = 64;                  // fp16 elements = 128 bytes = one swizzle row
-constexpr int GM_THREADS = 384;                 // 4 control warps + 2 epilogue groups of 4 warps
+constexpr int GM_THREADS = 640;                 // 4 control warps + 4 epilogue groups of 4 warps
 constexpr int GM_A_BYTES = GM_BLOCK_M * GM_BLOCK_K * 2;
 
 struct ConvGeom {
@@ -42,7 +42,7 @@ struct ConvGeom {
     int a_tx_bytes;                             // bytes one A box deposits
     float scale;
     // shared-memory carve-up (runtime, 1024-byte aligned regions)
-    int stages, stage_bytes, ring_off, bstat_off, epi_off, lut_off, bar_off, smem_total;
+    int stages, stage_bytes, ring_off, bstat_off, epi_off, epi_group_bytes, epi_codes_off, lut_off, bar_off, smem_total;
     // "program" mode for small layers (Cout <= BLOCK_N, all weights resident in shared memory): the K loop is
     // a table of A loads, each followed by 1-2 MMAs against stationary B tiles into an accumulator group
     int prog_steps, nb_tiles, n_groups;
@@ -141,6 +141,17 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *src, int c0, int c1, int c2, int c3)
 {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
@@ -166,7 +177,9 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr)
 
 constexpr int GM_LUT_MAX_BITS = 10;             // fused next-layer encode: 2^(bits+1) fp16 entries in smem
 constexpr int GM_MAX_STAGES = 8;
-constexpr int GM_EPI_BYTES = 16384 + 8192;      // per epilogue group: [128][32] fp32 + [128][32] fp16 staging
+constexpr int GM_EPI_GROUPS = 4;                // (accumulator stage, column half)
+constexpr int GM_EPI_F32_BYTES = 16384;         // per epilogue group: [128][32] fp32 staging (output tile / residual tile)
+constexpr int GM_EPI_CODE_BYTES = 8192;         // per epilogue group: [128][32] fp16 code staging
 constexpr int GM_SMEM_BUDGET = 227 * 1024;
 
 // MODE 0: A and B tiles stream through the stage ring.  MODE 1: all weight tiles resident in shared memory
@@ -176,7 +189,7 @@ template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD,
-                      const __grid_constant__ ConvGeom g)
+                      const __grid_constant__ CUtensorMap tmR, const __grid_constant__ ConvGeom g)
 {
     constexpr int B_BYTES = BLOCK_N * GM_BLOCK_K * 2;
     const int STAGES = g.stages;
@@ -189,7 +202,8 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint64_t *tfull_bar = empty_bar + GM_MAX_STAGES;    // [2] accumulator ready
     uint64_t *tempty_bar = tfull_bar + 2;               // [2] accumulator drained
     uint64_t *bfull_bar = tempty_bar + 2;               // stationary weights landed
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bfull_bar + 1);
+    uint64_t *res_bar = bfull_bar + 1;                  // [4] residual tile landed in an epilogue group's staging
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_bar + GM_EPI_GROUPS);
     constexpr bool prog = MODE != 0;
     const int acc_cols = g.n_groups * BLOCK_N;          // TMEM columns of one accumulator stage
 
@@ -204,6 +218,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         if (g.write_f32) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
         if (g.write_codes) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
+        if (g.residual) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
     }
     __half *lut = reinterpret_cast<__half *>(smem + g.lut_off);
     if (g.write_codes) {
@@ -216,7 +231,8 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         mbar_init(bfull_bar, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }   // 128 = one epilogue group
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 256); }   // 256 = two epilogue groups
+        for (int i = 0; i < GM_EPI_GROUPS; ++i) mbar_init(&res_bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -230,120 +246,119 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
     if (warp == 0) {
         // ================= TMA producer =================
-        // converged warp, one elected lane issues (same reason as the MMA warp below)
-        int stage = 0;
-        uint32_t phase = 0;
-        uint8_t *sdst = ring;
-        if (prog) {                                     // all weights once: they stay resident
-            if (elect_one()) {
+        // ONE thread runs the whole loop: no elect / reconvergence instructions per stage -- the per-stage
+        // latency of this loop (and of the MMA loop below) bounds the kernel when a stage holds only ~230
+        // cycles of tensor work (BLOCK_N = 64), see DESIGN.md section 6.
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            uint8_t *sdst = ring;
+            if constexpr (prog) {                           // all weights once: they stay resident
                 mbar_expect_tx(bfull_bar, (uint32_t)(g.nb_tiles * B_BYTES));
                 for (int t = 0; t < g.nb_tiles; ++t) tma_load_3d(&tmB, bfull_bar, bstat + t * B_BYTES, 0, 0, t);
             }
-            __syncwarp();
-        }
-        const int steps = prog ? g.prog_steps : kblocks;
-        uint32_t pw = MODE == 2 ? g.prog_ld[0] : 0u;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int n_tile = tile % g.n_tiles, m_tile = tile / g.n_tiles;
-            const int tw = m_tile % g.tiles_w, th = (m_tile / g.tiles_w) % g.tiles_h, tn = m_tile / (g.tiles_w * g.tiles_h);
-            const int w_in0 = tw * g.wbox * g.stride - g.pad, h_in0 = th * g.hbox * g.stride - g.pad, n0 = tn * g.nbox;
-            int r = 0, sx = 0, kc = 0;                  // streaming mode: tap (r, sx), channel block kc
-            for (int st = 0; st < steps; ++st) {
-                int cc, cw, ch, cn;
-                if constexpr (MODE == 2) {
-                    const uint32_t cur = pw;
-                    pw = g.prog_ld[st + 1 < steps ? st + 1 : 0];        // next step's word while this one is issued
-                    cw = w_in0 + (int)(cur & 0xFFu); ch = h_in0 + (int)((cur >> 8) & 0xFFu);
-                    cc = (int)((cur >> 16) & 0xFFu) * GM_BLOCK_K; cn = n0 + (int)(cur >> 24) * g.N;
-                } else {
-                    cw = w_in0 + sx; ch = h_in0 + r; cc = kc * GM_BLOCK_K; cn = n0;
-                }
-                mbar_wait(&empty_bar[stage], phase ^ 1u);
-                if (elect_one()) {
-                    if (g.dbg_skip_tma) mbar_arrive(&full_bar[stage]);
-                    else if constexpr (prog) {
-                        mbar_expect_tx(&full_bar[stage], (uint32_t)g.a_tx_bytes);
-                        tma_load_4d(&tmA, &full_bar[stage], sdst, cc, cw, ch, cn);
+            const int steps = prog ? g.prog_steps : kblocks;
+            const int S = g.S, kc_blocks = g.kc_blocks, stage_bytes = g.stage_bytes;
+            const uint32_t tx_bytes = (uint32_t)g.a_tx_bytes + (prog ? 0u : (uint32_t)B_BYTES);
+            const bool skip_tma = g.dbg_skip_tma != 0;
+            uint32_t pw = MODE == 2 ? g.prog_ld[0] : 0u;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_tile = tile % g.n_tiles, m_tile = tile / g.n_tiles;
+                const int tw = m_tile % g.tiles_w, th = (m_tile / g.tiles_w) % g.tiles_h, tn = m_tile / (g.tiles_w * g.tiles_h);
+                const int w_in0 = tw * g.wbox * g.stride - g.pad, h_in0 = th * g.hbox * g.stride - g.pad, n0 = tn * g.nbox;
+                const int nb0 = n_tile * BLOCK_N;
+                int r = 0, sx = 0, kc = 0;                  // tap (r, sx), channel block kc
+                for (int st = 0; st < steps; ++st) {
+                    int cc, cw, ch, cn;
+                    if constexpr (MODE == 2) {
+                        const uint32_t cur = pw;
+                        pw = g.prog_ld[st + 1 < steps ? st + 1 : 0];        // next step's word while this one is issued
+                        cw = w_in0 + (int)(cur & 0xFFu); ch = h_in0 + (int)((cur >> 8) & 0xFFu);
+                        cc = (int)((cur >> 16) & 0xFFu) * GM_BLOCK_K; cn = n0 + (int)(cur >> 24) * g.N;
                     } else {
-                        mbar_expect_tx(&full_bar[stage], (uint32_t)(g.a_tx_bytes + B_BYTES));
-                        tma_load_4d(&tmA, &full_bar[stage], sdst, cc, cw, ch, cn);
-                        tma_load_3d(&tmB, &full_bar[stage], sdst + GM_A_BYTES, cc, n_tile * BLOCK_N, r * g.S + sx);
+                        cw = w_in0 + sx; ch = h_in0 + r; cc = kc * GM_BLOCK_K; cn = n0;
                     }
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    if (skip_tma) mbar_arrive(&full_bar[stage]);
+                    else {
+                        mbar_expect_tx(&full_bar[stage], tx_bytes);
+                        tma_load_4d(&tmA, &full_bar[stage], sdst, cc, cw, ch, cn);
+                        if constexpr (!prog) tma_load_3d(&tmB, &full_bar[stage], sdst + GM_A_BYTES, cc, nb0, r * S + sx);
+                    }
+                    sdst += stage_bytes;
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; sdst = ring; }
+                    if (++kc == kc_blocks) { kc = 0; if (++sx == S) { sx = 0; ++r; } }
                 }
-                __syncwarp();
-                sdst += g.stage_bytes;
-                if (++stage == STAGES) { stage = 0; phase ^= 1u; sdst = ring; }
-                if (++kc == g.kc_blocks) { kc = 0; if (++sx == g.S) { sx = 0; ++r; } }
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        // The whole warp walks the loop converged; one elected lane issues tcgen05.mma / tcgen05.commit.
-        // The loop body is kept to a handful of instructions per stage: a single warp executes dependent
-        // scalar code at one instruction every few cycles, and 4 MMAs of N = 64 retire in ~230 cycles
-        // (tools/umma_issue_probe.cu), so descriptor arithmetic or table lookups here would pace the tensor pipe.
+        // ONE thread issues every tcgen05.mma / tcgen05.commit (see the producer's note).
         // instruction descriptor: D = F32, A = B = F16, both K-major, N = BLOCK_N, M = 128
         constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(GM_BLOCK_M >> 4) << 24);
         constexpr uint64_t DESC_HI = ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-        int stage = 0;
-        uint32_t phase = 0;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        const uint32_t a_lo0 = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (1u << 16);      // descriptor low words
-        const uint32_t b_lo0 = ((smem_u32(bstat) & 0x3FFFFu) >> 4) | (1u << 16);
-        const uint32_t a_step = (uint32_t)g.stage_bytes >> 4;
-        uint32_t a_lo = a_lo0;
-        const int steps = prog ? g.prog_steps : kblocks;
-        uint32_t pw = MODE == 2 ? g.prog_mma[0] : 0u;
-        if constexpr (prog) {
-            mbar_wait(bfull_bar, 0);
-            tc_fence_after();
-        }
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
-            if constexpr (MODE != 2) {
-                uint32_t b_lo = b_lo0;                              // MODE 1: resident tile of this step
-                for (int st = 0; st < steps; ++st) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    if (elect_one()) {
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            const uint32_t a_lo0 = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (1u << 16);      // descriptor low words
+            const uint32_t b_lo0 = ((smem_u32(bstat) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t a_step = (uint32_t)g.stage_bytes >> 4;
+            uint32_t a_lo = a_lo0;
+            const int steps = prog ? g.prog_steps : kblocks;
+            const bool skip_mma = g.dbg_skip_mma != 0;
+            uint32_t pw = MODE == 2 ? g.prog_mma[0] : 0u;
+            if constexpr (prog) {
+                mbar_wait(bfull_bar, 0);
+                tc_fence_after();
+            }
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
+                if constexpr (MODE != 2) {
+                    uint32_t b_lo = b_lo0;                              // MODE 1: resident tile of this step
+                    for (int st = 0; st < steps; ++st) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
                         const uint64_t da = DESC_HI | a_lo;
                         const uint64_t db = DESC_HI | (MODE == 1 ? b_lo : a_lo + (uint32_t)(GM_A_BYTES >> 4));
-                        if (!g.dbg_skip_mma) {
+                        if (!skip_mma) {
 #pragma unroll
                             for (int k = 0; k < GM_BLOCK_K / 16; ++k)   // UMMA_K = 16 fp16 = 32 bytes = +2 in the address field
                                 umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (st | k) != 0 ? 1u : 0u);
                         }
-                        umma_commit(&empty_bar[stage]);             // frees the smem stage when the MMAs retire
+                        umma_commit(&empty_bar[stage]);                 // frees the smem stage when the MMAs retire
+                        a_lo += a_step;
+                        b_lo += (uint32_t)(B_BYTES >> 4);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; a_lo = a_lo0; }
                     }
-                    __syncwarp();
-                    a_lo += a_step;
-                    b_lo += (uint32_t)(B_BYTES >> 4);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; a_lo = a_lo0; }
-                }
-            } else {
-                uint32_t started = 0;                               // accumulator groups already written in this tile
-                for (int st = 0; st < steps; ++st) {
-                    const uint32_t cur = pw;
-                    pw = g.prog_mma[st + 1 < steps ? st + 1 : 0];
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    if (elect_one()) {
+                } else {
+                    uint32_t started = 0;                               // accumulator groups already written in this tile
+                    for (int st = 0; st < steps; ++st) {
+                        const uint32_t cur = pw;
+                        pw = g.prog_mma[st + 1 < steps ? st + 1 : 0];
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
                         const uint64_t da = DESC_HI | a_lo;
                         const uint32_t g0 = (cur >> 8) & 0xFu;
                         const uint64_t db = DESC_HI | (b_lo0 + ((cur >> 4) & 0xFu) * (uint32_t)(B_BYTES >> 4));
                         const uint32_t first = ((started >> g0) & 1u) ^ 1u;
-                        if (!g.dbg_skip_mma) {
+                        started |= 1u << g0;
+                        if (!skip_mma) {
 #pragma unroll
                             for (int k = 0; k < GM_BLOCK_K / 16; ++k)
                                 umma_f16(tmem_d + g0 * BLOCK_N, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC,
                                          (k != 0 || !first) ? 1u : 0u);
-                            if ((cur & 0xFu) == 2u) {
-                                const uint32_t g1 = (cur >> 16) & 0xFu;
-                                const uint64_t db1 = DESC_HI | (b_lo0 + ((cur >> 12) & 0xFu) * (uint32_t)(B_BYTES >> 4));
-                                const uint32_t first1 = (((started | (1u << g0)) >> g1) & 1u) ^ 1u;
+                        }
+                        if ((cur & 0xFu) == 2u) {
+                            const uint32_t g1 = (cur >> 16) & 0xFu;
+                            const uint64_t db1 = DESC_HI | (b_lo0 + ((cur >> 12) & 0xFu) * (uint32_t)(B_BYTES >> 4));
+                            const uint32_t first1 = ((started >> g1) & 1u) ^ 1u;
+                            started |= 1u << g1;
+                            if (!skip_mma) {
 #pragma unroll
                                 for (int k = 0; k < GM_BLOCK_K / 16; ++k)
                                     umma_f16(tmem_d + g1 * BLOCK_N, da + (uint64_t)(2 * k), db1 + (uint64_t)(2 * k), IDESC,
@@ -351,43 +366,43 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                             }
                         }
                         umma_commit(&empty_bar[stage]);
+                        a_lo += a_step;
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; a_lo = a_lo0; }
                     }
-                    __syncwarp();
-                    started |= 1u << ((cur >> 8) & 0xFu);
-                    if ((cur & 0xFu) == 2u) started |= 1u << ((cur >> 16) & 0xFu);
-                    a_lo += a_step;
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; a_lo = a_lo0; }
                 }
+                umma_commit(&tfull_bar[acc]);                           // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
-            if (elect_one()) umma_commit(&tfull_bar[acc]);      // accumulator complete
-            __syncwarp();
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
+        __syncwarp();
     } else if (warp >= 4) {
         // ============ epilogue: TMEM -> registers -> swizzled smem -> TMA store ============
-        // Two groups of four warps; group `grp` drains accumulator stage `grp` (every second tile
-        // of this CTA), so one group's staging/TMA-store latency overlaps the other's arithmetic.
-        const int grp = (warp - 4) >> 2;
-        const int ew = (warp - 4) & 3;                          // TMEM lanes 32*ew .. 32*ew+31
+        // Four groups of four warps.  Group (a, h) drains column half h of accumulator stage a (every second
+        // tile of this CTA), in chunks of 32 columns: 16 epilogue warps keep enough arithmetic in flight to hide
+        // the TMEM / shared-memory / barrier latencies, and each group owns its staging tiles, so the only wait
+        // on a TMA store is for the group's own previous chunk, placed after the arithmetic.
+        // The residual tile is fetched by TMA into the fp32 staging tile (coalesced, asynchronous), updated in
+        // place and stored back out by TMA.
+        const int grp = (warp - 4) >> 2;                        // 0..3
+        const int acc = grp >> 1, half = grp & 1;
+        const int ew = warp & 3;                                // TMEM lanes 32*ew .. 32*ew+31
         const int row = ew * 32 + lane;
         const bool store_thread = (ew == 0 && lane == 0);
-        uint8_t *st_f32 = smem + g.epi_off + grp * GM_EPI_BYTES;        // [128][32] fp32, 128B swizzle
-        uint8_t *st_codes = st_f32 + 16384;                             // [128][32] fp16,  64B swizzle
+        uint8_t *st_f32 = smem + g.epi_off + grp * g.epi_group_bytes;   // [128][32] fp32, 128B swizzle
+        uint8_t *st_codes = st_f32 + g.epi_codes_off;                   // [128][32] fp16,  64B swizzle
         const uint32_t sw128 = (uint32_t)(row & 7);             // 16B piece index ^= row % 8
         const uint32_t sw64 = (uint32_t)((row >> 1) & 3);       // 16B piece index ^= (row / 2) % 4
         const Quant nq = make_quant(g.write_codes ? g.next_sf : 1.0f, (float)((1u << g.next_bits) - 1u));
         const bool has_res = g.residual != nullptr;
-        const int acc = grp;
-        uint32_t acc_phase = 0;
+        constexpr int CHUNKS = BLOCK_N / 64;                    // 32-column chunks per group and tile
+        const uint32_t res_bytes = (uint32_t)(g.wbox * g.hbox * g.nbox) * 128u;
+        uint32_t acc_phase = 0, res_phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            if ((it & 1) != grp) continue;
+            if ((it & 1) != acc) continue;
             const int n_tile = tile % g.n_tiles, m_tile = tile / g.n_tiles;
             const int tw = m_tile % g.tiles_w, th = (m_tile / g.tiles_w) % g.tiles_h, tn = m_tile / (g.tiles_w * g.tiles_h);
-            const int wl = row % g.wbox, hl = (row / g.wbox) % g.hbox, nl = row / (g.wbox * g.hbox);
-            const int wo = tw * g.wbox + wl, ho = th * g.hbox + hl, n = tn * g.nbox + nl;
-            const bool valid = nl < g.nbox && n < g.N && ho < g.Ho && wo < g.Wo;
-            const int64_t pix = ((int64_t)n * g.Ho + ho) * g.Wo + wo;
+            const int w0 = tw * g.wbox, h0 = th * g.hbox, n0 = tn * g.nbox;
 
             if (g.dbg_skip_epilogue) {
                 mbar_wait(&tfull_bar[acc], acc_phase);
@@ -398,72 +413,90 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 continue;
             }
 #pragma unroll 1
-            for (int cc = 0; cc < BLOCK_N / 32; ++cc) {
-                const int c0 = n_tile * BLOCK_N + cc * 32;
-                // (a) this group's previous TMA stores must have finished reading the staging tiles
-                if (store_thread) bulk_wait_read0();
-                epi_bar_sync(1 + grp);
-                // (b) residual row lands in the fp32 staging tile (own row only), asynchronously
-                if (has_res && valid) {
-                    const float *src = g.residual + pix * g.Cout + c0;
-#pragma unroll
-                    for (int p = 0; p < 8; ++p)
-                        if (c0 + p * 4 < g.Cout) cp_async16(st_f32 + row * 128 + (((uint32_t)p ^ sw128) << 4), src + p * 4);
+            for (int cc = 0; cc < CHUNKS; ++cc) {
+                const int col0 = half * (BLOCK_N / 2) + cc * 32;            // column of the tile
+                const int c0 = n_tile * BLOCK_N + col0;                     // output channel
+                const bool chunk_live = c0 < g.Cout;
+                // (a) residual tile -> fp32 staging (needs the staging tile free: the previous store has read it)
+                if (has_res && store_thread && chunk_live) {
+                    bulk_wait_read0();
+                    mbar_expect_tx(&res_bar[grp], res_bytes);
+                    tma_load_4d(&tmR, &res_bar[grp], st_f32, c0, w0, h0, n0);
                 }
                 if (cc == 0) {
                     mbar_wait(&tfull_bar[acc], acc_phase);
                     tc_fence_after();
                 }
-                uint32_t v[32];
-                const uint32_t tcol = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * acc_cols + cc * 32);
-                tmem_ld_32x32b_x32(tcol, v);
-                for (int gi = 1; gi < g.n_groups; ++gi) {        // accumulator groups are summed here, in fp32 RN
-                    uint32_t u[32];
-                    tmem_ld_32x32b_x32(tcol + (uint32_t)(gi * BLOCK_N), u);
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__fadd_rn(__uint_as_float(v[e]), __uint_as_float(u[e])));
+                if (!chunk_live) {                               // channels beyond Cout (uniform over the group)
+                    if (cc == CHUNKS - 1) {
+                        tc_fence_before();
+                        mbar_arrive(&tempty_bar[acc]);
+                    }
+                    continue;
                 }
-                if (cc == BLOCK_N / 32 - 1) {                    // accumulator fully drained into registers
+                float t[32];
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t v[16];
+                    const uint32_t tcol = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * acc_cols + col0 + hh * 16);
+                    tmem_ld_32x32b_x16(tcol, v);
+                    for (int gi = 1; gi < g.n_groups; ++gi) {    // accumulator groups are summed here, in fp32 RN
+                        uint32_t u[16];
+                        tmem_ld_32x32b_x16(tcol + (uint32_t)(gi * BLOCK_N), u);
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__fadd_rn(__uint_as_float(v[e]), __uint_as_float(u[e])));
+                    }
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) t[hh * 16 + e] = __fmul_rn(__uint_as_float(v[e]), g.scale);
+                }
+                if (cc == CHUNKS - 1) {                          // this group's share of the accumulator is in registers
                     tc_fence_before();
                     mbar_arrive(&tempty_bar[acc]);
                 }
-                if (has_res) cp_async_wait_all();
-                uint32_t cw[4];                                   // 8 codes = one 16-byte piece
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const int c = c0 + j;
                     const bool cvalid = c < g.Cout;               // Cout % 4 == 0
-                    float t[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) t[e] = __fmul_rn(__uint_as_float(v[j + e]), g.scale);
                     if (g.bias && cvalid) {
                         const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bias + c));
-                        t[0] = __fadd_rn(t[0], b.x); t[1] = __fadd_rn(t[1], b.y);
-                        t[2] = __fadd_rn(t[2], b.z); t[3] = __fadd_rn(t[3], b.w);
+                        t[j] = __fadd_rn(t[j], b.x); t[j + 1] = __fadd_rn(t[j + 1], b.y);
+                        t[j + 2] = __fadd_rn(t[j + 2], b.z); t[j + 3] = __fadd_rn(t[j + 3], b.w);
                     }
                     if (g.bn_a && cvalid) {
                         const float4 a = __ldg(reinterpret_cast<const float4 *>(g.bn_a + c));
                         const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bn_b + c));
-                        t[0] = __fmaf_rn(t[0], a.x, b.x); t[1] = __fmaf_rn(t[1], a.y, b.y);
-                        t[2] = __fmaf_rn(t[2], a.z, b.z); t[3] = __fmaf_rn(t[3], a.w, b.w);
+                        t[j] = __fmaf_rn(t[j], a.x, b.x); t[j + 1] = __fmaf_rn(t[j + 1], a.y, b.y);
+                        t[j + 2] = __fmaf_rn(t[j + 2], a.z, b.z); t[j + 3] = __fmaf_rn(t[j + 3], a.w, b.w);
                     }
+                }
+                // (b) staging: with a residual it already holds this chunk's residual tile; otherwise the previous
+                //     store of this group must have finished reading it before it is overwritten
+                if (has_res) {
+                    mbar_wait(&res_bar[grp], res_phase);
+                } else {
+                    if (store_thread) bulk_wait_read0();
+                    epi_bar_sync(1 + grp);
+                }
+                uint32_t cw[4];                                   // 8 codes = one 16-byte piece
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
                     float4 *slot = reinterpret_cast<float4 *>(st_f32 + row * 128 + (((uint32_t)(j >> 2) ^ sw128) << 4));
-                    if (has_res && valid && cvalid) {
-                        const float4 r = *slot;
-                        t[0] = __fadd_rn(t[0], r.x); t[1] = __fadd_rn(t[1], r.y);
-                        t[2] = __fadd_rn(t[2], r.z); t[3] = __fadd_rn(t[3], r.w);
+                    if (has_res) {
+                        const float4 r = *slot;                   // rows / channels outside the tensor arrive as zeros
+                        t[j] = __fadd_rn(t[j], r.x); t[j + 1] = __fadd_rn(t[j + 1], r.y);
+                        t[j + 2] = __fadd_rn(t[j + 2], r.z); t[j + 3] = __fadd_rn(t[j + 3], r.w);
                     }
                     if (g.relu) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) t[e] = fmaxf(t[e], 0.0f);
+                        for (int e = 0; e < 4; ++e) t[j + e] = fmaxf(t[j + e], 0.0f);
                     }
-                    if (g.write_f32) *slot = make_float4(t[0], t[1], t[2], t[3]);
+                    if (g.write_f32) *slot = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
                     if (g.write_codes) {
                         uint32_t hc[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const uint32_t neg = __float_as_uint(t[e]) >> 31;
-                            const uint32_t q = g.next_fastdiv ? quantize_f32<true>(t[e], nq) : quantize_f32<false>(t[e], nq);
+                            const uint32_t neg = __float_as_uint(t[j + e]) >> 31;
+                            const uint32_t q = g.next_fastdiv ? quantize_f32<true>(t[j + e], nq) : quantize_f32<false>(t[j + e], nq);
                             hc[e] = __half_as_ushort(lut[q | (neg << g.next_bits)]);
                         }
                         const int hi = (j >> 2) & 1;
@@ -476,11 +509,11 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         }
                     }
                 }
+                if (has_res) res_phase ^= 1u;
                 // (c) staging complete: hand it to the async proxy and store
                 fence_proxy_async();
                 epi_bar_sync(1 + grp);
-                if (store_thread && c0 < g.Cout) {
-                    const int w0 = tw * g.wbox, h0 = th * g.hbox, n0 = tn * g.nbox;
+                if (store_thread) {
                     if (g.write_f32) tma_store_4d(&tmC, st_f32, c0, w0, h0, n0);
                     if (g.write_codes) tma_store_4d(&tmD, st_codes, c0, w0, h0, n0);
                     bulk_commit();
@@ -554,7 +587,12 @@ static int plan_smem(ConvGeom &g, int block_n)
     g.stage_bytes = GM_A_BYTES + (prog ? 0 : b_bytes);
     g.bstat_off = 0;
     g.ring_off = prog ? g.nb_tiles * b_bytes : 0;
-    const int fixed = g.ring_off + 2 * GM_EPI_BYTES + (2 << GM_LUT_MAX_BITS) * 2 + 1024 /* barriers */ + 1024 /* align */;
+    // epilogue staging per group: fp32 tile only if an fp32 tile is written or a residual is read, code tile only
+    // if codes are written -- what is not needed goes to the stage ring
+    g.epi_codes_off = (g.write_f32 || g.residual) ? GM_EPI_F32_BYTES : 0;
+    g.epi_group_bytes = g.epi_codes_off + (g.write_codes ? GM_EPI_CODE_BYTES : 0);
+    const int epi_bytes = GM_EPI_GROUPS * g.epi_group_bytes;
+    const int fixed = g.ring_off + epi_bytes + (2 << GM_LUT_MAX_BITS) * 2 + 1024 /* barriers */ + 1024 /* align */;
     int stages = (GM_SMEM_BUDGET - fixed) / g.stage_bytes;
     if (stages > GM_MAX_STAGES) stages = GM_MAX_STAGES;
     static const int cap = getenv("TQ_CONV_STAGES") ? atoi(getenv("TQ_CONV_STAGES")) : GM_MAX_STAGES;
@@ -562,7 +600,7 @@ static int plan_smem(ConvGeom &g, int block_n)
     if (stages < 2) return fail(TQ_ERR_UNSUPPORTED, "shared memory budget: %d resident weight tiles do not fit", g.nb_tiles);
     g.stages = stages;
     g.epi_off = g.ring_off + stages * g.stage_bytes;
-    g.lut_off = g.epi_off + 2 * GM_EPI_BYTES;
+    g.lut_off = g.epi_off + epi_bytes;
     g.bar_off = g.lut_off + (2 << GM_LUT_MAX_BITS) * 2;
     g.smem_total = g.bar_off + 1024 + 1024;
     return TQ_OK;
@@ -570,7 +608,7 @@ static int plan_smem(ConvGeom &g, int block_n)
 
 template <int BLOCK_N, int MODE>
 static int launch_conv_mode(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
-                       const CUtensorMap &tmD, ConvGeom &g, cudaStream_t s)
+                            const CUtensorMap &tmD, const CUtensorMap &tmR, ConvGeom &g, cudaStream_t s)
 {
     static const bool skip_epi = getenv("TQ_CONV_SKIP_EPI") != nullptr;
     g.dbg_skip_epilogue = skip_epi ? 1 : 0;
@@ -588,7 +626,7 @@ static int launch_conv_mode(const CUtensorMap &tmA, const CUtensorMap &tmB, cons
     }
     const int total = g.m_tiles * g.n_tiles;
     const int grid = total < num_sms() ? total : num_sms();
-    kern<<<grid, GM_THREADS, g.smem_total, s>>>(tmA, tmB, tmC, tmD, g);
+    kern<<<grid, GM_THREADS, g.smem_total, s>>>(tmA, tmB, tmC, tmD, tmR, g);
     count_launch();
     return check_launch("conv_igemm_f16_kernel");
 }
@@ -596,16 +634,17 @@ static int launch_conv_mode(const CUtensorMap &tmA, const CUtensorMap &tmB, cons
 // general_prog: the step table (prog_ld / prog_mma) is in use; otherwise resident weights are tile = tap
 template <int BLOCK_N>
 static int launch_conv(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
-                       const CUtensorMap &tmD, ConvGeom &g, cudaStream_t s, bool general_prog = false)
+                       const CUtensorMap &tmD, const CUtensorMap &tmR, ConvGeom &g, cudaStream_t s,
+                       bool general_prog = false)
 {
     if (g.n_groups < 1) g.n_groups = 1;
     if (2 * g.n_groups * BLOCK_N > 512) return fail(TQ_ERR_UNSUPPORTED, "accumulator groups exceed tensor memory");
     int rc = plan_smem(g, BLOCK_N);
     if (rc != TQ_OK) return rc;
-    if (g.prog_steps == 0) return launch_conv_mode<BLOCK_N, 0>(tmA, tmB, tmC, tmD, g, s);
+    if (g.prog_steps == 0) return launch_conv_mode<BLOCK_N, 0>(tmA, tmB, tmC, tmD, tmR, g, s);
     if constexpr (BLOCK_N == 64) {
-        if (general_prog) return launch_conv_mode<64, 2>(tmA, tmB, tmC, tmD, g, s);
-        return launch_conv_mode<64, 1>(tmA, tmB, tmC, tmD, g, s);
+        if (general_prog) return launch_conv_mode<64, 2>(tmA, tmB, tmC, tmD, tmR, g, s);
+        return launch_conv_mode<64, 1>(tmA, tmB, tmC, tmD, tmR, g, s);
     }
     return fail(TQ_ERR_UNSUPPORTED, "resident-weight mode is built for BLOCK_N = 64 only");
 }
@@ -714,9 +753,14 @@ extern "C" int tq_conv2d_codes_fused(const void *act, const void *wgt, float *ou
         if (out_codes) { if ((rc = encode_map(enc, &tmD, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, out_codes, 4, odims, box, one, "code output", CU_TENSOR_MAP_SWIZZLE_64B)) != TQ_OK) return rc; }
         else tmD = tmA;
     }
+    CUtensorMap tmR = tmA;
+    if (residual) {   // residual tile: same box as the fp32 output tile
+        cuuint32_t box[4] = {32, (cuuint32_t)g.wbox, (cuuint32_t)g.hbox, (cuuint32_t)g.nbox};
+        if ((rc = encode_map(enc, &tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, residual, 4, odims, box, one, "residual")) != TQ_OK) return rc;
+    }
     cudaStream_t s = (cudaStream_t)stream;
-    if (block_n == 64) return launch_conv<64>(tmA, tmB, tmC, tmD, g, s);
-    return launch_conv<128>(tmA, tmB, tmC, tmD, g, s);
+    if (block_n == 64) return launch_conv<64>(tmA, tmB, tmC, tmD, tmR, g, s);
+    return launch_conv<128>(tmA, tmB, tmC, tmD, tmR, g, s);
 }
 
 extern "C" int tq_conv2d_codes_f16(const void *act, const void *wgt, const float *bias, float *out,
@@ -847,5 +891,5 @@ extern "C" int tq_stem_conv7x7s2(const float *x, void *x2_scratch, const void *w
     }
     if (g.nbox != 1) return fail(TQ_ERR_UNSUPPORTED, "stem conv expects images of at least 128 output pixels");
     if (block_n != 64) return fail(TQ_ERR_UNSUPPORTED, "stem conv supports Cout <= 64");
-    return launch_conv<64>(tmA, tmB, tmC, tmA, g, s, true);
+    return launch_conv<64>(tmA, tmB, tmC, tmA, tmA, g, s, true);
 }
