@@ -102,7 +102,7 @@ class KernelTimer:
     def __init__(self):
         from term_quantization_b200 import conv_codes, tr_cuda
         self.on = False
-        self.records = {"tr_encode": [], "conv": []}
+        self.records = {"tr_encode": [], "conv": [], "stem": [], "pool": []}
         self.targets = [(tr_cuda, "tr", "tr_encode", lambda a, k, out: a[0].numel() * a[0].element_size() * 2),
                         (tr_cuda, "tr_codes", "tr_encode",
                          lambda a, k, out: a[0].numel() * (a[0].element_size() + out.element_size())),
@@ -110,7 +110,11 @@ class KernelTimer:
                          lambda a, k, out: 2 * out.numel() * a[1].shape[0] * a[1].shape[2]),
                         (conv_codes, "conv2d_codes_fused", "conv",
                          lambda a, k, out: 2 * (out[0] if out[0] is not None else out[1]).numel()
-                         * a[1].shape[0] * a[1].shape[2])]
+                         * a[1].shape[0] * a[1].shape[2]),
+                        (conv_codes, "stem_conv7x7s2", "stem", lambda a, k, out: 2 * out[0].numel() * 147),
+                        (conv_codes, "bn_relu_maxpool_encode", "pool",
+                         lambda a, k, out: a[0].numel() * 4 + out[0].numel() * 4
+                         + (out[1].numel() * 2 if out[1] is not None else 0))]
         self.saved = []
 
     def __enter__(self):
@@ -188,7 +192,10 @@ def run_b200(args):
     model = build_tq_resnet18(dev)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     nbuf = 2
-    images = [torch.randn(BATCH, 3, 224, 224, device=dev, generator=gen) for _ in range(nbuf)]
+    # images travel and are stored as bf16 (BASELINE.json configs[1]: "bf16 -> int8"): synthetic randn
+    # rounded to bf16; --input-dtype fp32 keeps the reference loader's fp32 tensors
+    in_dtype = torch.bfloat16 if (args.input_dtype == "bf16" and args.conv_backend == "fused") else torch.float32
+    images = [torch.randn(BATCH, 3, 224, 224, device=dev, generator=gen).bfloat16().float() for _ in range(nbuf)]
     inference.calibrate(model, [images[0][:64]])          # untimed: histograms + fused sweep
     if args.conv_backend in ("tcgen05", "fused"):
         from term_quantization_b200 import fused, tr_layer
@@ -198,7 +205,10 @@ def run_b200(args):
         assert len(switched) == 19 and not skipped, (switched, skipped)
         if args.conv_backend == "fused":
             model = fused.FusedResNet(model)
-    runner = inference.ShardedInference(model, dev)
+    images = [im.to(in_dtype) for im in images]
+    use_graphs = args.conv_backend == "fused" and not args.no_cuda_graphs
+    runner = inference.ShardedInference(model, dev, cuda_graphs=use_graphs)
+    eager = inference.ShardedInference(model, dev) if use_graphs else runner
 
     def barrier():
         if world > 1:
@@ -211,23 +221,39 @@ def run_b200(args):
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.profiler.start()          # no-op unless ncu runs with --profile-from-start off
+    e0.record()
+    for i in range(args.steps):
+        out = runner.forward(images[i % nbuf])
+    e1.record()
+    barrier()
+    torch.cuda.profiler.stop()
+    ms_total = e0.elapsed_time(e1)
+    out = out.clone()
+    # the same K steps again, launch by launch with CUDA events around every kernel of this repo (the
+    # headline region above runs without them: as CUDA-graph replays when enabled): per-kernel durations
+    # for the roofline objects and the launch count
+    for i in range(args.warmup if use_graphs else 0):      # the eager path's own warm-up (allocator pools)
+        eager.forward(images[i % nbuf])
+    barrier()
     with KernelTimer() as trt:
         trt.on = True
         launches0 = _lib.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        torch.cuda.profiler.start()          # no-op unless ncu runs with --profile-from-start off
-        e0.record()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
         for i in range(args.steps):
-            out = runner.forward(images[i % nbuf])
-        e1.record()
+            eager.forward(images[i % nbuf])
+        k1.record()
         barrier()
-        torch.cuda.profiler.stop()
         launches = _lib.launch_count() - launches0
         trt.on = False
-        ms_total = e0.elapsed_time(e1)
+        ms_instrumented = k0.elapsed_time(k1)
         n_tr, tr_bytes, tr_ms = trt.summary("tr_encode")
         n_cv, cv_flops, cv_ms = trt.summary("conv")
+        n_st, st_flops, st_ms = trt.summary("stem")
+        n_pl, pl_bytes, pl_ms = trt.summary("pool")
     clocks = sampler.finish()
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -236,10 +262,10 @@ def run_b200(args):
     assert out.shape == (BATCH * world, 1000) and bool(torch.isfinite(out).all())
 
     # ---- e2e: pinned host images -> H2D -> forward -> all-gather -> logits D2H -------------
-    host = [torch.randn(BATCH, 3, 224, 224) for _ in range(2)]
+    host = [torch.randn(BATCH, 3, 224, 224).bfloat16().float() for _ in range(2)]
     if args.conv_backend in ("tcgen05", "fused"):
         host = [h.contiguous(memory_format=torch.channels_last) for h in host]
-    host = [h.pin_memory() for h in host]
+    host = [h.to(in_dtype).pin_memory() for h in host]
     slot = runner.stage(host[0])
     for i in range(max(args.warmup, 1)):
         nxt = runner.stage(host[(i + 1) % 2])
@@ -269,7 +295,7 @@ def run_b200(args):
                                                          else "fp32 out: 8 B/elem") + ")",
                    "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                    "traffic": None, "peak_source": peak_src, "launches_timed": n_tr,
-                   "algorithmic_bytes": tr_bytes, "kernel_ms_total": tr_ms, "share_of_step": tr_ms / ms_total}
+                   "algorithmic_bytes": tr_bytes, "kernel_ms_total": tr_ms, "share_of_step": tr_ms / ms_instrumented}
         conv_roof = None
         if n_cv:
             try:
@@ -282,7 +308,8 @@ def run_b200(args):
                                    "fused BN/residual/ReLU/encode epilogue, 19 launches per forward)",
                          "bound": "tensor", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s", "frac": tach / tpeak,
                          "traffic": None, "peak_source": tsrc, "launches_timed": n_cv,
-                         "algorithmic_flops": cv_flops, "kernel_ms_total": cv_ms, "share_of_step": cv_ms / ms_total}
+                         "algorithmic_flops": cv_flops, "kernel_ms_total": cv_ms, "share_of_step": cv_ms / ms_instrumented,
+                         "timed": "CUDA events around each launch in an eager pass of the same K steps"}
         dominant, other = (conv_roof, tr_roof) if (conv_roof and cv_ms > tr_ms) else (tr_roof, conv_roof)
         line = {
             "metric": METRIC, "value": BATCH * world * args.steps / (ms_total * 1e-3),
@@ -290,16 +317,17 @@ def run_b200(args):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": ("int term codes (TR encode) held in f16, f32 accumulate (exact integers) on tcgen05"
                                        if args.conv_backend != "cudnn_fp32" else "f32 values (TR encode); f32 conv"),
-            "data": "synthetic (randn images, random-init torchvision resnet18, seed 0)",
+            "data": "synthetic (randn images rounded to bf16, random-init torchvision resnet18, seed 0)",
             "config": {"workload": "ResNet-18 TQ inference, batch 256 per GPU at 3x224x224 "
                                    "(BASELINE.json configs[1])", **SETTING,
                        "global_batch": BATCH * world, "parallelism": f"batch-sharded x{world}, "
                        "logits all-gather (NCCL)" if world > 1 else "single GPU",
-                       "conv_backend": args.conv_backend,
+                       "conv_backend": args.conv_backend, "input_dtype": str(in_dtype).replace("torch.", ""),
+                       "cuda_graphs": bool(use_graphs),
                        "l2": "activations per step (2.08 GB fp32 through TR) exceed the 126 MB L2; "
                              "input batches rotate between 2 buffers"},
             "e2e": {"value": BATCH * world * args.steps / (e2e_ms * 1e-3), "unit": "images/s",
-                    "h2d_bytes_per_step": BATCH * 3 * 224 * 224 * 4,
+                    "h2d_bytes_per_step": BATCH * 3 * 224 * 224 * host[0].element_size(),
                     "d2h_bytes_per_step": BATCH * world * 1000 * 4,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
@@ -307,6 +335,13 @@ def run_b200(args):
             "roofline": dominant,
             "roofline_other": other,
             "tr_encode": tr_encode_roofline(dev, peak, peak_src),
+            "kernel_ms_per_step": {
+                "note": "CUDA-event time per step of each kernel family in the instrumented eager pass",
+                "conv_igemm_wrapped_convs": cv_ms / args.steps, "conv_igemm_launches_per_step": n_cv // args.steps,
+                "stem_prepare_plus_conv_igemm_stem": st_ms / args.steps,
+                "bn_relu_maxpool_encode": pl_ms / args.steps,
+                "bn_relu_maxpool_encode_GBs": (pl_bytes / (pl_ms * 1e-3) / 1e9) if pl_ms > 0 else None,
+                "tr_elem_standalone": tr_ms / args.steps, "instrumented_step": ms_instrumented / args.steps},
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_images_per_sec(sample_batch=args.cpu_batch, steps=1)
@@ -333,7 +368,7 @@ def cpu_reference_images_per_sec(sample_batch, steps, warmup=0):
     q = ref_stack.convert_cnn(model, SETTING["weight_bits"], SETTING["group_size"], SETTING["weight_terms"],
                               SETTING["data_bits"], SETTING["data_terms"])
     convert_s = time.time() - t0
-    x = torch.randn(sample_batch, 3, 224, 224, generator=torch.Generator().manual_seed(1234))
+    x = torch.randn(sample_batch, 3, 224, 224, generator=torch.Generator().manual_seed(1234)).bfloat16().float()
     # timing-only scale factors (max/2^bits of a tracking pass); logit parity is tested in tests/
     maxes = []
 
@@ -370,7 +405,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.cpu_batch / v,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic (randn images, random-init torchvision resnet18, seed 0)",
+            "data": "synthetic (randn images rounded to bf16, random-init torchvision resnet18, seed 0)",
             "config": {"workload": "ResNet-18 TQ inference, batch 256 per GPU at 3x224x224 "
                                    "(BASELINE.json configs[1])", **SETTING,
                        "note": f"each step is a bounded sample: batch {args.cpu_batch} on the host cores"},
@@ -389,6 +424,9 @@ def main():
                     help="fused: code-domain tcgen05 convs with BN/residual/ReLU/next-layer encode in the "
                          "epilogue (fused.FusedResNet); tcgen05: same kernel layer by layer under the "
                          "unchanged torchvision graph; cudnn_fp32: the reference's float path")
+    ap.add_argument("--input-dtype", default="bf16", choices=["bf16", "fp32"],
+                    help="dtype of the image batches in HBM and over PCIe (fused engine; bf16 per BASELINE configs[1])")
+    ap.add_argument("--no-cuda-graphs", action="store_true", help="launch the forward kernel by kernel")
     ap.add_argument("--cpu-batch", type=int, default=16, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -191,6 +191,11 @@ int tq_bn_relu_maxpool_encode(const float *x, const float *bn_a, const float *bn
  */
 int tq_stem_conv7x7s2(const float *x, void *x2_scratch, const void *w2, float *out,
                       int N, int H, int W, int Cout, void *stream);
+/* Same with the image dtype given (TQ_F32, TQ_BF16 or TQ_F16).  16-bit images are exact in the fp16 hi
+ * plane (down to 2^-14; smaller magnitudes lose < 2^-25 absolute), so the lo image plane and its MMAs are
+ * skipped: x2_scratch then needs N * (H/2+3) * (W/2+3) * 16 fp16. */
+int tq_stem_conv7x7s2_dt(const void *x, int x_dtype, void *x2_scratch, const void *w2, float *out,
+                         int N, int H, int W, int Cout, void *stream);
 
 /*
  * Device self-test: quantises n pseudo-random (a, sf) pairs (sf in [2^-30, 2^30], a over all

@@ -30,6 +30,7 @@ SYMBOLS = {
     "tq_conv2d_codes_fused": (_i, [_p] * 8 + [_i] * 9 + [_f, _i, _f, _i, _i, _p]),
     "tq_bn_relu_maxpool_encode": (_i, [_p] * 5 + [_i] * 5 + [_f, _i, _i, _p]),
     "tq_stem_conv7x7s2": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "tq_stem_conv7x7s2_dt": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _p]),
     "tq_selftest_division": (_i, [C.c_uint64, C.c_uint32, _p, _p]),
 }
 

@@ -107,18 +107,22 @@ def pack_stem_weight(w):
     return torch.cat([hi, lo], dim=0).contiguous()
 
 
+_STEM_DTYPES = {torch.float32: _lib.TQ_F32, torch.bfloat16: _lib.TQ_BF16, torch.float16: _lib.TQ_F16}
+
+
 def stem_conv7x7s2(x_nhwc, w2, scratch=None):
-    """fp32 [N, H, W, 3] -> fp32 [N, H/2, W/2, Cout] (7x7 / stride 2 / pad 3, no bias)."""
-    if x_nhwc.dtype != torch.float32 or not x_nhwc.is_contiguous() or x_nhwc.shape[-1] != 3:
-        raise RuntimeError("stem_conv7x7s2 expects a contiguous fp32 [N, H, W, 3] tensor")
+    """fp32 / bf16 / fp16 [N, H, W, 3] -> fp32 [N, H/2, W/2, Cout] (7x7 / stride 2 / pad 3, no bias)."""
+    if x_nhwc.dtype not in _STEM_DTYPES or not x_nhwc.is_contiguous() or x_nhwc.shape[-1] != 3:
+        raise RuntimeError("stem_conv7x7s2 expects a contiguous fp32 / bf16 / fp16 [N, H, W, 3] tensor")
     N, H, W, _ = x_nhwc.shape
     Cout = w2.shape[1]
-    need = 2 * N * (H // 2 + 3) * (W // 2 + 3) * 16
+    need = (2 if x_nhwc.dtype == torch.float32 else 1) * N * (H // 2 + 3) * (W // 2 + 3) * 16
     if scratch is None or scratch.numel() < need:
         scratch = torch.empty(need, dtype=torch.float16, device=x_nhwc.device)
     out = torch.empty((N, H // 2, W // 2, Cout), dtype=torch.float32, device=x_nhwc.device)
     with torch.cuda.device(x_nhwc.device):
-        rc = _lib.lib().tq_stem_conv7x7s2(x_nhwc.data_ptr(), scratch.data_ptr(), w2.data_ptr(), out.data_ptr(),
-                                          N, H, W, Cout, torch.cuda.current_stream(x_nhwc.device).cuda_stream)
+        rc = _lib.lib().tq_stem_conv7x7s2_dt(x_nhwc.data_ptr(), _STEM_DTYPES[x_nhwc.dtype], scratch.data_ptr(),
+                                             w2.data_ptr(), out.data_ptr(), N, H, W, Cout,
+                                             torch.cuda.current_stream(x_nhwc.device).cuda_stream)
     _lib.check(rc)
     return out, scratch

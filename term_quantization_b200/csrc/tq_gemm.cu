@@ -37,6 +37,8 @@ constexpr int GM_A_BYTES = GM_BLOCK_M * GM_BLOCK_K * 2;
 struct ConvGeom {
     int N, H, W, C, Cout, R, S, stride, pad, Ho, Wo;
     int wbox, hbox, nbox;                       // output pixels per M tile
+    int hw;                                     // pixels per MMA row group: wbox, or wbox + S - 1 in halo mode
+    int halo, halo_baseoff;                     // halo mode (MODE 3); whether to set the descriptor's base-offset field
     int tiles_w, tiles_h, tiles_n;              // M tiles along w, h, image
     int m_tiles, n_tiles, kc_blocks;
     int a_tx_bytes;                             // bytes one A box deposits
@@ -185,6 +187,10 @@ constexpr int GM_SMEM_BUDGET = 227 * 1024;
 // MODE 0: A and B tiles stream through the stage ring.  MODE 1: all weight tiles resident in shared memory
 // (tile = filter tap, one 64-channel block), only A streams.  MODE 2: resident weights + the general step
 // table (several MMA groups / accumulator groups / A planes per step: the hi/lo stem conv).
+// MODE 3: resident weights + ONE halo load per tile (stride-1 convs): the box of (hbox+R-1) x (wbox+S-1)
+// input pixels lands once in shared memory and filter tap (r, s) is the same buffer read from row
+// r * (wbox+S-1) + s on: MMA row m is halo row start + m, i.e. output pixel (m / hw, m % hw), of which the
+// columns m % hw >= wbox are junk and dropped by the epilogue.  A traffic per tile falls from R*S boxes to one.
 template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -257,8 +263,8 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 mbar_expect_tx(bfull_bar, (uint32_t)(g.nb_tiles * B_BYTES));
                 for (int t = 0; t < g.nb_tiles; ++t) tma_load_3d(&tmB, bfull_bar, bstat + t * B_BYTES, 0, 0, t);
             }
-            const int steps = prog ? g.prog_steps : kblocks;
-            const int S = g.S, kc_blocks = g.kc_blocks, stage_bytes = g.stage_bytes;
+            const int steps = MODE == 3 ? g.kc_blocks : (prog ? g.prog_steps : kblocks);
+            const int S = MODE == 3 ? 1 : g.S, kc_blocks = g.kc_blocks, stage_bytes = g.stage_bytes;
             const uint32_t tx_bytes = (uint32_t)g.a_tx_bytes + (prog ? 0u : (uint32_t)B_BYTES);
             const bool skip_tma = g.dbg_skip_tma != 0;
             uint32_t pw = MODE == 2 ? g.prog_ld[0] : 0u;
@@ -318,7 +324,32 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
-                if constexpr (MODE != 2) {
+                if constexpr (MODE == 3) {
+                    const int taps = g.R * g.S, S = g.S, kcb = g.kc_blocks;
+                    const uint32_t row_step = (uint32_t)g.hw * 8u;      // one halo row of pixels, in 16-byte units
+                    for (int kc = 0; kc < kcb; ++kc) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        uint32_t a_row = a_lo, b_lo = b_lo0 + (uint32_t)kc * (uint32_t)(B_BYTES >> 4);
+                        int s = 0;
+                        for (int tap = 0; tap < taps; ++tap) {
+                            const uint32_t a_tap = a_row + (uint32_t)s * 8u;
+                            uint64_t da = DESC_HI | a_tap;
+                            if (g.halo_baseoff) da |= (uint64_t)((a_tap >> 3) & 7u) << 49;
+                            const uint64_t db = DESC_HI | b_lo;
+                            if (!skip_mma) {
+#pragma unroll
+                                for (int k = 0; k < GM_BLOCK_K / 16; ++k)
+                                    umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kc | tap | k) != 0 ? 1u : 0u);
+                            }
+                            b_lo += (uint32_t)kcb * (uint32_t)(B_BYTES >> 4);
+                            if (++s == S) { s = 0; a_row += row_step; }
+                        }
+                        umma_commit(&empty_bar[stage]);
+                        a_lo += a_step;
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; a_lo = a_lo0; }
+                    }
+                } else if constexpr (MODE != 2) {
                     uint32_t b_lo = b_lo0;                              // MODE 1: resident tile of this step
                     for (int st = 0; st < steps; ++st) {
                         mbar_wait(&full_bar[stage], phase);
@@ -386,7 +417,11 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int grp = (warp - 4) >> 2;                        // 0..3
         const int acc = grp >> 1, half = grp & 1;
         const int ew = warp & 3;                                // TMEM lanes 32*ew .. 32*ew+31
-        const int row = ew * 32 + lane;
+        const int mrow = ew * 32 + lane;                        // accumulator row = TMEM lane
+        // staging row of this accumulator row: dense (hbox x wbox) pixel order; in halo mode the columns
+        // mrow % hw >= wbox are junk and write nothing
+        const int row = (mrow / g.hw) * g.wbox + (mrow % g.hw);
+        const bool row_live = (mrow % g.hw) < g.wbox && row < 128;
         const bool store_thread = (ew == 0 && lane == 0);
         uint8_t *st_f32 = smem + g.epi_off + grp * g.epi_group_bytes;   // [128][32] fp32, 128B swizzle
         uint8_t *st_codes = st_f32 + g.epi_codes_off;                   // [128][32] fp16,  64B swizzle
@@ -481,6 +516,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     float4 *slot = reinterpret_cast<float4 *>(st_f32 + row * 128 + (((uint32_t)(j >> 2) ^ sw128) << 4));
+                    if (!row_live) continue;
                     if (has_res) {
                         const float4 r = *slot;                   // rows / channels outside the tensor arrive as zeros
                         t[j] = __fadd_rn(t[j], r.x); t[j + 1] = __fadd_rn(t[j + 1], r.y);
@@ -579,12 +615,40 @@ static void pick_box(ConvGeom &g)
     g.a_tx_bytes = g.wbox * g.hbox * g.nbox * GM_BLOCK_K * 2;
 }
 
+// halo mode: the pixel box (wbox x hbox, one image) whose rows, laid out (wbox + S - 1) pixels apart, fit
+// 128 accumulator rows; fewest tiles first, then the smallest halo
+static bool pick_box_halo(ConvGeom &g)
+{
+    long best = -1, best_halo = 0;
+    int bw = 0, bh = 0;
+    for (int wb = 1; wb <= g.Wo; ++wb) {
+        const int hw = wb + g.S - 1;
+        if (hw > 128 || hw > 256) break;
+        int hb = 128 / hw;
+        if (hb > g.Ho) hb = g.Ho;
+        if (hb < 1 || hb + g.R - 1 > 256) continue;
+        const long tiles = (long)((g.Wo + wb - 1) / wb) * ((g.Ho + hb - 1) / hb) * g.N;
+        const long halo = (long)hw * (hb + g.R - 1);
+        if (best < 0 || tiles < best || (tiles == best && halo < best_halo)) { best = tiles; best_halo = halo; bw = wb; bh = hb; }
+    }
+    if (best < 0) return false;
+    g.wbox = bw; g.hbox = bh; g.nbox = 1;
+    g.hw = bw + g.S - 1;
+    g.tiles_w = (g.Wo + bw - 1) / bw;
+    g.tiles_h = (g.Ho + bh - 1) / bh;
+    g.tiles_n = g.N;
+    g.m_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
+    g.a_tx_bytes = g.hw * (bh + g.R - 1) * GM_BLOCK_K * 2;
+    return true;
+}
+
 // carve shared memory: [stationary B][stage ring][2 x epilogue staging][LUT][barriers]
 static int plan_smem(ConvGeom &g, int block_n)
 {
     const int b_bytes = block_n * GM_BLOCK_K * 2;
     const bool prog = g.prog_steps > 0;
     g.stage_bytes = GM_A_BYTES + (prog ? 0 : b_bytes);
+    if (g.halo) g.stage_bytes = (g.a_tx_bytes + 1023) & ~1023;
     g.bstat_off = 0;
     g.ring_off = prog ? g.nb_tiles * b_bytes : 0;
     // epilogue staging per group: fp32 tile only if an fp32 tile is written or a residual is read, code tile only
@@ -644,6 +708,7 @@ static int launch_conv(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUt
     if (g.prog_steps == 0) return launch_conv_mode<BLOCK_N, 0>(tmA, tmB, tmC, tmD, tmR, g, s);
     if constexpr (BLOCK_N == 64) {
         if (general_prog) return launch_conv_mode<64, 2>(tmA, tmB, tmC, tmD, tmR, g, s);
+        if (g.halo) return launch_conv_mode<64, 3>(tmA, tmB, tmC, tmD, tmR, g, s);
         return launch_conv_mode<64, 1>(tmA, tmB, tmC, tmD, tmR, g, s);
     }
     return fail(TQ_ERR_UNSUPPORTED, "resident-weight mode is built for BLOCK_N = 64 only");
@@ -699,6 +764,7 @@ extern "C" int tq_conv2d_codes_fused(const void *act, const void *wgt, float *ou
     g.scale = scale;
     g.kc_blocks = (C + GM_BLOCK_K - 1) / GM_BLOCK_K;
     pick_box(g);
+    g.hw = g.wbox;
     const int block_n = Cout <= 64 ? 64 : 128;
     g.n_tiles = (Cout + block_n - 1) / block_n;
     g.bias = bias; g.bn_a = bn_a; g.bn_b = bn_b; g.residual = residual;
@@ -716,6 +782,20 @@ extern "C" int tq_conv2d_codes_fused(const void *act, const void *wgt, float *ou
     if (!no_prog && Cout <= 64 && taps <= 12) {
         g.prog_steps = taps;
         g.nb_tiles = taps;
+        // stride-1 filters wider than 1x1 on maps big enough to fill the tile: one halo load per tile
+        static const bool no_halo = getenv("TQ_CONV_NO_HALO") != nullptr;
+        // The UMMA 128-byte swizzle is a function of the absolute shared-memory address (as TMA's is for a
+        // 1024-byte aligned box), so a descriptor may start at any 128-byte row of a swizzled buffer with the
+        // base-offset field left 0 (measured: with base offset = (addr >> 7) & 7 the results are wrong).
+        static const bool halo_baseoff = getenv("TQ_CONV_HALO_BASEOFF") ? atoi(getenv("TQ_CONV_HALO_BASEOFF")) != 0 : false;
+        if (!no_halo && g.kc_blocks == 1 && stride == 1 && R * S > 1) {
+            ConvGeom h = g;
+            if (pick_box_halo(h) && h.m_tiles <= g.m_tiles + g.m_tiles / 8) {
+                g = h;
+                g.halo = 1;
+                g.halo_baseoff = halo_baseoff ? 1 : 0;
+            }
+        }
     }
 
     CUtensorMap tmA, tmB, tmC, tmD;
@@ -723,6 +803,7 @@ extern "C" int tq_conv2d_codes_fused(const void *act, const void *wgt, float *ou
     {   // activations: (C, W, H, N) fp16; box spans wbox*stride x hbox*stride pixels, element strides = conv stride
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
         cuuint32_t box[4] = {(cuuint32_t)GM_BLOCK_K, (cuuint32_t)(g.wbox * stride), (cuuint32_t)(g.hbox * stride), (cuuint32_t)g.nbox};
+        if (g.halo) { box[1] = (cuuint32_t)g.hw; box[2] = (cuuint32_t)(g.hbox + R - 1); }
         cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
         if ((rc = encode_map(enc, &tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, act, 4, dims, box, estr, "activations")) != TQ_OK) return rc;
     }
@@ -735,6 +816,7 @@ extern "C" int tq_conv2d_codes_fused(const void *act, const void *wgt, float *ou
     } else {   // weights: (C, Cout, R*S) fp16
         g.prog_steps = 0;                                  // (program mode needs one channel block per tap)
         g.nb_tiles = 0;
+        g.halo = 0;
         cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Cout, (cuuint64_t)(R * S)};
         cuuint32_t box[3] = {(cuuint32_t)GM_BLOCK_K, (cuuint32_t)block_n, 1};
         cuuint32_t estr[3] = {1, 1, 1};
@@ -789,10 +871,12 @@ extern "C" int tq_conv2d_codes_f16(const void *act, const void *wgt, const float
 // =============================================================================================
 namespace tq {
 
+template <typename Tin, bool LO>
 __global__ void __launch_bounds__(256)
-stem_prepare_kernel(const float *__restrict__ x, __half *__restrict__ x2, int N, int H, int W, int Hs, int Ws)
+stem_prepare_kernel(const Tin *__restrict__ x, __half *__restrict__ x2, int N, int H, int W, int Hs, int Ws)
 {
-    // one thread per folded pixel (n, hs, ws): 16 halves hi + 16 halves lo
+    // one thread per folded pixel (n, hs, ws): 16 halves hi (+ 16 halves lo for fp32 input; bf16 / fp16
+    // images are fp16-exact down to 2^-14, below that the residue is < 2^-25 absolute and is dropped)
     const int64_t total = (int64_t)N * Hs * Ws;
     const int64_t plane = total * 16;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -805,25 +889,30 @@ stem_prepare_kernel(const float *__restrict__ x, __half *__restrict__ x2, int N,
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 float v = 0.0f;
-                if (in && c < 3) v = __ldg(x + (((int64_t)n * H + h) * W + w) * 3 + c);
+                if (in && c < 3) v = Elem<Tin>::to_f32(x[(((int64_t)n * H + h) * W + w) * 3 + c]);
                 const __half vh = __float2half_rn(v);
                 hi[d * 4 + c] = vh;
-                lo[d * 4 + c] = __float2half_rn(v - __half2float(vh));
+                if (LO) lo[d * 4 + c] = __float2half_rn(v - __half2float(vh));
             }
         }
         uint4 *dh = reinterpret_cast<uint4 *>(x2 + t * 16);
-        uint4 *dl = reinterpret_cast<uint4 *>(x2 + plane + t * 16);
         dh[0] = reinterpret_cast<const uint4 *>(hi)[0]; dh[1] = reinterpret_cast<const uint4 *>(hi)[1];
-        dl[0] = reinterpret_cast<const uint4 *>(lo)[0]; dl[1] = reinterpret_cast<const uint4 *>(lo)[1];
+        if (LO) {
+            uint4 *dl = reinterpret_cast<uint4 *>(x2 + plane + t * 16);
+            dl[0] = reinterpret_cast<const uint4 *>(lo)[0]; dl[1] = reinterpret_cast<const uint4 *>(lo)[1];
+        }
     }
 }
 
 }  // namespace tq
 
-extern "C" int tq_stem_conv7x7s2(const float *x, void *x2_scratch, const void *w2, float *out,
-                                 int N, int H, int W, int Cout, void *stream)
+extern "C" int tq_stem_conv7x7s2_dt(const void *x, int x_dtype, void *x2_scratch, const void *w2, float *out,
+                                    int N, int H, int W, int Cout, void *stream)
 {
     if (!x || !x2_scratch || !w2 || !out) return fail(TQ_ERR_INVALID, "NULL pointer");
+    if (x_dtype != TQ_F32 && x_dtype != TQ_BF16 && x_dtype != TQ_F16)
+        return fail(TQ_ERR_UNSUPPORTED, "stem conv input must be fp32, bf16 or fp16");
+    const bool lo_plane = x_dtype == TQ_F32;
     if (N < 1 || H < 2 || W < 2 || (H & 1) || (W & 1)) return fail(TQ_ERR_INVALID, "H and W must be even");
     if (Cout < 4 || Cout % 4) return fail(TQ_ERR_UNSUPPORTED, "Cout must be a multiple of 4");
     if ((((uintptr_t)x2_scratch | (uintptr_t)w2 | (uintptr_t)out) & 15u) != 0)
@@ -837,7 +926,12 @@ extern "C" int tq_stem_conv7x7s2(const float *x, void *x2_scratch, const void *w
         const int64_t total = (int64_t)N * Hs * Ws;
         int64_t blocks = (total + 255) / 256;
         if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
-        stem_prepare_kernel<<<(int)blocks, 256, 0, s>>>(x, (__half *)x2_scratch, N, H, W, Hs, Ws);
+        if (x_dtype == TQ_F32)
+            stem_prepare_kernel<float, true><<<(int)blocks, 256, 0, s>>>((const float *)x, (__half *)x2_scratch, N, H, W, Hs, Ws);
+        else if (x_dtype == TQ_BF16)
+            stem_prepare_kernel<__nv_bfloat16, false><<<(int)blocks, 256, 0, s>>>((const __nv_bfloat16 *)x, (__half *)x2_scratch, N, H, W, Hs, Ws);
+        else
+            stem_prepare_kernel<__half, false><<<(int)blocks, 256, 0, s>>>((const __half *)x, (__half *)x2_scratch, N, H, W, Hs, Ws);
         count_launch();
         int rc = check_launch("stem_prepare_kernel");
         if (rc != TQ_OK) return rc;
@@ -849,6 +943,7 @@ extern "C" int tq_stem_conv7x7s2(const float *x, void *x2_scratch, const void *w
     g.scale = 1.0f;
     g.kc_blocks = 1;
     pick_box(g);
+    g.hw = g.wbox;
     const int block_n = Cout <= 64 ? 64 : 128;
     g.n_tiles = (Cout + block_n - 1) / block_n;
     g.write_f32 = 1;
@@ -857,7 +952,7 @@ extern "C" int tq_stem_conv7x7s2(const float *x, void *x2_scratch, const void *w
     // accumulator) and one of x_lo (w_hi -> cross).  The main accumulator is split in two (rows 0-1 / 2-3):
     // tensor-core accumulation truncates, so fewer steps per accumulator = less bias; the small cross terms
     // live apart from the large ones and everything is summed once, in fp32 RN, in the epilogue.
-    g.prog_steps = 8; g.nb_tiles = 8; g.n_groups = 3;
+    g.prog_steps = lo_plane ? 8 : 4; g.nb_tiles = 8; g.n_groups = 3;
     for (uint32_t R = 0; R < 4; ++R) {
         g.prog_ld[R] = R << 8;                                              // x_hi, filter row R
         g.prog_mma[R] = 2u | (R << 4) | ((R < 2 ? 0u : 1u) << 8) | ((4u + R) << 12) | (2u << 16);
@@ -868,7 +963,7 @@ extern "C" int tq_stem_conv7x7s2(const float *x, void *x2_scratch, const void *w
     CUtensorMap tmA, tmB, tmC;
     int rc;
     {   // overlapping windows: inner 64 elements, output column advances by one folded pixel (16 elements)
-        cuuint64_t dims[4] = {64, (cuuint64_t)Wo, (cuuint64_t)Hs, (cuuint64_t)(2 * N)};
+        cuuint64_t dims[4] = {64, (cuuint64_t)Wo, (cuuint64_t)Hs, (cuuint64_t)((lo_plane ? 2 : 1) * N)};
         cuuint64_t strides[3] = {32, (cuuint64_t)Ws * 32, (cuuint64_t)Hs * Ws * 32};
         cuuint32_t box[4] = {64, (cuuint32_t)g.wbox, (cuuint32_t)g.hbox, (cuuint32_t)g.nbox};
         cuuint32_t one[4] = {1, 1, 1, 1};
@@ -892,4 +987,10 @@ extern "C" int tq_stem_conv7x7s2(const float *x, void *x2_scratch, const void *w
     if (g.nbox != 1) return fail(TQ_ERR_UNSUPPORTED, "stem conv expects images of at least 128 output pixels");
     if (block_n != 64) return fail(TQ_ERR_UNSUPPORTED, "stem conv supports Cout <= 64");
     return launch_conv<64>(tmA, tmB, tmC, tmA, tmA, g, s, true);
+}
+
+extern "C" int tq_stem_conv7x7s2(const float *x, void *x2_scratch, const void *w2, float *out,
+                                 int N, int H, int W, int Cout, void *stream)
+{
+    return tq_stem_conv7x7s2_dt(x, TQ_F32, x2_scratch, w2, out, N, H, W, Cout, stream);
 }

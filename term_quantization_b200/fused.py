@@ -102,6 +102,8 @@ class FusedResNet(nn.Module):
 
     @torch.no_grad()
     def forward(self, x):
+        """x: [N, 3, H, W] images, fp32 or bf16 / fp16 (16-bit images are used as they are: the values the
+        reference would see after `images.float()`), any memory format (channels_last avoids a copy)."""
         m = self.model
         x = x.contiguous(memory_format=torch.channels_last)
         if self.fuse_stem:
@@ -112,11 +114,11 @@ class FusedResNet(nn.Module):
                 y, self._stem_scratch = conv_codes.stem_conv7x7s2(x.permute(0, 2, 3, 1), self.stem_w,
                                                                   self._stem_scratch)
             else:
-                y = m.conv1(x).permute(0, 2, 3, 1)
+                y = m.conv1(x.float()).permute(0, 2, 3, 1)
             cur, c0 = conv_codes.bn_relu_maxpool_encode(y, self.stem_bn, relu=True, next_quant=q0)
             codes = {q0: c0}                             # quantiser -> fp16 codes of `cur`
         else:
-            x = m.maxpool(m.relu(m.bn1(m.conv1(x))))
+            x = m.maxpool(m.relu(m.bn1(m.conv1(x.float()))))
             cur = x.permute(0, 2, 3, 1)                  # fp32 [N, H, W, C], contiguous
             codes = {}
         for i, (c1, c2, down) in enumerate(self.blocks):

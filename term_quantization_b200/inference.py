@@ -67,8 +67,10 @@ class ShardedInference:
     copy stream, overlapping the previous step's compute) and the device->host read of the
     gathered logits."""
 
-    def __init__(self, model, device, group=None):
+    def __init__(self, model, device, group=None, cuda_graphs=False):
         self.model = model.eval()
+        self.cuda_graphs = bool(cuda_graphs)
+        self._graphs = {}
         self.device = torch.device(device)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -80,8 +82,31 @@ class ShardedInference:
         self._host_out = None
 
     @torch.no_grad()
+    def _local_forward(self, images_dev):
+        """The model on this rank's shard.  With cuda_graphs=True the forward is captured once per input
+        buffer (address, shape, dtype) and replayed: ~25 kernel launches become one graph launch.  The
+        returned logits are then a static buffer, overwritten by the next replay of the same graph."""
+        if not self.cuda_graphs:
+            return self.model(images_dev)
+        key = (images_dev.data_ptr(), tuple(images_dev.shape), tuple(images_dev.stride()), images_dev.dtype)
+        entry = self._graphs.get(key)
+        if entry is None:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):                      # allocator / lazy-init warm-up outside the capture
+                    self.model(images_dev)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.model(images_dev)
+            entry = self._graphs[key] = (graph, out, images_dev)    # keeps the input buffer alive
+        entry[0].replay()
+        return entry[1]
+
+    @torch.no_grad()
     def forward(self, images_dev):
-        return gather_logits(self.model(images_dev), self.group)
+        return gather_logits(self._local_forward(images_dev), self.group)
 
     def stage(self, pinned):
         """Start the host->device copy of a pinned shard on the copy stream; returns the slot.

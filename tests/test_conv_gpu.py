@@ -19,6 +19,12 @@ CASES = [
     (3, 14, 14, 256, 512, 1, 2, 0),
     (1, 9, 13, 72, 68, 3, 1, 1),            # ragged: C % 64 != 0, Cout % 64 != 0, odd image
     (2, 5, 5, 8, 4, 5, 1, 2),
+    # resident-weight + halo mode (Cout <= 64, one channel block, stride 1): ragged maps, narrow channels
+    (1, 9, 13, 64, 64, 3, 1, 1),
+    (2, 20, 33, 32, 40, 3, 1, 1),
+    (2, 17, 17, 16, 8, 3, 1, 1),
+    (2, 30, 31, 64, 64, 2, 1, 0),
+    (1, 130, 70, 48, 64, 3, 1, 1),
 ]
 
 
@@ -44,7 +50,8 @@ def test_conv_codes_exact_accumulators(case):
 
 
 FUSED = [(2, 56, 56, 64, 64, 3, 1, 1), (3, 28, 28, 128, 128, 3, 1, 1), (2, 56, 56, 64, 128, 1, 2, 0),
-         (5, 7, 7, 512, 512, 3, 1, 1), (1, 9, 13, 72, 72, 3, 1, 1), (3, 14, 14, 256, 256, 3, 1, 1)]
+         (5, 7, 7, 512, 512, 3, 1, 1), (1, 9, 13, 72, 72, 3, 1, 1), (3, 14, 14, 256, 256, 3, 1, 1),
+         (2, 20, 33, 32, 40, 3, 1, 1), (1, 57, 29, 64, 64, 3, 1, 1)]
 
 
 @pytest.mark.parametrize("case", FUSED)
@@ -129,3 +136,9 @@ def test_stem_conv_tensor_cores_fp32_accuracy():
         # tensor-core fp32 accumulation truncates (48 accumulate steps): ~2e-6 of the output range,
         # against ~3e-7 for an fp32 FMA chain; TF32 would be ~1e-3
         assert e_mine < 5e-6
+        # 16-bit images: the same values reach the MMAs through the hi plane alone
+        for dt in (torch.bfloat16, torch.float16):
+            x16 = x.permute(0, 2, 3, 1).to(dt).contiguous()
+            want16 = F.conv2d(x16.permute(0, 3, 1, 2).double(), w.double(), None, 2, 3).permute(0, 2, 3, 1)
+            got16, _ = conv_codes.stem_conv7x7s2(x16, conv_codes.pack_stem_weight(w))
+            assert float((got16.double() - want16).abs().max()) / scale < 5e-6
