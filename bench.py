@@ -112,6 +112,7 @@ class KernelTimer:
                          lambda a, k, out: 2 * (out[0] if out[0] is not None else out[1]).numel()
                          * a[1].shape[0] * a[1].shape[2]),
                         (conv_codes, "stem_conv7x7s2", "stem", lambda a, k, out: 2 * out[0].numel() * 147),
+                        (conv_codes, "stem_conv_pool", "stem", lambda a, k, out: 2 * out[0].numel() * 4 * 147),
                         (conv_codes, "bn_relu_maxpool_encode", "pool",
                          lambda a, k, out: a[0].numel() * 4 + out[0].numel() * 4
                          + (out[1].numel() * 2 if out[1] is not None else 0))]
@@ -338,7 +339,7 @@ def run_b200(args):
             "kernel_ms_per_step": {
                 "note": "CUDA-event time per step of each kernel family in the instrumented eager pass",
                 "conv_igemm_wrapped_convs": cv_ms / args.steps, "conv_igemm_launches_per_step": n_cv // args.steps,
-                "stem_prepare_plus_conv_igemm_stem": st_ms / args.steps,
+                "stem_prepare_plus_conv_igemm_stem_with_fused_pool": st_ms / args.steps,
                 "bn_relu_maxpool_encode": pl_ms / args.steps,
                 "bn_relu_maxpool_encode_GBs": (pl_bytes / (pl_ms * 1e-3) / 1e9) if pl_ms > 0 else None,
                 "tr_elem_standalone": tr_ms / args.steps, "instrumented_step": ms_instrumented / args.steps},

@@ -196,6 +196,17 @@ int tq_stem_conv7x7s2(const float *x, void *x2_scratch, const void *w2, float *o
  * skipped: x2_scratch then needs N * (H/2+3) * (W/2+3) * 16 fp16. */
 int tq_stem_conv7x7s2_dt(const void *x, int x_dtype, void *x2_scratch, const void *w2, float *out,
                          int N, int H, int W, int Cout, void *stream);
+/*
+ * The whole unquantised stem in one tensor-core kernel: conv 7x7/s2/p3 -> per-channel affine (BatchNorm) ->
+ * ReLU (if relu) -> max-pool 3x3/s2/p1 -> fp32 NHWC [N, Hp, Wp, Cout] (Hp = (H/2 - 1)/2 + 1) and, if out_codes,
+ * the fp16 term codes of that tensor for the first wrapped conv's quantiser (tr_layer.py:96-99).  Each tile
+ * computes the (2P+1) x (2Q+1) conv pixels under P x Q pooled pixels, so the conv output (822 MB at batch 256)
+ * never reaches HBM.  Same values as tq_stem_conv7x7s2_dt followed by tq_bn_relu_maxpool_encode.
+ */
+int tq_stem_conv7x7s2_pool(const void *x, int x_dtype, void *x2_scratch, const void *w2,
+                           const float *bn_a, const float *bn_b, int relu, float *out, void *out_codes,
+                           int N, int H, int W, int Cout, float next_sf, int next_bits, int next_terms,
+                           void *stream);
 
 /*
  * Device self-test: quantises n pseudo-random (a, sf) pairs (sf in [2^-30, 2^30], a over all

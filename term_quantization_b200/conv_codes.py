@@ -126,3 +126,29 @@ def stem_conv7x7s2(x_nhwc, w2, scratch=None):
                                              torch.cuda.current_stream(x_nhwc.device).cuda_stream)
     _lib.check(rc)
     return out, scratch
+
+
+def stem_conv_pool(x_nhwc, w2, bn, relu=True, next_quant=None, scratch=None):
+    """The whole stem in one launch: maxpool3x3/s2/p1(relu(fma(conv7x7s2(x), a, b))) -> fp32
+    [N, Hp, Wp, Cout] plus the fp16 term codes of the result (next_quant = (sf, bits, terms)).
+    Same values as stem_conv7x7s2 followed by bn_relu_maxpool_encode; the conv output never reaches HBM.
+    Returns (out, codes or None, scratch)."""
+    if x_nhwc.dtype not in _STEM_DTYPES or not x_nhwc.is_contiguous() or x_nhwc.shape[-1] != 3:
+        raise RuntimeError("stem_conv_pool expects a contiguous fp32 / bf16 / fp16 [N, H, W, 3] tensor")
+    N, H, W, _ = x_nhwc.shape
+    Cout = w2.shape[1]
+    need = (2 if x_nhwc.dtype == torch.float32 else 1) * N * (H // 2 + 3) * (W // 2 + 3) * 16
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty(need, dtype=torch.float16, device=x_nhwc.device)
+    Hp, Wp = (H // 2 - 1) // 2 + 1, (W // 2 - 1) // 2 + 1
+    out = torch.empty((N, Hp, Wp, Cout), dtype=torch.float32, device=x_nhwc.device)
+    codes = torch.empty((N, Hp, Wp, Cout), dtype=torch.float16, device=x_nhwc.device) if next_quant else None
+    sf, bits, terms = next_quant if next_quant else (1.0, 1, 0)
+    with torch.cuda.device(x_nhwc.device):
+        rc = _lib.lib().tq_stem_conv7x7s2_pool(
+            x_nhwc.data_ptr(), _STEM_DTYPES[x_nhwc.dtype], scratch.data_ptr(), w2.data_ptr(),
+            bn[0].data_ptr(), bn[1].data_ptr(), int(bool(relu)), out.data_ptr(),
+            codes.data_ptr() if codes is not None else None, N, H, W, Cout, float(sf), int(bits), int(terms),
+            torch.cuda.current_stream(x_nhwc.device).cuda_stream)
+    _lib.check(rc)
+    return out, codes, scratch

@@ -38,6 +38,8 @@ struct ConvGeom {
     int N, H, W, C, Cout, R, S, stride, pad, Ho, Wo;
     int wbox, hbox, nbox;                       // output pixels per M tile
     int hw;                                     // pixels per MMA row group: wbox, or wbox + S - 1 in halo mode
+    int step_w, step_h, off_w, off_h;           // tile origin in output pixels: (tw * step_w + off_w, th * step_h + off_h)
+    int pool, pool_p, pool_q;                   // fused 3x3/s2/p1 max-pool (stem): pooled pixels per tile
     int halo, halo_baseoff;                     // halo mode (MODE 3); whether to set the descriptor's base-offset field
     int tiles_w, tiles_h, tiles_n;              // M tiles along w, h, image
     int m_tiles, n_tiles, kc_blocks;
@@ -50,11 +52,9 @@ struct ConvGeom {
     int prog_steps, nb_tiles, n_groups;
     int dbg_skip_epilogue;      // profiling aid (TQ_CONV_SKIP_EPI=1): drain accumulators without storing
     int dbg_skip_mma, dbg_skip_tma;   // TQ_CONV_SKIP_MMA / TQ_CONV_SKIP_TMA: isolate the load and the MMA pipelines
-    // one packed word per step for each of the two control warps (a single indexed constant load per step):
-    //   prog_ld : dw | dh << 8 | kc << 16 | plane << 24   (A box offset = filter tap, 64-channel block, A plane
-    //             stacked along N: coordinate n0 + plane * N)
-    //   prog_mma: n_mma | b_tile0 << 4 | group0 << 8 | b_tile1 << 12 | group1 << 16
-    uint32_t prog_ld[16], prog_mma[16];
+    // MODE 2 step table, one packed word per (A plane, filter row), planes stacked along N (coordinate
+    // n0 + plane * N):   n_mma | b_tile0 << 4 | group0 << 8 | b_tile1 << 12 | group1 << 16
+    uint32_t prog_mma[16];
     // fused epilogue (all optional):  t = acc*scale (+bias) ; t = fma(t, bn_a, bn_b) ; t += residual ;
     // t = max(t, 0) ; fp32 tile out (TMA store) ; fp16 term codes of t for the next layer (TMA store)
     const float *bias, *bn_a, *bn_b, *residual;
@@ -185,8 +185,9 @@ constexpr int GM_EPI_CODE_BYTES = 8192;         // per epilogue group: [128][32]
 constexpr int GM_SMEM_BUDGET = 227 * 1024;
 
 // MODE 0: A and B tiles stream through the stage ring.  MODE 1: all weight tiles resident in shared memory
-// (tile = filter tap, one 64-channel block), only A streams.  MODE 2: resident weights + the general step
-// table (several MMA groups / accumulator groups / A planes per step: the hi/lo stem conv).
+// (tile = filter tap, one 64-channel block), only A streams.  MODE 2 (the hi/lo stem conv): resident weights,
+// one halo load per A plane (x_hi, x_lo) covering all R filter rows, and a step table naming, per
+// (plane, filter row), one or two MMA groups = (resident weight tile, accumulator group).
 // MODE 3: resident weights + ONE halo load per tile (stride-1 convs): the box of (hbox+R-1) x (wbox+S-1)
 // input pixels lands once in shared memory and filter tap (r, s) is the same buffer read from row
 // r * (wbox+S-1) + s on: MMA row m is halo row start + m, i.e. output pixel (m / hw, m % hw), of which the
@@ -263,24 +264,20 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 mbar_expect_tx(bfull_bar, (uint32_t)(g.nb_tiles * B_BYTES));
                 for (int t = 0; t < g.nb_tiles; ++t) tma_load_3d(&tmB, bfull_bar, bstat + t * B_BYTES, 0, 0, t);
             }
-            const int steps = MODE == 3 ? g.kc_blocks : (prog ? g.prog_steps : kblocks);
+            const int steps = MODE == 3 ? g.kc_blocks : (MODE == 2 ? g.prog_steps / g.R : (prog ? g.prog_steps : kblocks));
             const int S = MODE == 3 ? 1 : g.S, kc_blocks = g.kc_blocks, stage_bytes = g.stage_bytes;
             const uint32_t tx_bytes = (uint32_t)g.a_tx_bytes + (prog ? 0u : (uint32_t)B_BYTES);
             const bool skip_tma = g.dbg_skip_tma != 0;
-            uint32_t pw = MODE == 2 ? g.prog_ld[0] : 0u;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int n_tile = tile % g.n_tiles, m_tile = tile / g.n_tiles;
                 const int tw = m_tile % g.tiles_w, th = (m_tile / g.tiles_w) % g.tiles_h, tn = m_tile / (g.tiles_w * g.tiles_h);
-                const int w_in0 = tw * g.wbox * g.stride - g.pad, h_in0 = th * g.hbox * g.stride - g.pad, n0 = tn * g.nbox;
+                const int w_in0 = (tw * g.step_w + g.off_w) * g.stride - g.pad, h_in0 = (th * g.step_h + g.off_h) * g.stride - g.pad, n0 = tn * g.nbox;
                 const int nb0 = n_tile * BLOCK_N;
                 int r = 0, sx = 0, kc = 0;                  // tap (r, sx), channel block kc
                 for (int st = 0; st < steps; ++st) {
                     int cc, cw, ch, cn;
                     if constexpr (MODE == 2) {
-                        const uint32_t cur = pw;
-                        pw = g.prog_ld[st + 1 < steps ? st + 1 : 0];        // next step's word while this one is issued
-                        cw = w_in0 + (int)(cur & 0xFFu); ch = h_in0 + (int)((cur >> 8) & 0xFFu);
-                        cc = (int)((cur >> 16) & 0xFFu) * GM_BLOCK_K; cn = n0 + (int)(cur >> 24) * g.N;
+                        cw = w_in0; ch = h_in0; cc = 0; cn = n0 + st * g.N;   // plane st: rows h_in0 .. h_in0 + hbox + R - 2
                     } else {
                         cw = w_in0 + sx; ch = h_in0 + r; cc = kc * GM_BLOCK_K; cn = n0;
                     }
@@ -368,32 +365,38 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     }
                 } else {
                     uint32_t started = 0;                               // accumulator groups already written in this tile
-                    for (int st = 0; st < steps; ++st) {
-                        const uint32_t cur = pw;
-                        pw = g.prog_mma[st + 1 < steps ? st + 1 : 0];
+                    const int R = g.R, planes = steps / R;
+                    const uint32_t row_step = (uint32_t)g.hw * 8u;      // one row of the pixel box, in 16-byte units
+                    int st = 0;
+                    for (int pl = 0; pl < planes; ++pl) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-                        const uint64_t da = DESC_HI | a_lo;
-                        const uint32_t g0 = (cur >> 8) & 0xFu;
-                        const uint64_t db = DESC_HI | (b_lo0 + ((cur >> 4) & 0xFu) * (uint32_t)(B_BYTES >> 4));
-                        const uint32_t first = ((started >> g0) & 1u) ^ 1u;
-                        started |= 1u << g0;
-                        if (!skip_mma) {
-#pragma unroll
-                            for (int k = 0; k < GM_BLOCK_K / 16; ++k)
-                                umma_f16(tmem_d + g0 * BLOCK_N, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC,
-                                         (k != 0 || !first) ? 1u : 0u);
-                        }
-                        if ((cur & 0xFu) == 2u) {
-                            const uint32_t g1 = (cur >> 16) & 0xFu;
-                            const uint64_t db1 = DESC_HI | (b_lo0 + ((cur >> 12) & 0xFu) * (uint32_t)(B_BYTES >> 4));
-                            const uint32_t first1 = ((started >> g1) & 1u) ^ 1u;
-                            started |= 1u << g1;
+                        uint32_t a_row = a_lo;
+                        for (int r = 0; r < R; ++r, ++st, a_row += row_step) {
+                            const uint32_t cur = pw;
+                            pw = g.prog_mma[st + 1 < steps ? st + 1 : 0];
+                            const uint64_t da = DESC_HI | a_row;
+                            const uint32_t g0 = (cur >> 8) & 0xFu;
+                            const uint64_t db = DESC_HI | (b_lo0 + ((cur >> 4) & 0xFu) * (uint32_t)(B_BYTES >> 4));
+                            const uint32_t first = ((started >> g0) & 1u) ^ 1u;
+                            started |= 1u << g0;
                             if (!skip_mma) {
 #pragma unroll
                                 for (int k = 0; k < GM_BLOCK_K / 16; ++k)
-                                    umma_f16(tmem_d + g1 * BLOCK_N, da + (uint64_t)(2 * k), db1 + (uint64_t)(2 * k), IDESC,
-                                             (k != 0 || !first1) ? 1u : 0u);
+                                    umma_f16(tmem_d + g0 * BLOCK_N, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC,
+                                             (k != 0 || !first) ? 1u : 0u);
+                            }
+                            if ((cur & 0xFu) == 2u) {
+                                const uint32_t g1 = (cur >> 16) & 0xFu;
+                                const uint64_t db1 = DESC_HI | (b_lo0 + ((cur >> 12) & 0xFu) * (uint32_t)(B_BYTES >> 4));
+                                const uint32_t first1 = ((started >> g1) & 1u) ^ 1u;
+                                started |= 1u << g1;
+                                if (!skip_mma) {
+#pragma unroll
+                                    for (int k = 0; k < GM_BLOCK_K / 16; ++k)
+                                        umma_f16(tmem_d + g1 * BLOCK_N, da + (uint64_t)(2 * k), db1 + (uint64_t)(2 * k), IDESC,
+                                                 (k != 0 || !first1) ? 1u : 0u);
+                                }
                             }
                         }
                         umma_commit(&empty_bar[stage]);
@@ -502,6 +505,66 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bn_b + c));
                         t[j] = __fmaf_rn(t[j], a.x, b.x); t[j + 1] = __fmaf_rn(t[j + 1], a.y, b.y);
                         t[j + 2] = __fmaf_rn(t[j + 2], a.z, b.z); t[j + 3] = __fmaf_rn(t[j + 3], a.w, b.w);
+                    }
+                }
+                if constexpr (MODE == 2) {
+                    if (g.pool) {
+                        // ---- fused ReLU + 3x3 / stride 2 / pad 1 max-pool + next-layer encode (stem) ----
+                        // the tile is the (2P+1) x (2Q+1) box of conv pixels under P x Q pooled pixels: stage it
+                        // (pixels outside the conv output as -inf), pool out of shared memory, store the pooled tile
+                        const int hl = mrow / g.hw, wl = mrow % g.hw;
+                        const int oh = th * g.step_h + g.off_h + hl, ow = tw * g.step_w + g.off_w + wl;
+                        const bool pvalid = hl < g.hbox && oh >= 0 && oh < g.Ho && ow >= 0 && ow < g.Wo;
+                        if (store_thread) bulk_wait_read0();
+                        epi_bar_sync(1 + grp);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 v = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
+                            if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                            if (!pvalid) v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                            *reinterpret_cast<float4 *>(st_f32 + mrow * 128 + (((uint32_t)(j >> 2) ^ (uint32_t)(mrow & 7)) << 4)) = v;
+                        }
+                        epi_bar_sync(1 + grp);
+                        uint8_t *st_pool = st_codes, *st_pcodes = st_codes + 4096;   // [P*Q][32] fp32 / fp16 tiles
+                        const int pp = mrow >> 2, cb = mrow & 3;                     // pooled pixel, 8-channel block
+                        if (pp < g.pool_p * g.pool_q) {
+                            const int pl = pp / g.pool_q, ql = pp % g.pool_q;
+                            float4 m0 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), m1 = m0;
+#pragma unroll
+                            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                                for (int dx = 0; dx < 3; ++dx) {
+                                    const int mm = (2 * pl + dy) * g.hw + 2 * ql + dx;
+                                    const uint32_t sw = (uint32_t)(mm & 7);
+                                    const float4 a = *reinterpret_cast<const float4 *>(st_f32 + mm * 128 + (((uint32_t)(2 * cb) ^ sw) << 4));
+                                    const float4 b = *reinterpret_cast<const float4 *>(st_f32 + mm * 128 + (((uint32_t)(2 * cb + 1) ^ sw) << 4));
+                                    m0.x = fmaxf(m0.x, a.x); m0.y = fmaxf(m0.y, a.y); m0.z = fmaxf(m0.z, a.z); m0.w = fmaxf(m0.w, a.w);
+                                    m1.x = fmaxf(m1.x, b.x); m1.y = fmaxf(m1.y, b.y); m1.z = fmaxf(m1.z, b.z); m1.w = fmaxf(m1.w, b.w);
+                                }
+                            const uint32_t psw = (uint32_t)(pp & 7);
+                            *reinterpret_cast<float4 *>(st_pool + pp * 128 + (((uint32_t)(2 * cb) ^ psw) << 4)) = m0;
+                            *reinterpret_cast<float4 *>(st_pool + pp * 128 + (((uint32_t)(2 * cb + 1) ^ psw) << 4)) = m1;
+                            if (g.write_codes) {
+                                const float pv[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+                                uint32_t hc[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const uint32_t neg = __float_as_uint(pv[e]) >> 31;
+                                    const uint32_t q = g.next_fastdiv ? quantize_f32<true>(pv[e], nq) : quantize_f32<false>(pv[e], nq);
+                                    hc[e] = __half_as_ushort(lut[q | (neg << g.next_bits)]);
+                                }
+                                *reinterpret_cast<uint4 *>(st_pcodes + pp * 64 + (((uint32_t)cb ^ (uint32_t)((pp >> 1) & 3)) << 4)) =
+                                    make_uint4(hc[0] | (hc[1] << 16), hc[2] | (hc[3] << 16), hc[4] | (hc[5] << 16), hc[6] | (hc[7] << 16));
+                            }
+                        }
+                        fence_proxy_async();
+                        epi_bar_sync(1 + grp);
+                        if (store_thread) {
+                            tma_store_4d(&tmC, st_pool, c0, tw * g.pool_q, th * g.pool_p, n0);
+                            if (g.write_codes) tma_store_4d(&tmD, st_pcodes, c0, tw * g.pool_q, th * g.pool_p, n0);
+                            bulk_commit();
+                        }
+                        continue;
                     }
                 }
                 // (b) staging: with a residual it already holds this chunk's residual tile; otherwise the previous
@@ -654,7 +717,7 @@ static int plan_smem(ConvGeom &g, int block_n)
     // epilogue staging per group: fp32 tile only if an fp32 tile is written or a residual is read, code tile only
     // if codes are written -- what is not needed goes to the stage ring
     g.epi_codes_off = (g.write_f32 || g.residual) ? GM_EPI_F32_BYTES : 0;
-    g.epi_group_bytes = g.epi_codes_off + (g.write_codes ? GM_EPI_CODE_BYTES : 0);
+    g.epi_group_bytes = g.epi_codes_off + ((g.write_codes || g.pool) ? GM_EPI_CODE_BYTES : 0);
     const int epi_bytes = GM_EPI_GROUPS * g.epi_group_bytes;
     const int fixed = g.ring_off + epi_bytes + (2 << GM_LUT_MAX_BITS) * 2 + 1024 /* barriers */ + 1024 /* align */;
     int stages = (GM_SMEM_BUDGET - fixed) / g.stage_bytes;
@@ -798,6 +861,7 @@ extern "C" int tq_conv2d_codes_fused(const void *act, const void *wgt, float *ou
         }
     }
 
+    g.step_w = g.wbox; g.step_h = g.hbox; g.off_w = 0; g.off_h = 0;
     CUtensorMap tmA, tmB, tmC, tmD;
     int rc;
     {   // activations: (C, W, H, N) fp16; box spans wbox*stride x hbox*stride pixels, element strides = conv stride
@@ -906,8 +970,11 @@ stem_prepare_kernel(const Tin *__restrict__ x, __half *__restrict__ x2, int N, i
 
 }  // namespace tq
 
-extern "C" int tq_stem_conv7x7s2_dt(const void *x, int x_dtype, void *x2_scratch, const void *w2, float *out,
-                                    int N, int H, int W, int Cout, void *stream)
+// pool = 0: out = conv (fp32 [N, H/2, W/2, Cout]).  pool = 1: out = maxpool3x3s2p1(relu?(fma(conv, bn_a, bn_b)))
+// (fp32 [N, Hp, Wp, Cout]) and, if out_codes, its fp16 term codes for the next layer's quantiser.
+static int stem_impl(const void *x, int x_dtype, void *x2_scratch, const void *w2, float *out, void *out_codes,
+                     const float *bn_a, const float *bn_b, int relu, int pool, float next_sf, int next_bits,
+                     int next_terms, int N, int H, int W, int Cout, void *stream)
 {
     if (!x || !x2_scratch || !w2 || !out) return fail(TQ_ERR_INVALID, "NULL pointer");
     if (x_dtype != TQ_F32 && x_dtype != TQ_BF16 && x_dtype != TQ_F16)
@@ -942,31 +1009,58 @@ extern "C" int tq_stem_conv7x7s2_dt(const void *x, int x_dtype, void *x2_scratch
     g.Ho = Ho; g.Wo = Wo;
     g.scale = 1.0f;
     g.kc_blocks = 1;
-    pick_box(g);
+    int Hp = 0, Wp = 0;
+    if (!pool) {
+        if (!pick_box_halo(g)) return fail(TQ_ERR_UNSUPPORTED, "stem conv: no tile shape");
+        g.step_w = g.wbox; g.step_h = g.hbox;
+    } else {
+        // pooled tile P x Q over the (2P+1) x (2Q+1) conv pixels it needs (<= 128 accumulator rows): fewest tiles
+        Hp = (Ho + 2 - 3) / 2 + 1; Wp = (Wo + 2 - 3) / 2 + 1;
+        long best = -1;
+        for (int P = 1; P <= Hp && 2 * P + 1 <= 128; ++P)
+            for (int Q = 1; Q <= Wp && (2 * P + 1) * (2 * Q + 1) <= 128; ++Q) {
+                const long tiles = (long)((Hp + P - 1) / P) * ((Wp + Q - 1) / Q);
+                if (best < 0 || tiles < best || (tiles == best && Q > g.pool_q)) { best = tiles; g.pool_p = P; g.pool_q = Q; }
+            }
+        g.pool = 1;
+        g.wbox = 2 * g.pool_q + 1; g.hbox = 2 * g.pool_p + 1; g.nbox = 1;
+        g.step_w = 2 * g.pool_q; g.step_h = 2 * g.pool_p; g.off_w = -1; g.off_h = -1;
+        g.tiles_w = (Wp + g.pool_q - 1) / g.pool_q; g.tiles_h = (Hp + g.pool_p - 1) / g.pool_p; g.tiles_n = N;
+        g.m_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
+        g.a_tx_bytes = g.wbox * g.hbox * GM_BLOCK_K * 2;
+        if (g.pool_p * g.pool_q > 32) return fail(TQ_ERR_UNSUPPORTED, "pooled tile too large");
+        g.bn_a = bn_a; g.bn_b = bn_b; g.relu = relu ? 1 : 0;
+        g.write_codes = out_codes ? 1 : 0;
+        if (out_codes) {
+            if (!(next_sf > 0.0f) || !(next_sf < INFINITY)) return fail(TQ_ERR_INVALID, "next_sf must be positive and finite");
+            if (next_bits < 1 || next_bits > GM_LUT_MAX_BITS || next_terms < 0) return fail(TQ_ERR_UNSUPPORTED, "fused encode supports 1..%d bits", GM_LUT_MAX_BITS);
+        }
+    }
     g.hw = g.wbox;
     const int block_n = Cout <= 64 ? 64 : 128;
     g.n_tiles = (Cout + block_n - 1) / block_n;
     g.write_f32 = 1;
-    g.next_sf = 1.0f; g.next_bits = 1;
+    g.next_sf = out_codes ? next_sf : 1.0f; g.next_bits = out_codes ? next_bits : 1; g.next_terms = next_terms;
+    g.next_fastdiv = (g.next_sf >= 9.313225746154785e-10f && g.next_sf <= 1073741824.0f) ? 1 : 0;
     // program: per filter row R one load of x_hi (MMAs against w_hi -> main accumulator, w_lo -> cross
     // accumulator) and one of x_lo (w_hi -> cross).  The main accumulator is split in two (rows 0-1 / 2-3):
     // tensor-core accumulation truncates, so fewer steps per accumulator = less bias; the small cross terms
     // live apart from the large ones and everything is summed once, in fp32 RN, in the epilogue.
     g.prog_steps = lo_plane ? 8 : 4; g.nb_tiles = 8; g.n_groups = 3;
     for (uint32_t R = 0; R < 4; ++R) {
-        g.prog_ld[R] = R << 8;                                              // x_hi, filter row R
         g.prog_mma[R] = 2u | (R << 4) | ((R < 2 ? 0u : 1u) << 8) | ((4u + R) << 12) | (2u << 16);
-        g.prog_ld[4 + R] = (R << 8) | (1u << 24);                           // x_lo (plane 1), filter row R
         g.prog_mma[4 + R] = 1u | (R << 4) | (2u << 8);
     }
 
-    CUtensorMap tmA, tmB, tmC;
+    CUtensorMap tmA, tmB, tmC, tmD;
     int rc;
     {   // overlapping windows: inner 64 elements, output column advances by one folded pixel (16 elements)
         cuuint64_t dims[4] = {64, (cuuint64_t)Wo, (cuuint64_t)Hs, (cuuint64_t)((lo_plane ? 2 : 1) * N)};
         cuuint64_t strides[3] = {32, (cuuint64_t)Ws * 32, (cuuint64_t)Hs * Ws * 32};
-        cuuint32_t box[4] = {64, (cuuint32_t)g.wbox, (cuuint32_t)g.hbox, (cuuint32_t)g.nbox};
+        cuuint32_t box[4] = {64, (cuuint32_t)g.wbox, (cuuint32_t)(g.hbox + g.R - 1), 1};   // all R filter rows at once
         cuuint32_t one[4] = {1, 1, 1, 1};
+        g.a_tx_bytes = g.wbox * (g.hbox + g.R - 1) * GM_BLOCK_K * 2;
+        g.halo = 1;                                         // (stage size follows a_tx_bytes)
         CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x2_scratch, dims, strides, box, one,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -978,15 +1072,41 @@ extern "C" int tq_stem_conv7x7s2_dt(const void *x, int x_dtype, void *x2_scratch
         cuuint32_t one[3] = {1, 1, 1};
         if ((rc = encode_map(enc, &tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w2, 3, dims, box, one, "stem weights")) != TQ_OK) return rc;
     }
-    {
+    tmD = tmA;
+    if (!pool) {
         cuuint64_t odims[4] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
         cuuint32_t box[4] = {32, (cuuint32_t)g.wbox, (cuuint32_t)g.hbox, (cuuint32_t)g.nbox};
         cuuint32_t one[4] = {1, 1, 1, 1};
         if ((rc = encode_map(enc, &tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, 4, odims, box, one, "stem output")) != TQ_OK) return rc;
+    } else {
+        cuuint64_t odims[4] = {(cuuint64_t)Cout, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)N};
+        cuuint32_t box[4] = {32, (cuuint32_t)g.pool_q, (cuuint32_t)g.pool_p, 1};
+        cuuint32_t one[4] = {1, 1, 1, 1};
+        if ((rc = encode_map(enc, &tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, 4, odims, box, one, "pooled output")) != TQ_OK) return rc;
+        if (out_codes && (rc = encode_map(enc, &tmD, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, out_codes, 4, odims, box, one,
+                                          "pooled codes", CU_TENSOR_MAP_SWIZZLE_64B)) != TQ_OK) return rc;
     }
     if (g.nbox != 1) return fail(TQ_ERR_UNSUPPORTED, "stem conv expects images of at least 128 output pixels");
     if (block_n != 64) return fail(TQ_ERR_UNSUPPORTED, "stem conv supports Cout <= 64");
-    return launch_conv<64>(tmA, tmB, tmC, tmA, tmA, g, s, true);
+    return launch_conv<64>(tmA, tmB, tmC, tmD, tmA, g, s, true);
+}
+
+extern "C" int tq_stem_conv7x7s2_dt(const void *x, int x_dtype, void *x2_scratch, const void *w2, float *out,
+                                    int N, int H, int W, int Cout, void *stream)
+{
+    return stem_impl(x, x_dtype, x2_scratch, w2, out, nullptr, nullptr, nullptr, 0, 0, 1.0f, 1, 0, N, H, W, Cout, stream);
+}
+
+extern "C" int tq_stem_conv7x7s2_pool(const void *x, int x_dtype, void *x2_scratch, const void *w2,
+                                      const float *bn_a, const float *bn_b, int relu, float *out, void *out_codes,
+                                      int N, int H, int W, int Cout, float next_sf, int next_bits, int next_terms,
+                                      void *stream)
+{
+    if (!bn_a || !bn_b) return fail(TQ_ERR_INVALID, "NULL pointer");
+    if (Cout % 8) return fail(TQ_ERR_UNSUPPORTED, "Cout must be a multiple of 8");
+    if ((((uintptr_t)bn_a | (uintptr_t)bn_b | (uintptr_t)out_codes) & 15u) != 0) return fail(TQ_ERR_INVALID, "pointers must be 16-byte aligned");
+    return stem_impl(x, x_dtype, x2_scratch, w2, out, out_codes, bn_a, bn_b, relu, 1, next_sf, next_bits, next_terms,
+                     N, H, W, Cout, stream);
 }
 
 extern "C" int tq_stem_conv7x7s2(const float *x, void *x2_scratch, const void *w2, float *out,

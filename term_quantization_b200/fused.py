@@ -65,9 +65,14 @@ class FusedResNet(nn.Module):
     """Wraps a calibrated, TQ-converted torchvision ResNet built from BasicBlocks."""
 
     def __init__(self, model, stem="tcgen05"):
+        """stem: 'tcgen05' (stem conv on the tensor cores, then the fused BN+ReLU+max-pool+encode pass),
+        'tcgen05_pool' (the whole stem in ONE kernel, pooling in the conv epilogue: no 822 MB conv output in
+        HBM, but its epilogue is instruction-bound today and it is ~5 % slower than the two launches), or
+        'cudnn' (cuDNN's fp32 conv)."""
         super().__init__()
-        if stem not in ("tcgen05", "cudnn"):
-            raise ValueError("stem must be 'tcgen05' or 'cudnn'")
+        if stem not in ("tcgen05", "tcgen05_pool", "cudnn"):
+            raise ValueError("stem must be 'tcgen05', 'tcgen05_pool' or 'cudnn'")
+        self.stem_mode = stem
         self.model = model.to(memory_format=torch.channels_last).eval()
         self.blocks = []
         for stage in (model.layer1, model.layer2, model.layer3, model.layer4):
@@ -84,11 +89,11 @@ class FusedResNet(nn.Module):
         mp = model.maxpool
         self.fuse_stem = (isinstance(mp, nn.MaxPool2d) and mp.kernel_size in (3, (3, 3)) and mp.stride in (2, (2, 2))
                           and mp.padding in (1, (1, 1)) and mp.dilation in (1, (1, 1)) and not mp.ceil_mode
-                          and model.conv1.out_channels % 4 == 0 and self.blocks[0][0].quant[1] <= 12)
+                          and model.conv1.out_channels % 8 == 0 and self.blocks[0][0].quant[1] <= 10)
         self.stem_bn = _bn_affine(model.bn1)
         c1 = model.conv1
         self.stem_w = None
-        if (stem == "tcgen05" and self.fuse_stem and tuple(c1.weight.shape[1:]) == (3, 7, 7) and c1.stride == (2, 2)
+        if (stem != "cudnn" and self.fuse_stem and tuple(c1.weight.shape[1:]) == (3, 7, 7) and c1.stride == (2, 2)
                 and c1.padding == (3, 3) and c1.dilation == (1, 1) and c1.groups == 1 and c1.bias is None
                 and c1.out_channels <= 64):
             self.stem_w = conv_codes.pack_stem_weight(c1.weight)
@@ -111,11 +116,18 @@ class FusedResNet(nn.Module):
             q0 = self.blocks[0][0].quant
             if self.stem_w is not None and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0 \
                     and (x.shape[2] // 2) * (x.shape[3] // 2) >= 128:
-                y, self._stem_scratch = conv_codes.stem_conv7x7s2(x.permute(0, 2, 3, 1), self.stem_w,
-                                                                  self._stem_scratch)
+                if self.stem_mode == "tcgen05_pool":
+                    # conv + bn1 + relu + maxpool + first encode: one tensor-core kernel
+                    cur, c0, self._stem_scratch = conv_codes.stem_conv_pool(
+                        x.permute(0, 2, 3, 1), self.stem_w, self.stem_bn, relu=True, next_quant=q0,
+                        scratch=self._stem_scratch)
+                else:
+                    y, self._stem_scratch = conv_codes.stem_conv7x7s2(x.permute(0, 2, 3, 1), self.stem_w,
+                                                                      self._stem_scratch)
+                    cur, c0 = conv_codes.bn_relu_maxpool_encode(y, self.stem_bn, relu=True, next_quant=q0)
             else:
                 y = m.conv1(x.float()).permute(0, 2, 3, 1)
-            cur, c0 = conv_codes.bn_relu_maxpool_encode(y, self.stem_bn, relu=True, next_quant=q0)
+                cur, c0 = conv_codes.bn_relu_maxpool_encode(y, self.stem_bn, relu=True, next_quant=q0)
             codes = {q0: c0}                             # quantiser -> fp16 codes of `cur`
         else:
             x = m.maxpool(m.relu(m.bn1(m.conv1(x.float()))))

@@ -142,3 +142,27 @@ def test_stem_conv_tensor_cores_fp32_accuracy():
             want16 = F.conv2d(x16.permute(0, 3, 1, 2).double(), w.double(), None, 2, 3).permute(0, 2, 3, 1)
             got16, _ = conv_codes.stem_conv7x7s2(x16, conv_codes.pack_stem_weight(w))
             assert float((got16.double() - want16).abs().max()) / scale < 5e-6
+
+
+def test_stem_conv_pool_fused_equals_two_pass():
+    """conv7x7s2 -> BN -> ReLU -> maxpool -> encode in ONE tensor-core kernel (pooling in the epilogue out of
+    shared memory) must equal the two-pass path (stem conv, then bn_relu_maxpool_encode) bit for bit."""
+    from term_quantization_b200 import conv_codes
+    g = torch.Generator(device="cuda").manual_seed(21)
+    for (N, H, W, dt, relu) in ((3, 224, 224, torch.float32, True), (2, 64, 96, torch.bfloat16, True),
+                                (2, 50, 38, torch.float32, False), (1, 226, 222, torch.float16, True)):
+        x = torch.randn(N, H, W, 3, device="cuda", generator=g).to(dt).contiguous()
+        w = torch.randn(64, 3, 7, 7, device="cuda", generator=g) * 0.1
+        a = torch.randn(64, device="cuda", generator=g)
+        b = torch.randn(64, device="cuda", generator=g)
+        w2 = conv_codes.pack_stem_weight(w)
+        y, _ = conv_codes.stem_conv7x7s2(x, w2)
+        want, _ = conv_codes.bn_relu_maxpool_encode(y, (a, b), relu=relu)
+        nq = (float(want.abs().max()) / 512, 9, 3)
+        want, want_codes = conv_codes.bn_relu_maxpool_encode(y, (a, b), relu=relu, next_quant=nq)
+        got, codes, _ = conv_codes.stem_conv_pool(x, w2, (a, b), relu=relu, next_quant=nq)
+        assert got.shape == want.shape
+        assert torch.equal(got, want), float((got - want).abs().max())
+        assert torch.equal(codes, want_codes)
+        got2, none, _ = conv_codes.stem_conv_pool(x, w2, (a, b), relu=relu)
+        assert none is None and torch.equal(got2, want)

@@ -49,7 +49,7 @@ def main():
         total_ms += ms * cnt
         total_flop += flop * cnt
     print(json.dumps({"resnet18_wrapped_convs_ms": total_ms, "TFLOPs": total_flop / max(total_ms, 1e-9) / 1e9}))
-    if args.only < 0:
+    if args.only < 0 or args.only == 99:
         import torch.nn.functional as F
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cudnn.benchmark = True
@@ -58,7 +58,13 @@ def main():
         w2 = conv_codes.pack_stem_weight(w)
         xn = x.permute(0, 2, 3, 1)
         _, scratch = conv_codes.stem_conv7x7s2(xn, w2)
+        xb = xn.bfloat16().contiguous()
+        bn = (torch.rand(64, device="cuda") + 0.5, torch.randn(64, device="cuda"))
+        nq = (0.01, 9, 3)
         for name, fn in (("stem tcgen05 hi/lo", lambda: conv_codes.stem_conv7x7s2(xn, w2, scratch)),
+                         ("stem tcgen05 bf16 images", lambda: conv_codes.stem_conv7x7s2(xb, w2, scratch)),
+                         ("stem+bn+relu+pool+encode fused, fp32 images", lambda: conv_codes.stem_conv_pool(xn, w2, bn, True, nq, scratch)),
+                         ("stem+bn+relu+pool+encode fused, bf16 images", lambda: conv_codes.stem_conv_pool(xb, w2, bn, True, nq, scratch)),
                          ("stem cuDNN fp32", lambda: F.conv2d(x, w, None, 2, 3))):
             for _ in range(3):
                 fn()

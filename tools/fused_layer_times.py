@@ -70,6 +70,8 @@ def d_stem(a, k, out):
 wrap("conv2d_codes_fused", d_conv)
 wrap("bn_relu_maxpool_encode", d_pool)
 wrap("stem_conv7x7s2", d_stem)
+wrap("stem_conv_pool", lambda a, k, out: {"in": list(a[0].shape), "out": list(out[0].shape), "flop": 2 * out[0].numel() * 4 * 147,
+                                         "bytes": a[0].numel() * a[0].element_size() + out[0].numel() * 6})
 
 with torch.no_grad():
     for _ in range(3):
