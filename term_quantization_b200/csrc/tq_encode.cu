@@ -174,17 +174,28 @@ __device__ __forceinline__ int count_at_or_above(const uint32_t (&W)[NW], int p)
     return c;
 }
 
+constexpr int GROUP_LUT_MAX_BITS = 12;          // 2^bits entries of (T | N << 16) in shared memory: 16 KB at most
+
 template <int G, bool CONTIG, typename Tout, bool DEQ, bool FAST>
 __global__ void __launch_bounds__(GROUP_THREADS)
 tr_group_kernel(const float *__restrict__ in, Tout *__restrict__ out,
-                int64_t B, int64_t C, int64_t WH, EncParams p, int *__restrict__ overflow)
+                int64_t B, int64_t C, int64_t WH, EncParams p, int use_lut, int *__restrict__ overflow)
 {
     static_assert(G >= 2 && G <= 32 && (G & (G - 1)) == 0, "G must be a power of two");
     constexpr int NW = G / 2;
+    extern __shared__ uint32_t tn_lut[];            // q -> T | N << 16 (term presence / negative-term masks)
     const Quant k = make_quant(p.sf, p.maxv);
     const int64_t CG = C / G;                       // caller guarantees C % G == 0
     const int64_t total = B * CG * WH;
     bool ovf = false;
+    if (use_lut) {
+        for (uint32_t q = threadIdx.x; q < (1u << p.bits); q += GROUP_THREADS) {
+            uint32_t T, N;
+            term_masks(q, p.enc, T, N);
+            tn_lut[q] = T | (N << 16);
+        }
+        __syncthreads();
+    }
 
     for (int64_t t = (int64_t)blockIdx.x * GROUP_THREADS + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * GROUP_THREADS) {
@@ -218,20 +229,25 @@ tr_group_kernel(const float *__restrict__ in, Tout *__restrict__ out,
             for (int j = 0; j < G; ++j) x[j] = __ldg(in + base + j * stride);
         }
 
-        uint32_t qs[G];                              // q | sign << 31
-        uint32_t W[NW];
+        uint32_t tn[G];                              // T | N << 16 | sign << 31   (T, N < 2^15)
+        uint32_t W[NW];                              // two T masks per word, for the counting probes
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             uint32_t neg;
             const uint32_t q = quantize_any<float, FAST>(x[j], k, p.relu != 0, neg);
-            qs[j] = q | (neg << 31);
-            uint32_t T, N;
-            term_masks(q, p.enc, T, N);
-            if (j & 1) W[j >> 1] |= T << 16; else W[j >> 1] = T;
+            uint32_t e;
+            if (use_lut) e = tn_lut[q];
+            else {
+                uint32_t T, N;
+                term_masks(q, p.enc, T, N);
+                e = T | (N << 16);
+            }
+            if (j & 1) W[j >> 1] |= e << 16; else W[j >> 1] = e & 0xFFFFu;
+            tn[j] = e | (neg << 31);
         }
 
         // cut level: largest pc with (#terms at level >= pc) > alpha; none -> keep everything
-        uint32_t himask = 0xFFFFFFFFu, cutbit = 0u;
+        uint32_t himask = 0xFFFFu, cutbit = 0u;
         int r = 0;
         if (count_at_or_above<NW>(W, 0) > p.alpha) {
             int pc = 0;
@@ -242,28 +258,20 @@ tr_group_kernel(const float *__restrict__ in, Tout *__restrict__ out,
             }
             r = p.alpha - ((pc + 1 <= 15) ? count_at_or_above<NW>(W, pc + 1) : 0);
             cutbit = 1u << pc;
-            himask = ~((cutbit << 1) - 1u);
+            himask = 0xFFFFu & ~((cutbit << 1) - 1u);
         }
 
         int cnt = 0;
-        int codes[G];
-#pragma unroll
-        for (int j = 0; j < G; ++j) {
-            const uint32_t T = (j & 1) ? (W[j >> 1] >> 16) : (W[j >> 1] & 0xFFFFu);
-            uint32_t Tq, N;
-            term_masks(qs[j] & 0x7FFFFFFFu, p.enc, Tq, N);
-            uint32_t K = T & himask;
-            const uint32_t at_cut = T & cutbit;
-            if (at_cut) { if (cnt < r) K |= cutbit; ++cnt; }
-            const int v = (int)K - 2 * (int)(K & N);
-            codes[j] = (qs[j] >> 31) ? -v : v;
-        }
-
         Tout y[G];
 #pragma unroll
         for (int j = 0; j < G; ++j) {
-            if constexpr (DEQ) y[j] = dequant<Tout>(codes[j], p.sf);
-            else y[j] = pack_code<Tout>(codes[j], ovf);
+            const uint32_t e = tn[j];
+            uint32_t K = e & himask;
+            if (e & cutbit) { if (cnt < r) K |= cutbit; ++cnt; }
+            const int v = (int)K - 2 * (int)(K & (e >> 16) & 0x7FFFu);
+            const int code = ((int)e < 0) ? -v : v;
+            if constexpr (DEQ) y[j] = dequant<Tout>(code, p.sf);
+            else y[j] = pack_code<Tout>(code, ovf);
         }
         constexpr int OUT_BYTES = (int)sizeof(Tout) * G;
         if (CONTIG && OUT_BYTES % 16 == 0) {
@@ -386,9 +394,12 @@ static int launch_group_f32(const void *in, void *out, int64_t B, int64_t C, int
     const int64_t total = B * (C / g) * WH;
     const int grid = grid_for(total, GROUP_THREADS, 8);
     const bool contig = (WH == 1);
+    // the term-mask table pays for itself once a CTA has a few thousand values to encode
+    const int use_lut = (p.bits <= GROUP_LUT_MAX_BITS && total * g >= (int64_t)grid * (8 << p.bits)) ? 1 : 0;
+    const size_t lut_bytes = use_lut ? (sizeof(uint32_t) << p.bits) : 0;
 #define TQ_LAUNCH_GF(GG, CT, FD)                                                                \
-    tr_group_kernel<GG, CT, Tout, DEQ, FD><<<grid, GROUP_THREADS, 0, s>>>(                      \
-        (const float *)in, (Tout *)out, B, C, WH, p, overflow)
+    tr_group_kernel<GG, CT, Tout, DEQ, FD><<<grid, GROUP_THREADS, lut_bytes, s>>>(              \
+        (const float *)in, (Tout *)out, B, C, WH, p, use_lut, overflow)
 #define TQ_LAUNCH_G(GG)                                                                         \
     case GG:                                                                                    \
         if (contig) { if (p.fastdiv) TQ_LAUNCH_GF(GG, true, true); else TQ_LAUNCH_GF(GG, true, false); }   \
