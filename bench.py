@@ -47,8 +47,11 @@ class ClockSampler(threading.Thread):
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.02):
+        # NVML queries serialise on a driver-wide lock: 8 ranks polling at 100 Hz cost 0.28 ms per 2.1 ms step
+        # (measured), so only rank 0 samples, at 50 Hz
         super().__init__(daemon=True)
+        self.period = period
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
         self._stop_evt = threading.Event()
         try:
@@ -70,13 +73,14 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop_evt.wait(0.01)
+            self._stop_evt.wait(self.period)
 
     def finish(self):
         self._stop_evt.set()
-        self.join(timeout=2)
+        if self.is_alive():
+            self.join(timeout=2)
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_mhz_min": s[0] if s else None, "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
@@ -183,6 +187,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = inference.bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     # fp32 convs must be true fp32 for the 1e-5 logit tolerance (TF32 keeps 10 mantissa bits)
@@ -208,8 +213,8 @@ def run_b200(args):
             model = fused.FusedResNet(model)
     images = [im.to(in_dtype) for im in images]
     use_graphs = args.conv_backend == "fused" and not args.no_cuda_graphs
-    runner = inference.ShardedInference(model, dev, cuda_graphs=use_graphs)
-    eager = inference.ShardedInference(model, dev) if use_graphs else runner
+    runner = inference.ShardedInference(model, dev, cuda_graphs=use_graphs, gather=args.gather)
+    eager = inference.ShardedInference(model, dev, gather=args.gather) if use_graphs else runner
 
     def barrier():
         if world > 1:
@@ -219,25 +224,29 @@ def run_b200(args):
     # ---- value: inputs resident in HBM ----------------------------------------------------
     for i in range(args.warmup):
         runner.forward(images[i % nbuf])
+    runner.finish()
     barrier()
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     torch.cuda.profiler.start()          # no-op unless ncu runs with --profile-from-start off
     e0.record()
     for i in range(args.steps):
         out = runner.forward(images[i % nbuf])
+    fin = runner.finish()                # outstanding / final gather of logits: inside the timed region
     e1.record()
     barrier()
     torch.cuda.profiler.stop()
     ms_total = e0.elapsed_time(e1)
-    out = out.clone()
+    out = (fin[-1] if (fin is not None and fin.dim() == 3) else (fin if fin is not None else out)).clone()
     # the same K steps again, launch by launch with CUDA events around every kernel of this repo (the
     # headline region above runs without them: as CUDA-graph replays when enabled): per-kernel durations
     # for the roofline objects and the launch count
     for i in range(args.warmup if use_graphs else 0):      # the eager path's own warm-up (allocator pools)
         eager.forward(images[i % nbuf])
+    eager.finish()
     barrier()
     with KernelTimer() as trt:
         trt.on = True
@@ -246,6 +255,7 @@ def run_b200(args):
         k0.record()
         for i in range(args.steps):
             eager.forward(images[i % nbuf])
+        eager.finish()
         k1.record()
         barrier()
         launches = _lib.launch_count() - launches0
@@ -256,6 +266,39 @@ def run_b200(args):
         n_st, st_flops, st_ms = trt.summary("stem")
         n_pl, pl_bytes, pl_ms = trt.summary("pool")
     clocks = sampler.finish()
+    diag = None
+    if args.diag:
+        # extra timed loops (no clock sampler running): graph replay vs eager launches, same K steps
+        def timed_loop(r):
+            for i in range(3):
+                r.forward(images[i % nbuf])
+            r.finish()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(args.steps):
+                r.forward(images[i % nbuf])
+            r.finish()
+            b.record()
+            barrier()
+            tt = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item()) / args.steps
+        diag = {"graph_no_sampler_ms": timed_loop(runner), "eager_no_sampler_ms": timed_loop(eager)}
+        nogather = inference.ShardedInference(model, dev, cuda_graphs=use_graphs, gather="end")
+        t_ng = timed_loop(nogather)
+        diag["graph_gather_end_ms"] = t_ng
+    per_rank = None
+    if world > 1:
+        # every rank's own view: its timed region, its clocks, its kernel time (the last is independent of
+        # the per-step synchronisation with the other ranks)
+        mine = {"rank": rank, "ms_per_step": ms_total / args.steps, "sm_mhz": clocks["sm_mhz"],
+                "sm_mhz_min": clocks.get("sm_mhz_min"), "reasons": clocks["reasons"],
+                "conv_kernels_ms_per_step": cv_ms / args.steps,
+                "instrumented_ms_per_step": ms_instrumented / args.steps}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -272,6 +315,7 @@ def run_b200(args):
         nxt = runner.stage(host[(i + 1) % 2])
         runner.run(slot)
         slot = nxt
+    runner.finish()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -279,6 +323,7 @@ def run_b200(args):
         nxt = runner.stage(host[i % 2])
         host_logits = runner.run(slot)
         slot = nxt
+    runner.finish()
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -325,14 +370,17 @@ def run_b200(args):
                        "logits all-gather (NCCL)" if world > 1 else "single GPU",
                        "conv_backend": args.conv_backend, "input_dtype": str(in_dtype).replace("torch.", ""),
                        "cuda_graphs": bool(use_graphs),
+                       "numa": (f"rank pinned to the {len(numa_cpus)} CPUs local to its GPU" if numa_cpus else "not pinned"),
                        "l2": "activations per step (2.08 GB fp32 through TR) exceed the 126 MB L2; "
                              "input batches rotate between 2 buffers"},
             "e2e": {"value": BATCH * world * args.steps / (e2e_ms * 1e-3), "unit": "images/s",
                     "h2d_bytes_per_step": BATCH * 3 * 224 * 224 * host[0].element_size(),
-                    "d2h_bytes_per_step": BATCH * world * 1000 * 4,
+                    "d2h_bytes_per_step": int(host_logits.numel()) * 4,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            **({"per_rank": per_rank} if per_rank else {}),
+            **({"diag": diag} if diag else {}),
             "roofline": dominant,
             "roofline_other": other,
             "tr_encode": tr_encode_roofline(dev, peak, peak_src),
@@ -427,6 +475,9 @@ def main():
                          "unchanged torchvision graph; cudnn_fp32: the reference's float path")
     ap.add_argument("--input-dtype", default="bf16", choices=["bf16", "fp32"],
                     help="dtype of the image batches in HBM and over PCIe (fused engine; bf16 per BASELINE configs[1])")
+    ap.add_argument("--gather", default="step", choices=["step", "async", "end"],
+                    help="when the other ranks' logits are collected (inference.ShardedInference)")
+    ap.add_argument("--diag", action="store_true", help="extra timed loops: graph vs eager, no clock sampler")
     ap.add_argument("--no-cuda-graphs", action="store_true", help="launch the forward kernel by kernel")
     ap.add_argument("--cpu-batch", type=int, default=16, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -14,6 +14,35 @@ import torch.distributed as dist
 from . import tr_layer
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs `local_cpulist` of the GPU's PCI
+    function), so that pinned staging buffers are first-touched on that node and the H2D copies of the ranks do not
+    cross the socket interconnect.  Returns the CPU set, or None when the topology cannot be read."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device_index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()[-12:]                                 # 0000:xx:yy.z
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def shard_bounds(n_items, world_size, rank):
     """Contiguous [lo, hi) slice of rank `rank`; the first n % world ranks hold one extra."""
     base, extra = divmod(n_items, world_size)
@@ -48,6 +77,13 @@ def gather_logits(logits, group=None):
     return torch.cat(parts, dim=0)
 
 
+def gather_steps(kept, group=None):
+    """One all-gather for a whole run: `kept` = per-step local logits [batch, classes] -> [steps, world * batch,
+    classes], rank-major within each step (the same order a per-step gather_logits gives)."""
+    stacked = torch.stack(list(kept), dim=1).contiguous()      # [batch, steps, classes]
+    return gather_logits(stacked, group).permute(1, 0, 2)
+
+
 def calibrate(model, batches, group=None):
     """Reference protocol (evaluate_cnn.py:36-37): forward the calibration batches in tracking
     mode, then leave tracking, which runs the fused scale-factor sweep per layer."""
@@ -67,7 +103,21 @@ class ShardedInference:
     copy stream, overlapping the previous step's compute) and the device->host read of the
     gathered logits."""
 
-    def __init__(self, model, device, group=None, cuda_graphs=False):
+    def __init__(self, model, device, group=None, cuda_graphs=False, gather="step"):
+        """gather: when the logits of the other ranks are collected.
+        'step'  -- one all-gather per forward on the compute stream (every rank holds every step's logits before
+                   the next forward starts; the ranks re-synchronise on every step);
+        'async' -- the same all-gather on a side stream, off the compute stream's critical path (results of step i
+                   are complete once `finish()` or the next-but-one forward has run);
+        'end'   -- local logits are kept per step and ONE all-gather runs in `finish()` (the north star's "only a
+                   final NCCL gather of logits")."""
+        if gather not in ("step", "async", "end"):
+            raise ValueError("gather must be 'step', 'async' or 'end'")
+        self.gather = gather
+        self._side = None
+        self._gathered = [None, None]
+        self._kept = []
+        self._step = 0
         self.model = model.eval()
         self.cuda_graphs = bool(cuda_graphs)
         self._graphs = {}
@@ -106,7 +156,41 @@ class ShardedInference:
 
     @torch.no_grad()
     def forward(self, images_dev):
-        return gather_logits(self._local_forward(images_dev), self.group)
+        local = self._local_forward(images_dev)
+        if self.world == 1 or self.gather == "step":
+            return gather_logits(local, self.group)
+        if self.gather == "end":
+            self._kept.append(local.clone())                    # (the graph's static output is overwritten next step)
+            return local
+        # 'async': all-gather on a side stream into one of two rotating buffers
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        slot = self._step & 1
+        self._step += 1
+        if self._gathered[slot] is None:
+            self._gathered[slot] = torch.empty((self.world * local.shape[0],) + tuple(local.shape[1:]),
+                                               dtype=local.dtype, device=self.device)
+        snap = local.clone()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            dist.all_gather_into_tensor(self._gathered[slot], snap, group=self.group)
+        snap.record_stream(self._side)
+        return self._gathered[slot]
+
+    @torch.no_grad()
+    def finish(self):
+        """Complete outstanding gathers.  Returns the gathered logits: of the last step ('step' / 'async') or of
+        every step since the last finish(), shape [steps, world * batch, classes] ('end')."""
+        cur = torch.cuda.current_stream(self.device)
+        if self.gather == "async" and self._side is not None:
+            cur.wait_stream(self._side)
+            return self._gathered[(self._step - 1) & 1]
+        if self.gather == "end" and self.world > 1 and self._kept:
+            kept, self._kept = self._kept, []
+            return gather_steps(kept, self.group)
+        self._kept = []
+        return None
 
     def stage(self, pinned):
         """Start the host->device copy of a pinned shard on the copy stream; returns the slot.
@@ -134,5 +218,9 @@ class ShardedInference:
         logits = self.forward(self._stage[slot])
         if self._host_out is None or self._host_out.shape != logits.shape:
             self._host_out = torch.empty(logits.shape, dtype=logits.dtype, pin_memory=True)
-        self._host_out.copy_(logits, non_blocking=True)
+        if self.gather == "async" and self.world > 1:
+            with torch.cuda.stream(self._side):                 # behind the gather it reads
+                self._host_out.copy_(logits, non_blocking=True)
+        else:
+            self._host_out.copy_(logits, non_blocking=True)
         return self._host_out

@@ -33,7 +33,11 @@ def _worker(rank, world, port, ret):
         inference.allreduce_histograms(q)
         ok_hist = all(float(m.hist_bins.sum()) == 3.0 and float(m.hist_bins[i]) == 1.0 and
                       float(m.hist_bins[i + 1]) == 2.0 for i, m in enumerate(q))
-        ret[rank] = (ok_gather, ok_hist)
+        # one gather for a whole run (gather="end"): same rank-major order per step as per-step gathers
+        steps = [batch[lo:hi] * float(k + 1) for k in range(3)]
+        all_steps = inference.gather_steps(steps)
+        ok_steps = all_steps.shape == (3, 10, 4) and all(torch.equal(all_steps[k], batch * float(k + 1)) for k in range(3))
+        ret[rank] = (ok_gather, ok_hist and ok_steps)
     finally:
         dist.destroy_process_group()
 

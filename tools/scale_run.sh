@@ -11,7 +11,7 @@ import json
 base = None
 for n in (1, 2, 4, 8):
     try:
-        d = json.load(open(f"gpurun_out/scale_n{n}.json"))
+        d = json.loads([l for l in open(f"gpurun_out/scale_n{n}.json").read().splitlines() if l.startswith("{")][-1])
     except Exception as e:
         print(n, "failed", e); continue
     base = base or d["value"]
