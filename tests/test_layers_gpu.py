@@ -268,3 +268,44 @@ def test_fused_resnet_matches_unfused_tensor_core_path():
     assert d_unfused < 2e-2
     assert d_fused < 2e-2
     assert float((got.argmax(1) == ref.argmax(1)).float().mean()) >= 0.75
+
+
+@pytest.mark.parametrize("arch,size,expect_grouped", [("vgg16_bn", 64, 0), ("mobilenet_v2", 96, 17)])
+def test_other_cnn_configs_layer_by_layer_on_tensor_cores(arch, size, expect_grouped):
+    """BASELINE configs[2] / [3]: every wrapped conv of VGG-16-bn and MobileNet-V2 (random init, reference
+    layer settings: depthwise convs get the (16, 1, 16) 'unquantised' setting and stay on the float path) run on
+    the tcgen05 code-domain kernel must reproduce the float path's output for the SAME input: the integer
+    accumulators are exact, so the two differ by fp32 rounding of the cuDNN conv only."""
+    import torchvision
+    from term_quantization_b200 import cnn_models, inference, tr_layer
+    torch.manual_seed(0)
+    base = getattr(torchvision.models, arch)(weights=None).cuda().eval()
+    q = cnn_models.convert_model(base, cnn_models.static_conv_layer_settings(base, 9, 8, 12), 9, 3)
+    x = torch.randn(2, 3, size, size, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+    inference.calibrate(q, [x])
+    layers = [(n, m) for n, m in q.named_modules() if isinstance(m, tr_layer.TRConv2dLayer)]
+    feats = {}
+    hooks = [m.register_forward_hook(lambda mod, i, o, k=n: feats.__setitem__(k, (i[0].detach(), o.detach())))
+             for n, m in layers]
+    with torch.no_grad():
+        ref = q(x)
+        for h in hooks:
+            h.remove()
+        switched, skipped = tr_layer.use_tensor_cores(q)
+        assert len(skipped) == expect_grouped and all("grouped" in why for _, why in skipped)
+        assert len(switched) == len(layers) - expect_grouped
+        worst = 0.0
+        for n, m in layers:
+            if n not in switched:
+                continue
+            xin, yref = feats[n]
+            ytc = m(xin)
+            k = m.conv.in_channels * m.conv.kernel_size[0] * m.conv.kernel_size[1]
+            tol = 2e-6 * max(float(yref.abs().max()), 1e-30) * k ** 0.5
+            err = float((ytc - yref).abs().max())
+            worst = max(worst, err / tol)
+            assert err <= tol, (n, err, tol)
+        got = q(x)
+    assert got.shape == ref.shape and bool(torch.isfinite(got).all())
+    print(f"{arch}: {len(switched)} convs on tcgen05, {len(skipped)} grouped on the float path, worst err/tol {worst:.2f}, "
+          f"logit rel diff {float((got - ref).abs().max()) / max(float(ref.abs().max()), 1e-30):.2e}")
