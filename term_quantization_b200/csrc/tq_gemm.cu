@@ -184,6 +184,84 @@ constexpr int GM_EPI_F32_BYTES = 16384;         // per epilogue group: [128][32]
 constexpr int GM_EPI_CODE_BYTES = 8192;         // per epilogue group: [128][32] fp16 code staging
 constexpr int GM_SMEM_BUDGET = 227 * 1024;
 
+// ---- epilogue arithmetic (per 32-column chunk of one accumulator row) -------------------------
+// FULL = all 32 channels of the chunk exist (c0 + 32 <= Cout): no per-channel guards, parameter loads with
+// immediate offsets
+template <bool FULL>
+__device__ __forceinline__ void epi_affine(float (&t)[32], const ConvGeom &g, int c0)
+{
+    if (g.bias) {
+        const float4 *bp = reinterpret_cast<const float4 *>(g.bias + c0);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            if (FULL || c0 + j < g.Cout) {
+                const float4 b = __ldg(bp + (j >> 2));
+                t[j] = __fadd_rn(t[j], b.x); t[j + 1] = __fadd_rn(t[j + 1], b.y);
+                t[j + 2] = __fadd_rn(t[j + 2], b.z); t[j + 3] = __fadd_rn(t[j + 3], b.w);
+            }
+        }
+    }
+    if (g.bn_a) {
+        const float4 *ap = reinterpret_cast<const float4 *>(g.bn_a + c0);
+        const float4 *bp = reinterpret_cast<const float4 *>(g.bn_b + c0);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            if (FULL || c0 + j < g.Cout) {
+                const float4 a = __ldg(ap + (j >> 2));
+                const float4 b = __ldg(bp + (j >> 2));
+                t[j] = __fmaf_rn(t[j], a.x, b.x); t[j + 1] = __fmaf_rn(t[j + 1], a.y, b.y);
+                t[j + 2] = __fmaf_rn(t[j + 2], a.z, b.z); t[j + 3] = __fmaf_rn(t[j + 3], a.w, b.w);
+            }
+        }
+    }
+}
+
+// residual add (the staging tile holds the residual), ReLU, fp32 tile and / or term codes into the staging tiles.
+// RELU: the values are >= 0 afterwards, so the encode needs neither |x| nor the sign half of the table.
+template <bool RELU>
+__device__ __forceinline__ void epi_stage(float (&t)[32], const ConvGeom &g, uint8_t *st_f32, uint8_t *st_codes, int row,
+                                          bool has_res, const __half *lut, const Quant &nq)
+{
+    const uint32_t sw128 = (uint32_t)(row & 7);             // 16B piece index ^= row % 8
+    const uint32_t sw64 = (uint32_t)((row >> 1) & 3);       // 16B piece index ^= (row / 2) % 4
+    uint8_t *frow = st_f32 + row * 128, *crow = st_codes + row * 64;
+    const bool wf = g.write_f32 != 0, wc = g.write_codes != 0, fast = g.next_fastdiv != 0;
+    const uint32_t nbits = (uint32_t)g.next_bits;
+    uint32_t cw[4];                                         // 8 codes = one 16-byte piece
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        float4 *slot = reinterpret_cast<float4 *>(frow + (((uint32_t)(j >> 2) ^ sw128) << 4));
+        if (has_res) {
+            const float4 r = *slot;                         // rows / channels outside the tensor arrive as zeros
+            t[j] = __fadd_rn(t[j], r.x); t[j + 1] = __fadd_rn(t[j + 1], r.y);
+            t[j + 2] = __fadd_rn(t[j + 2], r.z); t[j + 3] = __fadd_rn(t[j + 3], r.w);
+        }
+        if (RELU) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) t[j + e] = fmaxf(t[j + e], 0.0f);
+        }
+        if (wf) *slot = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
+        if (wc) {
+            uint32_t hc[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                uint32_t idx;
+                if (RELU) {
+                    idx = fast ? quantize_f32_nonneg<true>(t[j + e], nq) : quantize_f32_nonneg<false>(t[j + e], nq);
+                } else {
+                    const uint32_t neg = __float_as_uint(t[j + e]) >> 31;
+                    idx = (fast ? quantize_f32<true>(t[j + e], nq) : quantize_f32<false>(t[j + e], nq)) | (neg << nbits);
+                }
+                hc[e] = __half_as_ushort(lut[idx]);
+            }
+            const int hi = (j >> 2) & 1;
+            cw[2 * hi] = hc[0] | (hc[1] << 16);
+            cw[2 * hi + 1] = hc[2] | (hc[3] << 16);
+            if (hi) *reinterpret_cast<uint4 *>(crow + (((uint32_t)(j >> 3) ^ sw64) << 4)) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+        }
+    }
+}
+
 // MODE 0: A and B tiles stream through the stage ring.  MODE 1: all weight tiles resident in shared memory
 // (tile = filter tap, one 64-channel block), only A streams.  MODE 2 (the hi/lo stem conv): resident weights,
 // one halo load per A plane (x_hi, x_lo) covering all R filter rows, and a step table naming, per
@@ -192,7 +270,9 @@ constexpr int GM_SMEM_BUDGET = 227 * 1024;
 // input pixels lands once in shared memory and filter tap (r, s) is the same buffer read from row
 // r * (wbox+S-1) + s on: MMA row m is halo row start + m, i.e. output pixel (m / hw, m % hw), of which the
 // columns m % hw >= wbox are junk and dropped by the epilogue.  A traffic per tile falls from R*S boxes to one.
-template <int BLOCK_N, int MODE>
+// RELU: the epilogue's ReLU flag as a compile-time constant (the encode after a ReLU needs no sign handling; a
+// run-time branch would duplicate the staging code inside one kernel and cost instruction-cache misses).
+template <int BLOCK_N, int MODE, bool RELU>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD,
@@ -428,8 +508,6 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const bool store_thread = (ew == 0 && lane == 0);
         uint8_t *st_f32 = smem + g.epi_off + grp * g.epi_group_bytes;   // [128][32] fp32, 128B swizzle
         uint8_t *st_codes = st_f32 + g.epi_codes_off;                   // [128][32] fp16,  64B swizzle
-        const uint32_t sw128 = (uint32_t)(row & 7);             // 16B piece index ^= row % 8
-        const uint32_t sw64 = (uint32_t)((row >> 1) & 3);       // 16B piece index ^= (row / 2) % 4
         const Quant nq = make_quant(g.write_codes ? g.next_sf : 1.0f, (float)((1u << g.next_bits) - 1u));
         const bool has_res = g.residual != nullptr;
         constexpr int CHUNKS = BLOCK_N / 64;                    // 32-column chunks per group and tile
@@ -491,22 +569,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     tc_fence_before();
                     mbar_arrive(&tempty_bar[acc]);
                 }
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const int c = c0 + j;
-                    const bool cvalid = c < g.Cout;               // Cout % 4 == 0
-                    if (g.bias && cvalid) {
-                        const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bias + c));
-                        t[j] = __fadd_rn(t[j], b.x); t[j + 1] = __fadd_rn(t[j + 1], b.y);
-                        t[j + 2] = __fadd_rn(t[j + 2], b.z); t[j + 3] = __fadd_rn(t[j + 3], b.w);
-                    }
-                    if (g.bn_a && cvalid) {
-                        const float4 a = __ldg(reinterpret_cast<const float4 *>(g.bn_a + c));
-                        const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bn_b + c));
-                        t[j] = __fmaf_rn(t[j], a.x, b.x); t[j + 1] = __fmaf_rn(t[j + 1], a.y, b.y);
-                        t[j + 2] = __fmaf_rn(t[j + 2], a.z, b.z); t[j + 3] = __fmaf_rn(t[j + 3], a.w, b.w);
-                    }
-                }
+                if (c0 + 32 <= g.Cout) epi_affine<true>(t, g, c0); else epi_affine<false>(t, g, c0);
                 if constexpr (MODE == 2) {
                     if (g.pool) {
                         // ---- fused ReLU + 3x3 / stride 2 / pad 1 max-pool + next-layer encode (stem) ----
@@ -520,7 +583,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             float4 v = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
-                            if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                            if (RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                             if (!pvalid) v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
                             *reinterpret_cast<float4 *>(st_f32 + mrow * 128 + (((uint32_t)(j >> 2) ^ (uint32_t)(mrow & 7)) << 4)) = v;
                         }
@@ -575,39 +638,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     if (store_thread) bulk_wait_read0();
                     epi_bar_sync(1 + grp);
                 }
-                uint32_t cw[4];                                   // 8 codes = one 16-byte piece
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 *slot = reinterpret_cast<float4 *>(st_f32 + row * 128 + (((uint32_t)(j >> 2) ^ sw128) << 4));
-                    if (!row_live) continue;
-                    if (has_res) {
-                        const float4 r = *slot;                   // rows / channels outside the tensor arrive as zeros
-                        t[j] = __fadd_rn(t[j], r.x); t[j + 1] = __fadd_rn(t[j + 1], r.y);
-                        t[j + 2] = __fadd_rn(t[j + 2], r.z); t[j + 3] = __fadd_rn(t[j + 3], r.w);
-                    }
-                    if (g.relu) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) t[j + e] = fmaxf(t[j + e], 0.0f);
-                    }
-                    if (g.write_f32) *slot = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
-                    if (g.write_codes) {
-                        uint32_t hc[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const uint32_t neg = __float_as_uint(t[j + e]) >> 31;
-                            const uint32_t q = g.next_fastdiv ? quantize_f32<true>(t[j + e], nq) : quantize_f32<false>(t[j + e], nq);
-                            hc[e] = __half_as_ushort(lut[q | (neg << g.next_bits)]);
-                        }
-                        const int hi = (j >> 2) & 1;
-                        cw[2 * hi] = hc[0] | (hc[1] << 16);
-                        cw[2 * hi + 1] = hc[2] | (hc[3] << 16);
-                        if (hi) {
-                            const uint32_t piece = (uint32_t)(j >> 3);
-                            *reinterpret_cast<uint4 *>(st_codes + row * 64 + ((piece ^ sw64) << 4)) =
-                                make_uint4(cw[0], cw[1], cw[2], cw[3]);
-                        }
-                    }
-                }
+                if (row_live) epi_stage<RELU>(t, g, st_f32, st_codes, row, has_res, lut, nq);
                 if (has_res) res_phase ^= 1u;
                 // (c) staging complete: hand it to the async proxy and store
                 fence_proxy_async();
@@ -742,14 +773,14 @@ static int launch_conv_mode(const CUtensorMap &tmA, const CUtensorMap &tmB, cons
     static const bool skip_mma = getenv("TQ_CONV_SKIP_MMA") != nullptr, skip_tma = getenv("TQ_CONV_SKIP_TMA") != nullptr;
     g.dbg_skip_mma = skip_mma ? 1 : 0;
     g.dbg_skip_tma = skip_tma ? 1 : 0;
-    auto kern = conv_igemm_f16_kernel<BLOCK_N, MODE>;
-    static bool attr_set[64] = {false};
+    auto kern = g.relu ? conv_igemm_f16_kernel<BLOCK_N, MODE, true> : conv_igemm_f16_kernel<BLOCK_N, MODE, false>;
+    static bool attr_set[2][64] = {{false}};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    if (dev >= 0 && dev < 64 && !attr_set[g.relu ? 1 : 0][dev]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_BUDGET) != cudaSuccess)
             return check_launch("cudaFuncSetAttribute(conv_igemm_f16_kernel)");
-        attr_set[dev] = true;
+        attr_set[g.relu ? 1 : 0][dev] = true;
     }
     const int total = g.m_tiles * g.n_tiles;
     const int grid = total < num_sms() ? total : num_sms();
