@@ -148,6 +148,28 @@ class KernelTimer:
         return len(rec), sum(w for _, _, w in rec), sum(a.elapsed_time(b) for a, b, _ in rec)
 
 
+def ncu_conv_traffic():
+    """DRAM bytes per launch of the conv kernel (mean over the wrapped-conv launches of the profiled steps) from
+    the committed ncu launch list of this same command (profiles/r01_launches_final_steps2.csv:
+    dram__bytes_read.sum + dram__bytes_write.sum per launch), or None."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01_launches_final_steps2.csv")
+    try:
+        rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+        h = rows[0]
+        ik, im, iv, iu, iid = (h.index(c) for c in ("Kernel Name", "Metric Name", "Metric Value", "Metric Unit", "ID"))
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        total, ids = 0.0, set()
+        for r in rows[1:]:
+            # wrapped convs only: MODE 2 (<64, 2, ...>) is the unquantised stem conv
+            if "conv_igemm_f16_kernel" in r[ik] and "<64, 2," not in r[ik] and r[im].startswith("dram__bytes_"):
+                total += float(r[iv].replace(",", "")) * scale[r[iu]]
+                ids.add(r[iid])
+        return (total / len(ids), os.path.relpath(path, ROOT)) if ids else (None, None)
+    except Exception:
+        return None, None
+
+
 def tr_encode_roofline(dev, peak, peak_src, iters=20):
     """BASELINE metric 1: TR-encode GB/s at the largest ResNet-18 activation (256x64x56x56 fp32,
     g=1, 9-bit, 3 terms, drop-in fp32 -> fp32 contract: 8 B/element).  Two 205 MB inputs rotate
@@ -210,7 +232,7 @@ def run_b200(args):
         switched, skipped = tr_layer.use_tensor_cores(model)
         assert len(switched) == 19 and not skipped, (switched, skipped)
         if args.conv_backend == "fused":
-            model = fused.FusedResNet(model)
+            model = fused.FusedResNet(model, stem=args.stem)
     images = [im.to(in_dtype) for im in images]
     use_graphs = args.conv_backend == "fused" and not args.no_cuda_graphs
     runner = inference.ShardedInference(model, dev, cuda_graphs=use_graphs, gather=args.gather)
@@ -350,10 +372,13 @@ def run_b200(args):
             except Exception:
                 tpeak, tsrc = 1400.0, "fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)"
             tach = cv_flops / (cv_ms * 1e-3) / 1e12
+            traffic, traffic_src = ncu_conv_traffic()
             conv_roof = {"kernel": "tq::conv_igemm_f16_kernel (tcgen05 kind::f16 implicit GEMM on term codes with "
                                    "fused BN/residual/ReLU/encode epilogue, 19 launches per forward)",
                          "bound": "tensor", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s", "frac": tach / tpeak,
-                         "traffic": None, "peak_source": tsrc, "launches_timed": n_cv,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": 3.53e9 / 19,
+                         "peak_source": tsrc, "launches_timed": n_cv,
                          "algorithmic_flops": cv_flops, "kernel_ms_total": cv_ms, "share_of_step": cv_ms / ms_instrumented,
                          "timed": "CUDA events around each launch in an eager pass of the same K steps"}
         dominant, other = (conv_roof, tr_roof) if (conv_roof and cv_ms > tr_ms) else (tr_roof, conv_roof)
@@ -475,6 +500,8 @@ def main():
                          "unchanged torchvision graph; cudnn_fp32: the reference's float path")
     ap.add_argument("--input-dtype", default="bf16", choices=["bf16", "fp32"],
                     help="dtype of the image batches in HBM and over PCIe (fused engine; bf16 per BASELINE configs[1])")
+    ap.add_argument("--stem", default="tcgen05_pool", choices=["tcgen05", "tcgen05_pool", "cudnn"],
+                    help="fused engine: two-launch tensor-core stem, one-kernel stem (pooling in the conv epilogue), cuDNN")
     ap.add_argument("--gather", default="step", choices=["step", "async", "end"],
                     help="when the other ranks' logits are collected (inference.ShardedInference)")
     ap.add_argument("--diag", action="store_true", help="extra timed loops: graph vs eager, no clock sampler")

@@ -202,6 +202,10 @@ int tq_stem_conv7x7s2_dt(const void *x, int x_dtype, void *x2_scratch, const voi
  * the fp16 term codes of that tensor for the first wrapped conv's quantiser (tr_layer.py:96-99).  Each tile
  * computes the (2P+1) x (2Q+1) conv pixels under P x Q pooled pixels, so the conv output (822 MB at batch 256)
  * never reaches HBM.  Same values as tq_stem_conv7x7s2_dt followed by tq_bn_relu_maxpool_encode.
+ * CONTRACT: bn_a >= 0.  The pooling takes the window maximum of the raw conv sums and applies the affine once
+ * per pooled value; a channel with a negative slope is handled by the caller folding sign(bn_a) into that
+ * channel's weights and passing |bn_a| (conv_codes.pack_stem_weight(w, bn_a) / stem_conv_pool do this): negation
+ * of a channel's weights negates its sums exactly, and max_i fma(x_i, a, b) = fma(max_i(sign(a) x_i), |a|, b).
  */
 int tq_stem_conv7x7s2_pool(const void *x, int x_dtype, void *x2_scratch, const void *w2,
                            const float *bn_a, const float *bn_b, int relu, float *out, void *out_codes,

@@ -91,15 +91,19 @@ def bn_relu_maxpool_encode(x_nhwc, bn, relu=True, next_quant=None):
     return out, codes
 
 
-def pack_stem_weight(w):
+def pack_stem_weight(w, channel_sign=None):
     """(Cout, 3, 7, 7) fp32 -> fp16 [8][Cout][64] for tq_stem_conv7x7s2: the kernel padded to 8x8 and
     folded 2x2 (r = 2R + dr, s = 2S + ds), row R holding (S, dr, ds, c) with c padded to 4, as the
-    two operand planes (w_hi, w_lo) with w = w_hi + w_lo in fp16 pairs."""
+    two operand planes (w_hi, w_lo) with w = w_hi + w_lo in fp16 pairs.  `channel_sign` (+1 / -1 per
+    output channel) is folded into the weights (the one-kernel stem pools before the BatchNorm affine and
+    needs non-negative slopes: see stem_conv_pool)."""
     Cout, Cin, kh, kw = w.shape
     if (Cin, kh, kw) != (3, 7, 7):
         raise NotImplementedError("stem conv packing expects a (Cout, 3, 7, 7) weight")
     w8 = torch.zeros(Cout, 4, 8, 8, dtype=torch.float32, device=w.device)
     w8[:, :3, :7, :7] = w.detach().float()
+    if channel_sign is not None:
+        w8 = w8 * channel_sign.view(-1, 1, 1, 1).to(w8)
     # [co, c, R, dr, S, ds] -> [R, co, S, dr, ds, c]
     w2 = w8.view(Cout, 4, 4, 2, 4, 2).permute(2, 0, 4, 3, 5, 1).reshape(4, Cout, 64)
     hi = w2.half()
@@ -128,10 +132,20 @@ def stem_conv7x7s2(x_nhwc, w2, scratch=None):
     return out, scratch
 
 
+def stem_pool_operands(w, bn):
+    """Operands of the one-kernel stem for a (Cout, 3, 7, 7) weight and BatchNorm affine (a, b): the kernel pools
+    the raw conv sums and applies the affine once per pooled value, which needs a >= 0, so sign(a) moves into the
+    channel's weights (exact) and |a| is passed.  Returns (w2_signed, (|a|, b))."""
+    a, b = bn
+    sign = torch.where(a < 0, -torch.ones_like(a), torch.ones_like(a))
+    return pack_stem_weight(w, sign), (a.abs().contiguous(), b.contiguous())
+
+
 def stem_conv_pool(x_nhwc, w2, bn, relu=True, next_quant=None, scratch=None):
     """The whole stem in one launch: maxpool3x3/s2/p1(relu(fma(conv7x7s2(x), a, b))) -> fp32
     [N, Hp, Wp, Cout] plus the fp16 term codes of the result (next_quant = (sf, bits, terms)).
     Same values as stem_conv7x7s2 followed by bn_relu_maxpool_encode; the conv output never reaches HBM.
+    `w2`, `bn` must come from stem_pool_operands (sign of the slope folded into the weights, bn[0] >= 0).
     Returns (out, codes or None, scratch)."""
     if x_nhwc.dtype not in _STEM_DTYPES or not x_nhwc.is_contiguous() or x_nhwc.shape[-1] != 3:
         raise RuntimeError("stem_conv_pool expects a contiguous fp32 / bf16 / fp16 [N, H, W, 3] tensor")

@@ -569,52 +569,85 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     tc_fence_before();
                     mbar_arrive(&tempty_bar[acc]);
                 }
-                if (c0 + 32 <= g.Cout) epi_affine<true>(t, g, c0); else epi_affine<false>(t, g, c0);
                 if constexpr (MODE == 2) {
                     if (g.pool) {
-                        // ---- fused ReLU + 3x3 / stride 2 / pad 1 max-pool + next-layer encode (stem) ----
-                        // the tile is the (2P+1) x (2Q+1) box of conv pixels under P x Q pooled pixels: stage it
-                        // (pixels outside the conv output as -inf), pool out of shared memory, store the pooled tile
-                        const int hl = mrow / g.hw, wl = mrow % g.hw;
-                        const int oh = th * g.step_h + g.off_h + hl, ow = tw * g.step_w + g.off_w + wl;
-                        const bool pvalid = hl < g.hbox && oh >= 0 && oh < g.Ho && ow >= 0 && ow < g.Wo;
-                        if (store_thread) bulk_wait_read0();
-                        epi_bar_sync(1 + grp);
+                        // ---- fused BatchNorm + ReLU + 3x3 / stride 2 / pad 1 max-pool + next-layer encode (stem) ----
+                        // The tile is the (2P+1) x (2Q+1) box of conv pixels under P x Q pooled pixels.  The RAW conv
+                        // sums are staged; the pooling threads take the window maximum out of shared memory (window
+                        // positions outside the conv output are replaced by the centre, which always exists) and only
+                        // then apply fma(., bn_a, bn_b), ReLU and the encode -- once per pooled value instead of once
+                        // per conv value.  max commutes with the affine because bn_a >= 0 here: the host folds
+                        // sign(bn_a) into the weights of the channel (exact: products and truncated sums negate
+                        // exactly), so max_i fma(x_i, a, b) = fma(max_i(sign(a) x_i), |a|, b).
+                        // (the conv staging tile is never read by TMA; the previous tile's pooling reads of it
+                        // finished before that tile's last group barrier)
+                        {
+                            uint8_t *frow = st_f32 + mrow * 128;
+                            const uint32_t sw = (uint32_t)(mrow & 7);
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 v = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
-                            if (RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                            if (!pvalid) v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-                            *reinterpret_cast<float4 *>(st_f32 + mrow * 128 + (((uint32_t)(j >> 2) ^ (uint32_t)(mrow & 7)) << 4)) = v;
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4 *>(frow + (((uint32_t)(j >> 2) ^ sw) << 4)) =
+                                    make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
                         }
                         epi_bar_sync(1 + grp);
                         uint8_t *st_pool = st_codes, *st_pcodes = st_codes + 4096;   // [P*Q][32] fp32 / fp16 tiles
                         const int pp = mrow >> 2, cb = mrow & 3;                     // pooled pixel, 8-channel block
-                        if (pp < g.pool_p * g.pool_q) {
+                        float pv[8];
+                        const bool pool_thread = pp < g.pool_p * g.pool_q;
+                        if (pool_thread) {
                             const int pl = pp / g.pool_q, ql = pp % g.pool_q;
+                            // conv pixel of window position (dy, dx): (2 (p0 + pl) - 1 + dy, 2 (q0 + ql) - 1 + dx)
+                            const int oh0 = 2 * (th * g.pool_p + pl) - 1, ow0 = 2 * (tw * g.pool_q + ql) - 1;
+                            int rowoff[3], coloff[3];
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) {
+                                rowoff[d] = (2 * pl + (((unsigned)(oh0 + d) < (unsigned)g.Ho) ? d : 1)) * g.hw;
+                                coloff[d] = 2 * ql + (((unsigned)(ow0 + d) < (unsigned)g.Wo) ? d : 1);
+                            }
                             float4 m0 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), m1 = m0;
 #pragma unroll
                             for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                                 for (int dx = 0; dx < 3; ++dx) {
-                                    const int mm = (2 * pl + dy) * g.hw + 2 * ql + dx;
+                                    const int mm = rowoff[dy] + coloff[dx];
                                     const uint32_t sw = (uint32_t)(mm & 7);
                                     const float4 a = *reinterpret_cast<const float4 *>(st_f32 + mm * 128 + (((uint32_t)(2 * cb) ^ sw) << 4));
                                     const float4 b = *reinterpret_cast<const float4 *>(st_f32 + mm * 128 + (((uint32_t)(2 * cb + 1) ^ sw) << 4));
                                     m0.x = fmaxf(m0.x, a.x); m0.y = fmaxf(m0.y, a.y); m0.z = fmaxf(m0.z, a.z); m0.w = fmaxf(m0.w, a.w);
                                     m1.x = fmaxf(m1.x, b.x); m1.y = fmaxf(m1.y, b.y); m1.z = fmaxf(m1.z, b.z); m1.w = fmaxf(m1.w, b.w);
                                 }
+                            pv[0] = m0.x; pv[1] = m0.y; pv[2] = m0.z; pv[3] = m0.w; pv[4] = m1.x; pv[5] = m1.y; pv[6] = m1.z; pv[7] = m1.w;
+                            const int c8 = c0 + 8 * cb;
+                            if (c8 < g.Cout) {                                        // Cout % 8 == 0
+                                const float4 a0 = __ldg(reinterpret_cast<const float4 *>(g.bn_a + c8));
+                                const float4 a1 = __ldg(reinterpret_cast<const float4 *>(g.bn_a + c8 + 4));
+                                const float4 b0 = __ldg(reinterpret_cast<const float4 *>(g.bn_b + c8));
+                                const float4 b1 = __ldg(reinterpret_cast<const float4 *>(g.bn_b + c8 + 4));
+                                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    pv[e] = __fmaf_rn(pv[e], av[e], bv[e]);
+                                    if (RELU) pv[e] = fmaxf(pv[e], 0.0f);
+                                }
+                            }
+                        }
+                        // the pooled staging tiles are free once this group's previous TMA store has read them
+                        if (store_thread) bulk_wait_read0();
+                        epi_bar_sync(1 + grp);
+                        if (pool_thread) {
                             const uint32_t psw = (uint32_t)(pp & 7);
-                            *reinterpret_cast<float4 *>(st_pool + pp * 128 + (((uint32_t)(2 * cb) ^ psw) << 4)) = m0;
-                            *reinterpret_cast<float4 *>(st_pool + pp * 128 + (((uint32_t)(2 * cb + 1) ^ psw) << 4)) = m1;
+                            *reinterpret_cast<float4 *>(st_pool + pp * 128 + (((uint32_t)(2 * cb) ^ psw) << 4)) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+                            *reinterpret_cast<float4 *>(st_pool + pp * 128 + (((uint32_t)(2 * cb + 1) ^ psw) << 4)) = make_float4(pv[4], pv[5], pv[6], pv[7]);
                             if (g.write_codes) {
-                                const float pv[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
                                 uint32_t hc[8];
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) {
-                                    const uint32_t neg = __float_as_uint(pv[e]) >> 31;
-                                    const uint32_t q = g.next_fastdiv ? quantize_f32<true>(pv[e], nq) : quantize_f32<false>(pv[e], nq);
-                                    hc[e] = __half_as_ushort(lut[q | (neg << g.next_bits)]);
+                                    uint32_t idx;
+                                    if (RELU) idx = g.next_fastdiv ? quantize_f32_nonneg<true>(pv[e], nq) : quantize_f32_nonneg<false>(pv[e], nq);
+                                    else idx = (g.next_fastdiv ? quantize_f32<true>(pv[e], nq) : quantize_f32<false>(pv[e], nq)) |
+                                               ((__float_as_uint(pv[e]) >> 31) << g.next_bits);
+                                    hc[e] = __half_as_ushort(lut[idx]);
                                 }
                                 *reinterpret_cast<uint4 *>(st_pcodes + pp * 64 + (((uint32_t)cb ^ (uint32_t)((pp >> 1) & 3)) << 4)) =
                                     make_uint4(hc[0] | (hc[1] << 16), hc[2] | (hc[3] << 16), hc[4] | (hc[5] << 16), hc[6] | (hc[7] << 16));
@@ -630,6 +663,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         continue;
                     }
                 }
+                if (c0 + 32 <= g.Cout) epi_affine<true>(t, g, c0); else epi_affine<false>(t, g, c0);
                 // (b) staging: with a residual it already holds this chunk's residual tile; otherwise the previous
                 //     store of this group must have finished reading it before it is overwritten
                 if (has_res) {
@@ -1077,10 +1111,12 @@ static int stem_impl(const void *x, int x_dtype, void *x2_scratch, const void *w
     // accumulator) and one of x_lo (w_hi -> cross).  The main accumulator is split in two (rows 0-1 / 2-3):
     // tensor-core accumulation truncates, so fewer steps per accumulator = less bias; the small cross terms
     // live apart from the large ones and everything is summed once, in fp32 RN, in the epilogue.
-    g.prog_steps = lo_plane ? 8 : 4; g.nb_tiles = 8; g.n_groups = 3;
+    static const int stem_groups = getenv("TQ_STEM_GROUPS") ? atoi(getenv("TQ_STEM_GROUPS")) : 3;
+    g.prog_steps = lo_plane ? 8 : 4; g.nb_tiles = 8; g.n_groups = stem_groups < 1 ? 1 : (stem_groups > 3 ? 3 : stem_groups);
+    const uint32_t g_main1 = g.n_groups >= 3 ? 1u : 0u, g_cross = (uint32_t)(g.n_groups - 1);
     for (uint32_t R = 0; R < 4; ++R) {
-        g.prog_mma[R] = 2u | (R << 4) | ((R < 2 ? 0u : 1u) << 8) | ((4u + R) << 12) | (2u << 16);
-        g.prog_mma[4 + R] = 1u | (R << 4) | (2u << 8);
+        g.prog_mma[R] = 2u | (R << 4) | ((R < 2 ? 0u : g_main1) << 8) | ((4u + R) << 12) | (g_cross << 16);
+        g.prog_mma[4 + R] = 1u | (R << 4) | (g_cross << 8);
     }
 
     CUtensorMap tmA, tmB, tmC, tmD;

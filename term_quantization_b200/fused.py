@@ -64,11 +64,11 @@ class _Conv:
 class FusedResNet(nn.Module):
     """Wraps a calibrated, TQ-converted torchvision ResNet built from BasicBlocks."""
 
-    def __init__(self, model, stem="tcgen05"):
-        """stem: 'tcgen05' (stem conv on the tensor cores, then the fused BN+ReLU+max-pool+encode pass),
-        'tcgen05_pool' (the whole stem in ONE kernel, pooling in the conv epilogue: no 822 MB conv output in
-        HBM, but its epilogue is instruction-bound today and it is ~5 % slower than the two launches), or
-        'cudnn' (cuDNN's fp32 conv)."""
+    def __init__(self, model, stem="tcgen05_pool"):
+        """stem: 'tcgen05_pool' (the whole stem -- conv, BatchNorm, ReLU, max-pool, first encode -- in ONE
+        tensor-core kernel, pooling in the conv epilogue: the 822 MB conv output never reaches HBM),
+        'tcgen05' (stem conv on the tensor cores, then the fused BN+ReLU+max-pool+encode pass; bit-identical,
+        ~1 % slower end to end), or 'cudnn' (cuDNN's fp32 conv)."""
         super().__init__()
         if stem not in ("tcgen05", "tcgen05_pool", "cudnn"):
             raise ValueError("stem must be 'tcgen05', 'tcgen05_pool' or 'cudnn'")
@@ -97,6 +97,8 @@ class FusedResNet(nn.Module):
                 and c1.padding == (3, 3) and c1.dilation == (1, 1) and c1.groups == 1 and c1.bias is None
                 and c1.out_channels <= 64):
             self.stem_w = conv_codes.pack_stem_weight(c1.weight)
+            if stem == "tcgen05_pool":
+                self.stem_w_pool, self.stem_bn_pool = conv_codes.stem_pool_operands(c1.weight, self.stem_bn)
         self._stem_scratch = None
 
     @staticmethod
@@ -119,7 +121,7 @@ class FusedResNet(nn.Module):
                 if self.stem_mode == "tcgen05_pool":
                     # conv + bn1 + relu + maxpool + first encode: one tensor-core kernel
                     cur, c0, self._stem_scratch = conv_codes.stem_conv_pool(
-                        x.permute(0, 2, 3, 1), self.stem_w, self.stem_bn, relu=True, next_quant=q0,
+                        x.permute(0, 2, 3, 1), self.stem_w_pool, self.stem_bn_pool, relu=True, next_quant=q0,
                         scratch=self._stem_scratch)
                 else:
                     y, self._stem_scratch = conv_codes.stem_conv7x7s2(x.permute(0, 2, 3, 1), self.stem_w,

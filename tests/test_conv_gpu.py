@@ -160,9 +160,10 @@ def test_stem_conv_pool_fused_equals_two_pass():
         want, _ = conv_codes.bn_relu_maxpool_encode(y, (a, b), relu=relu)
         nq = (float(want.abs().max()) / 512, 9, 3)
         want, want_codes = conv_codes.bn_relu_maxpool_encode(y, (a, b), relu=relu, next_quant=nq)
-        got, codes, _ = conv_codes.stem_conv_pool(x, w2, (a, b), relu=relu, next_quant=nq)
+        w2s, bns = conv_codes.stem_pool_operands(w, (a, b))      # sign of the slope folded into the weights
+        got, codes, _ = conv_codes.stem_conv_pool(x, w2s, bns, relu=relu, next_quant=nq)
         assert got.shape == want.shape
         assert torch.equal(got, want), float((got - want).abs().max())
         assert torch.equal(codes, want_codes)
-        got2, none, _ = conv_codes.stem_conv_pool(x, w2, (a, b), relu=relu)
+        got2, none, _ = conv_codes.stem_conv_pool(x, w2s, bns, relu=relu)
         assert none is None and torch.equal(got2, want)

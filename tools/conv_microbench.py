@@ -61,10 +61,11 @@ def main():
         xb = xn.bfloat16().contiguous()
         bn = (torch.rand(64, device="cuda") + 0.5, torch.randn(64, device="cuda"))
         nq = (0.01, 9, 3)
+        w2s, bns = conv_codes.stem_pool_operands(w, bn)
         for name, fn in (("stem tcgen05 hi/lo", lambda: conv_codes.stem_conv7x7s2(xn, w2, scratch)),
                          ("stem tcgen05 bf16 images", lambda: conv_codes.stem_conv7x7s2(xb, w2, scratch)),
-                         ("stem+bn+relu+pool+encode fused, fp32 images", lambda: conv_codes.stem_conv_pool(xn, w2, bn, True, nq, scratch)),
-                         ("stem+bn+relu+pool+encode fused, bf16 images", lambda: conv_codes.stem_conv_pool(xb, w2, bn, True, nq, scratch)),
+                         ("stem+bn+relu+pool+encode fused, fp32 images", lambda: conv_codes.stem_conv_pool(xn, w2s, bns, True, nq, scratch)),
+                         ("stem+bn+relu+pool+encode fused, bf16 images", lambda: conv_codes.stem_conv_pool(xb, w2s, bns, True, nq, scratch)),
                          ("stem cuDNN fp32", lambda: F.conv2d(x, w, None, 2, 3))):
             for _ in range(3):
                 fn()
