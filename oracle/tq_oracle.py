@@ -121,6 +121,43 @@ def ref_tr(x, sf, bits, g, alpha, threads=0):
     return out
 
 
+_ref_gpu = None
+
+
+def have_ref_gpu():
+    """oracle/_ref/libtq_ref_gpu.so: the reference kernel body compiled for sm_100a (ref_gpu_shim.cu)."""
+    return os.path.exists(os.path.join(_HERE, "_ref", "libtq_ref_gpu.so"))
+
+
+def ref_gpu_tr(x, sf, bits, g, alpha, out=None):
+    """The REFERENCE kernel (kernels/tr_cuda_kernel.cu:58-125, byte-identical body) launched on the GPU exactly as
+    the reference's launcher does (zeros_like + <<<ceil(n/128), 128>>>), on a torch CUDA tensor, on the current
+    stream.  The GPU-side oracle and "the kernel to beat"."""
+    import torch
+    global _ref_gpu
+    if _ref_gpu is None:
+        L = C.CDLL(os.path.join(_HERE, "_ref", "libtq_ref_gpu.so"))
+        for name in ("tq_refgpu_tr_f32", "tq_refgpu_tr_f64"):
+            fn = getattr(L, name)
+            fn.restype = C.c_int
+            fn.argtypes = [C.c_void_p, C.c_void_p, C.c_float] + [C.c_int] * 7 + [C.c_void_p]
+        _ref_gpu = L
+    assert x.is_cuda and x.is_contiguous() and x.dtype in (torch.float32, torch.float64)
+    if x.dim() == 4:
+        B, Cc, W, H = x.shape
+    else:
+        (B, Cc), W, H = x.shape, 1, 1
+    if out is None:
+        out = torch.empty_like(x)
+    fn = _ref_gpu.tq_refgpu_tr_f32 if x.dtype == torch.float32 else _ref_gpu.tq_refgpu_tr_f64
+    with torch.cuda.device(x.device):
+        rc = fn(x.data_ptr(), out.data_ptr(), float(np.float32(sf)), bits, g, alpha, B, Cc, W, H,
+                torch.cuda.current_stream(x.device).cuda_stream)
+    if rc != 0:
+        raise ValueError(f"reference GPU kernel: launch refused / failed (rc={rc})")
+    return out
+
+
 def ref_hese_terms(x, sf, bits):
     buf = (C.c_int32 * 64)()
     n = ref().tq_ref_hese_terms_f32(float(x), float(np.float32(sf)), bits, buf)

@@ -241,3 +241,30 @@ def test_hoisted_reciprocal_divide_is_exact():
     for sf in (1e-12, 1e-38, 3e12):
         xs = small if sf < 1 else x[:, :5000] * np.float32(1e12)
         assert bits_equal(_tr(xs, sf, 8, 1, 3), O.tr(xs, sf, 8, 1, 3)), sf
+
+
+@pytest.mark.skipif(not O.have_ref_gpu(), reason="oracle/_ref/libtq_ref_gpu.so not built")
+def test_matches_reference_kernel_on_the_gpu_at_full_sizes():
+    """GPU-vs-GPU parity at BASELINE sizes: the reference's own kernel (kernels/tr_cuda_kernel.cu:58-125, body
+    byte-identical, compiled for sm_100a by oracle/Makefile) against this repo's kernels on the same tensors,
+    bit for bit: the largest ResNet-18 activation (51,380,224 values, g = 1) and every ResNet-18 conv-weight shape
+    in the reference's OIHW layout (groups of 8 input channels, stride kh*kw), plus g in {2, 4, 16, 32}."""
+    from term_quantization_b200 import tr_cuda
+    gen = torch.Generator(device="cuda").manual_seed(12)
+    x = torch.randn(1, 256 * 64 * 56 * 56, 1, 1, device="cuda", generator=gen) * 1.7      # both signs
+    for bits, k in ((9, 3), (8, 4), (9, 2)):
+        sf = float(x.abs().max()) / 2 ** bits
+        assert torch.equal(tr_cuda.tr(x, sf, bits, 1, k).view(torch.int32), O.ref_gpu_tr(x, sf, bits, 1, k).view(torch.int32))
+    for (o, i, kk) in ((64, 64, 3), (128, 64, 3), (128, 64, 1), (128, 128, 3), (256, 128, 3), (256, 256, 3),
+                       (512, 256, 3), (512, 256, 1), (512, 512, 3)):
+        w = torch.randn(o, i, kk, kk, device="cuda", generator=gen) * (2.0 / (i * kk * kk)) ** 0.5
+        for bits in (8, 9):
+            sf = float(w.abs().max()) / 2 ** (bits - 1)
+            got, want = tr_cuda.tr(w, sf, bits, 8, 12), O.ref_gpu_tr(w, sf, bits, 8, 12)
+            assert torch.equal(got.view(torch.int32), want.view(torch.int32)), (o, i, kk, bits)
+    w2 = torch.randn(4096, 1024, device="cuda", generator=gen) * 0.03
+    sf = float(w2.abs().max()) / 128
+    for g_, a_ in ((2, 3), (4, 6), (8, 12), (16, 20), (32, 40)):
+        assert torch.equal(tr_cuda.tr(w2, sf, 8, g_, a_).view(torch.int32), O.ref_gpu_tr(w2, sf, 8, g_, a_).view(torch.int32))
+    xd = torch.randn(2048, 512, device="cuda", generator=gen, dtype=torch.float64)
+    assert torch.equal(tr_cuda.tr(xd, 0.01, 8, 8, 12).view(torch.int64), O.ref_gpu_tr(xd, 0.01, 8, 8, 12).view(torch.int64))
