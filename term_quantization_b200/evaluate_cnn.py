@@ -33,8 +33,29 @@ def eval_model(args, model, val_loader, criterion, weight_bits, group_size, weig
             m.hist_bins.zero_()
     util.validate(val_loader, qmodel, criterion, args, verbose=args.verbose, pct=0.05)
     tr_layer.set_tr_tracking(qmodel, False)
-    _, acc = util.validate(val_loader, qmodel, criterion, args, verbose=args.verbose)
+    _, acc = util.validate(val_loader, select_engine(qmodel, getattr(args, "engine", "float")), criterion, args,
+                           verbose=args.verbose)
     return acc, tmacs, avg_terms, params
+
+
+def select_engine(qmodel, engine):
+    """How the calibrated model runs the validation pass.
+    'float'   -- the reference's path: TR kernels + cuDNN fp32 conv on dequantised tensors (tr_layer.py:124-126);
+    'tcgen05' -- every supported wrapped conv on integer term codes with the tcgen05 kernel, module tree unchanged;
+    'fused'   -- fused.FusedResNet (BasicBlock ResNets): BN / residual / ReLU / next encode in the conv epilogue;
+    'auto'    -- 'fused' where the topology allows it, else 'tcgen05'."""
+    if engine == "float":
+        return qmodel
+    from . import fused
+    qmodel = qmodel.to(memory_format=torch.channels_last)
+    switched, skipped = tr_layer.use_tensor_cores(qmodel)
+    if engine in ("fused", "auto"):
+        try:
+            return fused.FusedResNet(qmodel)
+        except (NotImplementedError, AttributeError):
+            if engine == "fused":
+                raise
+    return qmodel
 
 
 def main(argv=None):
@@ -48,6 +69,8 @@ def main(argv=None):
     parser.add_argument('-v', '--verbose', action='store_true')
     parser.add_argument('--images', default=1024, type=int, help='synthetic validation images')
     parser.add_argument('--quick', action='store_true', help='one TR setting only')
+    parser.add_argument('--engine', default='float', choices=['float', 'tcgen05', 'fused', 'auto'],
+                        help='how the calibrated model runs (float = the reference path)')
     parser.add_argument('--out-file', default=None)
     args = parser.parse_args(argv)
     if not torch.cuda.is_available():

@@ -309,3 +309,17 @@ def test_other_cnn_configs_layer_by_layer_on_tensor_cores(arch, size, expect_gro
     assert got.shape == ref.shape and bool(torch.isfinite(got).all())
     print(f"{arch}: {len(switched)} convs on tcgen05, {len(skipped)} grouped on the float path, worst err/tol {worst:.2f}, "
           f"logit rel diff {float((got - ref).abs().max()) / max(float(ref.abs().max()), 1e-30):.2e}")
+
+
+def test_evaluate_cnn_driver_engines(tmp_path):
+    """evaluate_cnn (mirror of evaluate_cnn.py) end to end on synthetic data: the reference float path and the
+    fused tensor-core engine give the same term-pair counts and a finite accuracy."""
+    from term_quantization_b200 import evaluate_cnn
+    res = {}
+    for engine in ("float", "auto"):
+        res[engine] = evaluate_cnn.main(["-a", "resnet18", "-b", "16", "--images", "32", "--quick", "--engine", engine,
+                                         "--out-file", str(tmp_path / f"{engine}.json")])
+        assert len(res[engine]["tr-data3"]["accs"]) == 1
+    # data_terms * (alpha / g) * MACs = 3 * 1.5 * 1,695,547,392, accumulated in float32 (thop/profile.py:72-73)
+    assert res["float"]["tr-data3"]["tmacs"] == res["auto"]["tr-data3"]["tmacs"]
+    assert abs(res["float"]["tr-data3"]["tmacs"][0] / (3 * 1.5 * 1695547392) - 1) < 1e-6
