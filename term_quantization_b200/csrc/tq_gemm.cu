@@ -286,9 +286,9 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint8_t *bstat = smem + g.bstat_off;            // stationary B tiles (program mode)
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + g.bar_off);
     uint64_t *empty_bar = full_bar + GM_MAX_STAGES;
-    uint64_t *tfull_bar = empty_bar + GM_MAX_STAGES;    // [2] accumulator ready
-    uint64_t *tempty_bar = tfull_bar + 2;               // [2] accumulator drained
-    uint64_t *bfull_bar = tempty_bar + 2;               // stationary weights landed
+    uint64_t *tfull_bar = empty_bar + GM_MAX_STAGES;    // [3] accumulator ready
+    uint64_t *tempty_bar = tfull_bar + 3;               // [3] accumulator drained
+    uint64_t *bfull_bar = tempty_bar + 3;               // stationary weights landed
     uint64_t *res_bar = bfull_bar + 1;                  // [4] residual tile landed in an epilogue group's staging
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_bar + GM_EPI_GROUPS);
     constexpr bool prog = MODE != 0;
@@ -297,8 +297,11 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = g.m_tiles * g.n_tiles;
     const int kblocks = g.R * g.S * g.kc_blocks;
-    uint32_t TMEM_COLS = 32;                            // power of two >= 2 accumulator stages
-    while (TMEM_COLS < (uint32_t)(2 * acc_cols)) TMEM_COLS <<= 1;
+    // accumulator stages in TMEM: three when they fit the 512 columns (the MMA issuer may then run two tiles ahead of
+    // an epilogue that holds its accumulator until the last chunk is in registers), else two
+    const int ACC_STAGES = 3 * acc_cols <= 512 ? 3 : 2;
+    uint32_t TMEM_COLS = 32;                            // power of two >= the accumulator stages
+    while (TMEM_COLS < (uint32_t)(ACC_STAGES * acc_cols)) TMEM_COLS <<= 1;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -318,7 +321,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         mbar_init(bfull_bar, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 256); }   // 256 = two epilogue groups
+        for (int i = 0; i < 3; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 256); }   // 256 = two epilogue groups
         for (int i = 0; i < GM_EPI_GROUPS; ++i) mbar_init(&res_bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -485,7 +488,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     }
                 }
                 umma_commit(&tfull_bar[acc]);                           // accumulator complete
-                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
             }
         }
         __syncwarp();
@@ -498,7 +501,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         // The residual tile is fetched by TMA into the fp32 staging tile (coalesced, asynchronous), updated in
         // place and stored back out by TMA.
         const int grp = (warp - 4) >> 2;                        // 0..3
-        const int acc = grp >> 1, half = grp & 1;
+        const int pair = grp >> 1, half = grp & 1;               // the pair takes every second tile of this CTA
         const int ew = warp & 3;                                // TMEM lanes 32*ew .. 32*ew+31
         const int mrow = ew * 32 + lane;                        // accumulator row = TMEM lane
         // staging row of this accumulator row: dense (hbox x wbox) pixel order; in halo mode the columns
@@ -512,10 +515,12 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const bool has_res = g.residual != nullptr;
         constexpr int CHUNKS = BLOCK_N / 64;                    // 32-column chunks per group and tile
         const uint32_t res_bytes = (uint32_t)(g.wbox * g.hbox * g.nbox) * 128u;
-        uint32_t acc_phase = 0, res_phase = 0;
+        uint32_t res_phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            if ((it & 1) != acc) continue;
+            if ((it & 1) != pair) continue;
+            const int acc = it % ACC_STAGES;                          // accumulator stage of this tile and its use parity
+            const uint32_t acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
             const int n_tile = tile % g.n_tiles, m_tile = tile / g.n_tiles;
             const int tw = m_tile % g.tiles_w, th = (m_tile / g.tiles_w) % g.tiles_h, tn = m_tile / (g.tiles_w * g.tiles_h);
             const int w0 = tw * g.wbox, h0 = th * g.hbox, n0 = tn * g.nbox;
@@ -525,7 +530,6 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 tc_fence_after();
                 tc_fence_before();
                 mbar_arrive(&tempty_bar[acc]);
-                acc_phase ^= 1u;
                 continue;
             }
 #pragma unroll 1
@@ -683,7 +687,6 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     bulk_commit();
                 }
             }
-            acc_phase ^= 1u;
         }
         if (store_thread) bulk_wait0();
     }
