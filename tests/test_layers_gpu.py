@@ -323,3 +323,29 @@ def test_evaluate_cnn_driver_engines(tmp_path):
     # data_terms * (alpha / g) * MACs = 3 * 1.5 * 1,695,547,392, accumulated in float32 (thop/profile.py:72-73)
     assert res["float"]["tr-data3"]["tmacs"] == res["auto"]["tr-data3"]["tmacs"]
     assert abs(res["float"]["tr-data3"]["tmacs"][0] / (3 * 1.5 * 1695547392) - 1) < 1e-6
+
+
+def test_fused_resnet34_odd_resolution():
+    """The fused engine on another BasicBlock ResNet and a ragged shape (batch 3, 160 x 192: 40 x 48 ... 5 x 6 maps,
+    partial tiles everywhere): same logits as the layer-by-layer tensor-core path up to the fused BatchNorm's
+    1-2 ulp, and the three stem variants agree."""
+    from torchvision.models import resnet34
+    from term_quantization_b200 import cnn_models, fused, inference, tr_layer
+    torch.manual_seed(1)
+    base = resnet34(weights=None).cuda().eval()
+    q = cnn_models.convert_model(base, cnn_models.static_conv_layer_settings(base, 9, 8, 12), 9, 3)
+    x = torch.randn(3, 3, 160, 192, device="cuda", generator=torch.Generator(device="cuda").manual_seed(8))
+    inference.calibrate(q, [x])
+    with torch.no_grad():
+        q = q.to(memory_format=torch.channels_last)
+        switched, skipped = tr_layer.use_tensor_cores(q)
+        assert len(switched) == 35 and not skipped
+        unfused = q(x.contiguous(memory_format=torch.channels_last))
+        a = fused.FusedResNet(q)(x)
+        b = fused.FusedResNet(q, stem="tcgen05")(x)
+        c = fused.FusedResNet(q, stem="cudnn")(x)
+    scale = float(unfused.abs().max())
+    assert torch.equal(a, b)
+    assert float((a - c).abs().max()) / scale < 2e-2
+    assert float((a - unfused).abs().max()) / scale < 2e-2
+    assert float((a.argmax(1) == unfused.argmax(1)).float().mean()) >= 2 / 3
