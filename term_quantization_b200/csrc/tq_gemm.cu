@@ -896,7 +896,13 @@ extern "C" int tq_conv2d_codes_fused(const void *act, const void *wgt, float *ou
     g.kc_blocks = (C + GM_BLOCK_K - 1) / GM_BLOCK_K;
     pick_box(g);
     g.hw = g.wbox;
-    const int block_n = Cout <= 64 ? 64 : 128;
+    // N tile.  At N = 128 the operand reads from shared memory (A 4 KB + B 4 KB per 64-cycle MMA) plus the TMA writes
+    // of the next stage ask for twice the 128 B/cycle of shared-memory bandwidth; N = 256 halves
+    // the A share, but on the ResNet shapes it loses more than it gains: 48 KB stages leave 2-3 ring stages beside the
+    // epilogue staging tiles and 512 tiles are 3.46 waves of 148 CTAs (measured: 14x14 / 7x7 layers 5-13 % slower,
+    // only the residual-without-codes layer 8 % faster).  Opt-in: TQ_CONV_N256=1.
+    static const int n256 = getenv("TQ_CONV_N256") ? atoi(getenv("TQ_CONV_N256")) : 0;
+    const int block_n = Cout <= 64 ? 64 : ((n256 && Cout % 256 == 0) ? 256 : 128);
     g.n_tiles = (Cout + block_n - 1) / block_n;
     g.bias = bias; g.bn_a = bn_a; g.bn_b = bn_b; g.residual = residual;
     g.relu = relu ? 1 : 0;
@@ -974,6 +980,7 @@ extern "C" int tq_conv2d_codes_fused(const void *act, const void *wgt, float *ou
     }
     cudaStream_t s = (cudaStream_t)stream;
     if (block_n == 64) return launch_conv<64>(tmA, tmB, tmC, tmD, tmR, g, s);
+    if (block_n == 256) return launch_conv<256>(tmA, tmB, tmC, tmD, tmR, g, s);
     return launch_conv<128>(tmA, tmB, tmC, tmD, tmR, g, s);
 }
 
