@@ -46,6 +46,7 @@ struct ConvGeom {
     int a_tx_bytes;                             // bytes one A box deposits
     float scale;
     // shared-memory carve-up (runtime, 1024-byte aligned regions)
+    int a_stages, a_stage_bytes;                 // MODE 4: ring of halo buffers (at bstat_off) beside the weight-tile ring
     int stages, stage_bytes, ring_off, bstat_off, epi_off, epi_group_bytes, epi_codes_off, lut_off, bar_off, smem_total;
     // "program" mode for small layers (Cout <= BLOCK_N, all weights resident in shared memory): the K loop is
     // a table of A loads, each followed by 1-2 MMAs against stationary B tiles into an accumulator group
@@ -270,6 +271,9 @@ __device__ __forceinline__ void epi_stage(float (&t)[32], const ConvGeom &g, uin
 // input pixels lands once in shared memory and filter tap (r, s) is the same buffer read from row
 // r * (wbox+S-1) + s on: MMA row m is halo row start + m, i.e. output pixel (m / hw, m % hw), of which the
 // columns m % hw >= wbox are junk and dropped by the epilogue.  A traffic per tile falls from R*S boxes to one.
+// MODE 4: halo mode for layers whose weights do not fit shared memory (Cout > 64 or several 64-channel blocks):
+// a ring of halo buffers (one load per tile and channel block) and a ring of streamed weight tiles (one per
+// filter tap and channel block), each with its own full / empty barriers.
 // RELU: the epilogue's ReLU flag as a compile-time constant (the encode after a ReLU needs no sign handling; a
 // run-time branch would duplicate the staging code inside one kernel and cost instruction-cache misses).
 template <int BLOCK_N, int MODE, bool RELU>
@@ -290,8 +294,10 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint64_t *tempty_bar = tfull_bar + 3;               // [3] accumulator drained
     uint64_t *bfull_bar = tempty_bar + 3;               // stationary weights landed
     uint64_t *res_bar = bfull_bar + 1;                  // [4] residual tile landed in an epilogue group's staging
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_bar + GM_EPI_GROUPS);
-    constexpr bool prog = MODE != 0;
+    uint64_t *afull_bar = res_bar + GM_EPI_GROUPS;      // [4] MODE 4: halo buffer landed / consumed
+    uint64_t *aempty_bar = afull_bar + 4;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(aempty_bar + 4);
+    constexpr bool prog = MODE >= 1 && MODE <= 3;       // weights resident in shared memory
     const int acc_cols = g.n_groups * BLOCK_N;          // TMEM columns of one accumulator stage
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -323,6 +329,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         mbar_init(bfull_bar, 1);
         for (int i = 0; i < 3; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 256); }   // 256 = two epilogue groups
         for (int i = 0; i < GM_EPI_GROUPS; ++i) mbar_init(&res_bar[i], 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(&afull_bar[i], 1); mbar_init(&aempty_bar[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -347,6 +354,29 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 mbar_expect_tx(bfull_bar, (uint32_t)(g.nb_tiles * B_BYTES));
                 for (int t = 0; t < g.nb_tiles; ++t) tma_load_3d(&tmB, bfull_bar, bstat + t * B_BYTES, 0, 0, t);
             }
+            if constexpr (MODE == 4) {
+                const int kcb = g.kc_blocks, taps = g.R * g.S, a_stages = g.a_stages;
+                int as = 0, bs = 0;
+                uint32_t aph = 0, bph = 0;
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                    const int n_tile = tile % g.n_tiles, m_tile = tile / g.n_tiles;
+                    const int tw = m_tile % g.tiles_w, th = (m_tile / g.tiles_w) % g.tiles_h, tn = m_tile / (g.tiles_w * g.tiles_h);
+                    const int w_in0 = tw * g.step_w - g.pad, h_in0 = th * g.step_h - g.pad;     // stride 1
+                    const int nb0 = n_tile * BLOCK_N;
+                    for (int kc = 0; kc < kcb; ++kc) {
+                        mbar_wait(&aempty_bar[as], aph ^ 1u);
+                        mbar_expect_tx(&afull_bar[as], (uint32_t)g.a_tx_bytes);
+                        tma_load_4d(&tmA, &afull_bar[as], bstat + as * g.a_stage_bytes, kc * GM_BLOCK_K, w_in0, h_in0, tn);
+                        if (++as == a_stages) { as = 0; aph ^= 1u; }
+                        for (int tap = 0; tap < taps; ++tap) {
+                            mbar_wait(&empty_bar[bs], bph ^ 1u);
+                            mbar_expect_tx(&full_bar[bs], (uint32_t)B_BYTES);
+                            tma_load_3d(&tmB, &full_bar[bs], ring + bs * B_BYTES, kc * GM_BLOCK_K, nb0, tap);
+                            if (++bs == STAGES) { bs = 0; bph ^= 1u; }
+                        }
+                    }
+                }
+            } else {
             const int steps = MODE == 3 ? g.kc_blocks : (MODE == 2 ? g.prog_steps / g.R : (prog ? g.prog_steps : kblocks));
             const int S = MODE == 3 ? 1 : g.S, kc_blocks = g.kc_blocks, stage_bytes = g.stage_bytes;
             const uint32_t tx_bytes = (uint32_t)g.a_tx_bytes + (prog ? 0u : (uint32_t)B_BYTES);
@@ -376,6 +406,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     if (++kc == kc_blocks) { kc = 0; if (++sx == S) { sx = 0; ++r; } }
                 }
             }
+            }
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -396,6 +427,8 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const int steps = prog ? g.prog_steps : kblocks;
             const bool skip_mma = g.dbg_skip_mma != 0;
             uint32_t pw = MODE == 2 ? g.prog_mma[0] : 0u;
+            int as4 = 0;                                    // MODE 4: halo ring position
+            uint32_t aph4 = 0;
             if constexpr (prog) {
                 mbar_wait(bfull_bar, 0);
                 tc_fence_after();
@@ -404,7 +437,33 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
-                if constexpr (MODE == 3) {
+                if constexpr (MODE == 4) {
+                    const int taps = g.R * g.S, S = g.S, kcb = g.kc_blocks;
+                    const uint32_t row_step = (uint32_t)g.hw * 8u;      // one halo row of pixels, in 16-byte units
+                    for (int kc = 0; kc < kcb; ++kc) {
+                        mbar_wait(&afull_bar[as4], aph4);
+                        tc_fence_after();
+                        uint32_t a_row = b_lo0 + (uint32_t)as4 * ((uint32_t)g.a_stage_bytes >> 4);   // halo ring lives at bstat
+                        int sx = 0;
+                        for (int tap = 0; tap < taps; ++tap) {
+                            mbar_wait(&full_bar[stage], phase);
+                            tc_fence_after();
+                            const uint64_t da = DESC_HI | (a_row + (uint32_t)sx * 8u);
+                            const uint64_t db = DESC_HI | a_lo;         // weight-tile ring (stage_bytes = B_BYTES)
+                            if (!skip_mma) {
+#pragma unroll
+                                for (int k = 0; k < GM_BLOCK_K / 16; ++k)
+                                    umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kc | tap | k) != 0 ? 1u : 0u);
+                            }
+                            umma_commit(&empty_bar[stage]);             // weight tile consumed
+                            a_lo += a_step;
+                            if (++stage == STAGES) { stage = 0; phase ^= 1u; a_lo = a_lo0; }
+                            if (++sx == S) { sx = 0; a_row += row_step; }
+                        }
+                        umma_commit(&aempty_bar[as4]);                  // halo buffer consumed
+                        if (++as4 == g.a_stages) { as4 = 0; aph4 ^= 1u; }
+                    }
+                } else if constexpr (MODE == 3) {
                     const int taps = g.R * g.S, S = g.S, kcb = g.kc_blocks;
                     const uint32_t row_step = (uint32_t)g.hw * 8u;      // one halo row of pixels, in 16-byte units
                     for (int kc = 0; kc < kcb; ++kc) {
@@ -782,6 +841,13 @@ static int plan_smem(ConvGeom &g, int block_n)
     if (g.halo) g.stage_bytes = (g.a_tx_bytes + 1023) & ~1023;
     g.bstat_off = 0;
     g.ring_off = prog ? g.nb_tiles * b_bytes : 0;
+    if (g.halo && !prog) {                          // MODE 4: [halo ring][weight-tile ring]
+        g.a_stage_bytes = (g.a_tx_bytes + 1023) & ~1023;
+        static const int a_stages_env = getenv("TQ_CONV_ASTAGES") ? atoi(getenv("TQ_CONV_ASTAGES")) : 0;
+        g.a_stages = a_stages_env >= 2 && a_stages_env <= 4 ? a_stages_env : 2;   // measured: 2 halo buffers + a deeper weight ring win
+        g.stage_bytes = b_bytes;
+        g.ring_off = g.a_stages * g.a_stage_bytes;
+    }
     // epilogue staging per group: fp32 tile only if an fp32 tile is written or a residual is read, code tile only
     // if codes are written -- what is not needed goes to the stage ring
     g.epi_codes_off = (g.write_f32 || g.residual) ? GM_EPI_F32_BYTES : 0;
@@ -836,6 +902,10 @@ static int launch_conv(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUt
     if (2 * g.n_groups * BLOCK_N > 512) return fail(TQ_ERR_UNSUPPORTED, "accumulator groups exceed tensor memory");
     int rc = plan_smem(g, BLOCK_N);
     if (rc != TQ_OK) return rc;
+    if (g.prog_steps == 0 && g.halo) {
+        if constexpr (BLOCK_N == 128) return launch_conv_mode<128, 4>(tmA, tmB, tmC, tmD, tmR, g, s);
+        return fail(TQ_ERR_UNSUPPORTED, "streamed-weight halo mode is built for BLOCK_N = 128 only");
+    }
     if (g.prog_steps == 0) return launch_conv_mode<BLOCK_N, 0>(tmA, tmB, tmC, tmD, tmR, g, s);
     if constexpr (BLOCK_N == 64) {
         if (general_prog) return launch_conv_mode<64, 2>(tmA, tmB, tmC, tmD, tmR, g, s);
@@ -936,6 +1006,16 @@ extern "C" int tq_conv2d_codes_fused(const void *act, const void *wgt, float *ou
     }
 
     g.step_w = g.wbox; g.step_h = g.hbox; g.off_w = 0; g.off_h = 0;
+    // streamed-weight halo mode (MODE 4): stride-1 filters wider than 1x1 on maps that fill the tile
+    static const bool no_halo4 = getenv("TQ_CONV_NO_HALO4") != nullptr;
+    if (!no_halo4 && g.prog_steps == 0 && !g.halo && block_n == 128 && stride == 1 && R * S > 1) {
+        ConvGeom h = g;
+        if (pick_box_halo(h) && h.m_tiles <= g.m_tiles + g.m_tiles / 8) {
+            h.step_w = h.wbox; h.step_h = h.hbox;
+            g = h;
+            g.halo = 1;
+        }
+    }
     CUtensorMap tmA, tmB, tmC, tmD;
     int rc;
     {   // activations: (C, W, H, N) fp16; box spans wbox*stride x hbox*stride pixels, element strides = conv stride
@@ -952,9 +1032,9 @@ extern "C" int tq_conv2d_codes_fused(const void *act, const void *wgt, float *ou
         cuuint32_t estr[3] = {1, 1, 1};
         if ((rc = encode_map(enc, &tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wgt, 3, dims, box, estr, "weights")) != TQ_OK) return rc;
     } else {   // weights: (C, Cout, R*S) fp16
-        g.prog_steps = 0;                                  // (program mode needs one channel block per tap)
+        if (g.prog_steps > 0) g.halo = 0;                  // (program mode needs one channel block per tap)
+        g.prog_steps = 0;
         g.nb_tiles = 0;
-        g.halo = 0;
         cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Cout, (cuuint64_t)(R * S)};
         cuuint32_t box[3] = {(cuuint32_t)GM_BLOCK_K, (cuuint32_t)block_n, 1};
         cuuint32_t estr[3] = {1, 1, 1};

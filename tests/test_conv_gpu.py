@@ -25,6 +25,11 @@ CASES = [
     (2, 17, 17, 16, 8, 3, 1, 1),
     (2, 30, 31, 64, 64, 2, 1, 0),
     (1, 130, 70, 48, 64, 3, 1, 1),
+    # streamed-weight halo mode (Cout > 64 or several channel blocks, stride 1)
+    (2, 28, 28, 128, 128, 3, 1, 1),
+    (1, 33, 21, 72, 136, 3, 1, 1),
+    (2, 14, 14, 256, 256, 3, 1, 1),
+    (1, 40, 40, 64, 128, 5, 1, 2),
 ]
 
 
@@ -51,7 +56,7 @@ def test_conv_codes_exact_accumulators(case):
 
 FUSED = [(2, 56, 56, 64, 64, 3, 1, 1), (3, 28, 28, 128, 128, 3, 1, 1), (2, 56, 56, 64, 128, 1, 2, 0),
          (5, 7, 7, 512, 512, 3, 1, 1), (1, 9, 13, 72, 72, 3, 1, 1), (3, 14, 14, 256, 256, 3, 1, 1),
-         (2, 20, 33, 32, 40, 3, 1, 1), (1, 57, 29, 64, 64, 3, 1, 1)]
+         (2, 20, 33, 32, 40, 3, 1, 1), (1, 57, 29, 64, 64, 3, 1, 1), (2, 30, 27, 128, 192, 3, 1, 1)]
 
 
 @pytest.mark.parametrize("case", FUSED)
