@@ -422,8 +422,7 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    if line is not None:
-        print(json.dumps(line))
+    return line
 
 
 # ---------------------------------------------------------------------------------------------
@@ -472,7 +471,7 @@ def cpu_reference_images_per_sec(sample_batch, steps, warmup=0):
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     world = int(os.environ.get("WORLD_SIZE", "1"))
     base = cpu_reference_images_per_sec(sample_batch=args.cpu_batch, steps=args.steps, warmup=min(args.warmup, 1))
     v = base["value"]
@@ -485,7 +484,7 @@ def run_reference(args):
                        "note": f"each step is a bounded sample: batch {args.cpu_batch} on the host cores"},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    return line
 
 
 def main():
@@ -511,10 +510,22 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    # stdout carries ONE JSON line: anything a library prints to file descriptor 1 meanwhile (NCCL's version banner,
+    # for one) goes to stderr; the descriptor is restored for the final print
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if args.impl == "reference":
+            line = run_reference(args)
+        else:
+            line = run_b200(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -147,3 +147,82 @@ class FusedResNet(nn.Module):
             codes = {nxt: out_codes} if nxt is not None else {}
         y = cur.permute(0, 3, 1, 2)                      # NCHW shape, channels_last memory
         return m.fc(torch.flatten(m.avgpool(y), 1))
+
+
+class FusedVGG(nn.Module):
+    """Fused execution of a TQ-converted torchvision VGG (`features` = conv [-> BatchNorm] -> ReLU [-> MaxPool 2x2]
+    chains; BASELINE.json configs[2]).  Every wrapped conv is one launch of the tcgen05 kernel with bias,
+    BatchNorm affine and ReLU in the epilogue, emitting directly the fp16 term codes of the NEXT wrapped conv's
+    quantiser.  Max-pooling runs on those codes: for g = 1 the truncated-HESE code is a monotone non-decreasing
+    function of the (post-ReLU, non-negative) value, so maxpool(code(x)) == code(maxpool(x)) exactly and no fp32
+    activation is materialised between the first and the last conv (tests/test_oracle.py checks the monotonicity
+    exhaustively).  The first conv (never wrapped, cnn_models/__init__.py:34-36) stays on cuDNN fp32."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.model = model.to(memory_format=torch.channels_last).eval()
+        mods = list(model.features.children())
+        if not isinstance(mods[0], nn.Conv2d) or isinstance(mods[0], tr_layer.TRConv2dLayer):
+            raise NotImplementedError("FusedVGG expects an unwrapped first conv")
+        self.stages = []                     # (kind, payload): 'torch' module | 'conv' (_Conv, relu) | 'pool' module
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, tr_layer.TRConv2dLayer):
+                bn = None
+                relu = False
+                j = i + 1
+                if j < len(mods) and isinstance(mods[j], nn.BatchNorm2d):
+                    bn = mods[j]
+                    j += 1
+                if j < len(mods) and isinstance(mods[j], nn.ReLU):
+                    relu = True
+                    j += 1
+                self.stages.append(("conv", (_Conv(m, bn), relu)))
+                i = j
+            elif isinstance(m, nn.MaxPool2d):
+                if m.dilation not in (1, (1, 1)) or m.ceil_mode:
+                    raise NotImplementedError("FusedVGG: unsupported max-pool")
+                self.stages.append(("pool", m))
+                i += 1
+            else:
+                self.stages.append(("torch", m))
+                i += 1
+        self.first_tr = next(k for k, (kind, _) in enumerate(self.stages) if kind == "conv")
+        if any(kind == "torch" for kind, _ in self.stages[self.first_tr:]):
+            raise NotImplementedError("FusedVGG: unexpected module after the first wrapped conv")
+        # every conv but the last must be followed (through pools) by a conv and end in a ReLU (pooling on codes)
+        convs = [k for k, (kind, _) in enumerate(self.stages) if kind == "conv"]
+        for k in convs[:-1]:
+            if not self.stages[k][1][1]:
+                raise NotImplementedError("FusedVGG: conv without ReLU before a quantiser")
+
+    @torch.no_grad()
+    def forward(self, x):
+        m = self.model
+        x = x.float().contiguous(memory_format=torch.channels_last)
+        for kind, mod in self.stages[:self.first_tr]:             # unwrapped stem: conv / BN / ReLU (/ pool) on torch
+            x = mod(x)
+        convs = [k for k, (kind, _) in enumerate(self.stages) if kind == "conv"]
+        codes = FusedResNet._encode(x.permute(0, 2, 3, 1), self.stages[convs[0]][1][0].quant)   # NHWC fp16 codes
+        out = None
+        for k in range(self.first_tr, len(self.stages)):
+            kind, payload = self.stages[k]
+            if kind == "conv":
+                conv, relu = payload
+                nxt = next((self.stages[j][1][0].quant for j in range(k + 1, len(self.stages))
+                            if self.stages[j][0] == "conv"), None)
+                if nxt is not None:
+                    _, codes = conv(codes, relu=relu, want_f32=False, next_quant=nxt)
+                else:
+                    out, _ = conv(codes, relu=relu, want_f32=True)
+                    codes = None
+            else:                                                   # max-pool: on the codes (exact), or on the last fp32 map
+                t = codes if codes is not None else out
+                t = payload(t.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+                if codes is not None:
+                    codes = t.contiguous()
+                else:
+                    out = t.contiguous()
+        y = out.permute(0, 3, 1, 2)
+        return m.classifier(torch.flatten(m.avgpool(y), 1))

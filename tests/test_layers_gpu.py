@@ -349,3 +349,34 @@ def test_fused_resnet34_odd_resolution():
     assert float((a - c).abs().max()) / scale < 2e-2
     assert float((a - unfused).abs().max()) / scale < 2e-2
     assert float((a.argmax(1) == unfused.argmax(1)).float().mean()) >= 2 / 3
+
+
+def test_fused_vgg_pools_on_codes():
+    """fused.FusedVGG (BASELINE configs[2]): conv + bias + BN + ReLU + next encode in one launch per conv, max-pool on
+    the fp16 codes.  Against the layer-by-layer tensor-core path (same integer contraction, BatchNorm by cuDNN) the
+    logits differ only by the fused BatchNorm's 1-2 ulp; max-pooling on codes is exact."""
+    import torchvision
+    from term_quantization_b200 import cnn_models, fused, inference, tr_layer
+    torch.manual_seed(0)
+    base = torchvision.models.vgg16_bn(weights=None).cuda().eval()
+    q = cnn_models.convert_model(base, cnn_models.static_conv_layer_settings(base, 9, 8, 12), 9, 3)
+    x = torch.randn(4, 3, 96, 128, device="cuda", generator=torch.Generator(device="cuda").manual_seed(6))
+    inference.calibrate(q, [x])
+    with torch.no_grad():
+        ref = q(x)
+        q = q.to(memory_format=torch.channels_last)
+        switched, skipped = tr_layer.use_tensor_cores(q)
+        assert len(switched) == 12 and not skipped
+        unfused = q(x.contiguous(memory_format=torch.channels_last))
+        got = fused.FusedVGG(q)(x)
+    scale = float(ref.abs().max())
+    print(f"vgg16_bn: fused vs layer-by-layer {float((got - unfused).abs().max()) / scale:.2e}, "
+          f"layer-by-layer vs float path {float((unfused - ref).abs().max()) / scale:.2e}")
+    assert got.shape == ref.shape
+    assert float((got - unfused).abs().max()) / scale < 2e-2
+    # exactness of pooling on codes, on one layer's real codes
+    codes = torch.randint(0, 513, (2, 8, 10, 64), device="cuda").half()
+    vals = codes.float() * 0.0371
+    pc = torch.nn.functional.max_pool2d(codes.permute(0, 3, 1, 2), 2, 2)
+    pv = torch.nn.functional.max_pool2d(vals.permute(0, 3, 1, 2), 2, 2)
+    assert torch.equal(pc.float() * 0.0371, pv)

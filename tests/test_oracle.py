@@ -132,3 +132,14 @@ def test_gemm_i32():
     a = rng.integers(-256, 257, size=(5, 33)).astype(np.int16)
     w = rng.integers(-128, 129, size=(7, 33)).astype(np.int16)
     assert np.array_equal(O.gemm_i32(a, w), a.astype(np.int64) @ w.astype(np.int64).T)
+
+
+def test_truncated_hese_code_is_monotone_in_q():
+    """For g = 1 the sum of the k largest HESE terms is a non-decreasing function of the quantised value (and the
+    quantised value of the input), so a max-pool commutes with the encode of non-negative activations:
+    maxpool(code(x)) == code(maxpool(x)).  fused.FusedVGG pools on the fp16 codes because of this."""
+    for bits in (4, 6, 8, 9, 10):
+        q = np.arange(0, 2 ** bits, dtype=np.float32).reshape(1, -1, 1, 1)
+        for k in range(1, 7):
+            _, codes = O.tr(q, 1.0, bits, 1, k, return_codes=True)
+            assert np.all(np.diff(codes.reshape(-1)) >= 0), (bits, k)
