@@ -246,28 +246,29 @@ tr_group_kernel(const float *__restrict__ in, Tout *__restrict__ out,
             tn[j] = e | (neg << 31);
         }
 
-        // cut level: largest pc with (#terms at level >= pc) > alpha; none -> keep everything
-        uint32_t himask = 0xFFFFu, cutbit = 0u;
-        int r = 0;
-        if (count_at_or_above<NW>(W, 0) > p.alpha) {
-            int pc = 0;
+        // cut level: largest pc with (#terms at level >= pc) > alpha; none -> keep everything.
+        // Branch-free (selects, no divergence between the groups of a warp): 4-probe binary search over levels 0..15.
+        const int alpha = p.alpha, bits = p.bits;
+        const bool cut = count_at_or_above<NW>(W, 0) > alpha;
+        int pc = 0;
 #pragma unroll
-            for (int step = 8; step >= 1; step >>= 1) {
-                const int cand = pc + step;
-                if (cand <= p.bits && count_at_or_above<NW>(W, cand) > p.alpha) pc = cand;
-            }
-            r = p.alpha - ((pc + 1 <= 15) ? count_at_or_above<NW>(W, pc + 1) : 0);
-            cutbit = 1u << pc;
-            himask = 0xFFFFu & ~((cutbit << 1) - 1u);
+        for (int step = 8; step >= 1; step >>= 1) {
+            const int cand = pc + step;
+            const int c = count_at_or_above<NW>(W, cand);
+            pc = (cand <= bits && c > alpha) ? cand : pc;
         }
+        const int r = alpha - count_at_or_above<NW>(W, pc + 1);      // (pc + 1 == 16 -> empty mask -> 0)
+        const uint32_t cutbit = cut ? (1u << pc) : 0u;
+        const uint32_t himask = cut ? (0xFFFFu & ~((2u << pc) - 1u)) : 0xFFFFu;
 
         int cnt = 0;
         Tout y[G];
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             const uint32_t e = tn[j];
-            uint32_t K = e & himask;
-            if (e & cutbit) { if (cnt < r) K |= cutbit; ++cnt; }
+            const uint32_t at = (e & cutbit) != 0u ? 1u : 0u;       // a term at the cut level: the first r of the group keep it
+            const uint32_t K = (e & himask) | ((at != 0u && cnt < r) ? cutbit : 0u);
+            cnt += (int)at;
             const int v = (int)K - 2 * (int)(K & (e >> 16) & 0x7FFFu);
             const int code = ((int)e < 0) ? -v : v;
             if constexpr (DEQ) y[j] = dequant<Tout>(code, p.sf);
