@@ -196,6 +196,7 @@ tr_group_kernel(const float *__restrict__ in, Tout *__restrict__ out,
         }
         __syncthreads();
     }
+    const uint32_t lut_base = (uint32_t)__cvta_generic_to_shared(tn_lut);
 
     for (int64_t t = (int64_t)blockIdx.x * GROUP_THREADS + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * GROUP_THREADS) {
@@ -231,19 +232,28 @@ tr_group_kernel(const float *__restrict__ in, Tout *__restrict__ out,
 
         uint32_t tn[G];                              // T | N << 16 | sign << 31   (T, N < 2^15)
         uint32_t W[NW];                              // two T masks per word, for the counting probes
+        const bool relu = p.relu != 0;
+        if (use_lut) {                               // one branch per group, one LDS per value (32-bit shared address)
 #pragma unroll
-        for (int j = 0; j < G; ++j) {
-            uint32_t neg;
-            const uint32_t q = quantize_any<float, FAST>(x[j], k, p.relu != 0, neg);
-            uint32_t e;
-            if (use_lut) e = tn_lut[q];
-            else {
+            for (int j = 0; j < G; ++j) {
+                uint32_t neg;
+                const uint32_t q = quantize_any<float, FAST>(x[j], k, relu, neg);
+                uint32_t e;
+                asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lut_base + q * 4u));
+                if (j & 1) W[j >> 1] |= e << 16; else W[j >> 1] = e & 0xFFFFu;
+                tn[j] = e | (neg << 31);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                uint32_t neg;
+                const uint32_t q = quantize_any<float, FAST>(x[j], k, relu, neg);
                 uint32_t T, N;
                 term_masks(q, p.enc, T, N);
-                e = T | (N << 16);
+                const uint32_t e = T | (N << 16);
+                if (j & 1) W[j >> 1] |= e << 16; else W[j >> 1] = e & 0xFFFFu;
+                tn[j] = e | (neg << 31);
             }
-            if (j & 1) W[j >> 1] |= e << 16; else W[j >> 1] = e & 0xFFFFu;
-            tn[j] = e | (neg << 31);
         }
 
         // cut level: largest pc with (#terms at level >= pc) > alpha; none -> keep everything.
