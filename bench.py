@@ -382,6 +382,8 @@ def run_b200(args):
                          "algorithmic_flops": cv_flops, "kernel_ms_total": cv_ms, "share_of_step": cv_ms / ms_instrumented,
                          "timed": "CUDA events around each launch in an eager pass of the same K steps"}
         dominant, other = (conv_roof, tr_roof) if (conv_roof and cv_ms > tr_ms) else (tr_roof, conv_roof)
+        if other is tr_roof and n_tr == 0:
+            other = None            # fused engine: every encode runs inside a conv / stem epilogue (see "tr_encode")
         line = {
             "metric": METRIC, "value": BATCH * world * args.steps / (ms_total * 1e-3),
             "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
