@@ -393,8 +393,10 @@ def run_b200(args):
             "data": "synthetic (randn images rounded to bf16, random-init torchvision resnet18, seed 0)",
             "config": {"workload": "ResNet-18 TQ inference, batch 256 per GPU at 3x224x224 "
                                    "(BASELINE.json configs[1])", **SETTING,
-                       "global_batch": BATCH * world, "parallelism": f"batch-sharded x{world}, "
-                       "logits all-gather (NCCL)" if world > 1 else "single GPU",
+                       "global_batch": BATCH * world, "parallelism": (f"batch-sharded x{world}, logits all-gather (NCCL) " + {
+                           "step": "every step on the compute stream", "async": "every step on a side stream",
+                           "end": "once, after the last step (inside the timed region)"}[args.gather])
+                       if world > 1 else "single GPU",
                        "conv_backend": args.conv_backend, "input_dtype": str(in_dtype).replace("torch.", ""),
                        "cuda_graphs": bool(use_graphs),
                        "numa": (f"rank pinned to the {len(numa_cpus)} CPUs local to its GPU" if numa_cpus else "not pinned"),
