@@ -75,6 +75,19 @@ class ClockSampler(threading.Thread):
                 pass
             self._stop_evt.wait(self.period)
 
+    def sample_now(self):
+        """One sample from the calling thread (used while the GPU drains the enqueued timed region)."""
+        if self.nv is None:
+            return
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
     def finish(self):
         self._stop_evt.set()
         if self.is_alive():
@@ -259,6 +272,8 @@ def run_b200(args):
         out = runner.forward(images[i % nbuf])
     fin = runner.finish()                # outstanding / final gather of logits: inside the timed region
     e1.record()
+    if rank == 0:
+        sampler.sample_now()             # the GPU is still draining the region: at least one sample under load
     barrier()
     torch.cuda.profiler.stop()
     ms_total = e0.elapsed_time(e1)
