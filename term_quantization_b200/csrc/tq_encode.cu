@@ -188,7 +188,19 @@ tr_group_kernel(const float *__restrict__ in, Tout *__restrict__ out,
     const int64_t CG = C / G;                       // caller guarantees C % G == 0
     const int64_t total = B * CG * WH;
     bool ovf = false;
-    if (use_lut) {
+    if (use_lut == 2) {
+        // 16-byte entries: bytes 0..11 = number of terms of q at level >= 0..11 (cumulative from the top), word 3 =
+        // T | N << 16.  Adding the entries of a group gives its term count at EVERY level at once.
+        for (uint32_t q = threadIdx.x; q < (1u << p.bits); q += GROUP_THREADS) {
+            uint32_t T, N;
+            term_masks(q, p.enc, T, N);
+            uint32_t w[3] = {0u, 0u, 0u};
+#pragma unroll
+            for (int lvl = 0; lvl < 12; ++lvl) w[lvl >> 2] |= (uint32_t)__popc(T >> lvl) << (8 * (lvl & 3));
+            reinterpret_cast<uint4 *>(tn_lut)[q] = make_uint4(w[0], w[1], w[2], T | (N << 16));
+        }
+        __syncthreads();
+    } else if (use_lut) {
         for (uint32_t q = threadIdx.x; q < (1u << p.bits); q += GROUP_THREADS) {
             uint32_t T, N;
             term_masks(q, p.enc, T, N);
@@ -231,43 +243,67 @@ tr_group_kernel(const float *__restrict__ in, Tout *__restrict__ out,
         }
 
         uint32_t tn[G];                              // T | N << 16 | sign << 31   (T, N < 2^15)
-        uint32_t W[NW];                              // two T masks per word, for the counting probes
         const bool relu = p.relu != 0;
-        if (use_lut) {                               // one branch per group, one LDS per value (32-bit shared address)
-#pragma unroll
-            for (int j = 0; j < G; ++j) {
-                uint32_t neg;
-                const uint32_t q = quantize_any<float, FAST>(x[j], k, relu, neg);
-                uint32_t e;
-                asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lut_base + q * 4u));
-                if (j & 1) W[j >> 1] |= e << 16; else W[j >> 1] = e & 0xFFFFu;
-                tn[j] = e | (neg << 31);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < G; ++j) {
-                uint32_t neg;
-                const uint32_t q = quantize_any<float, FAST>(x[j], k, relu, neg);
-                uint32_t T, N;
-                term_masks(q, p.enc, T, N);
-                const uint32_t e = T | (N << 16);
-                if (j & 1) W[j >> 1] |= e << 16; else W[j >> 1] = e & 0xFFFFu;
-                tn[j] = e | (neg << 31);
-            }
-        }
-
-        // cut level: largest pc with (#terms at level >= pc) > alpha; none -> keep everything.
-        // Branch-free (selects, no divergence between the groups of a warp): 4-probe binary search over levels 0..15.
+        int pc, r;
+        bool cut;
         const int alpha = p.alpha, bits = p.bits;
-        const bool cut = count_at_or_above<NW>(W, 0) > alpha;
-        int pc = 0;
+        if (use_lut == 2) {
+            // group term counts at every level from one 16-byte lookup + 3 adds per value (bytes cannot carry: <= 7
+            // terms per value, G <= 16); the levels whose count exceeds alpha are 0..pc, so pc = (#such levels) - 1
+            uint32_t S0 = 0u, S1 = 0u, S2 = 0u;
 #pragma unroll
-        for (int step = 8; step >= 1; step >>= 1) {
-            const int cand = pc + step;
-            const int c = count_at_or_above<NW>(W, cand);
-            pc = (cand <= bits && c > alpha) ? cand : pc;
+            for (int j = 0; j < G; ++j) {
+                uint32_t neg;
+                const uint32_t q = quantize_any<float, FAST>(x[j], k, relu, neg);
+                uint32_t a0, a1, a2, e;
+                asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(e) : "r"(lut_base + q * 16u));
+                S0 += a0; S1 += a1; S2 += a2;
+                tn[j] = e | (neg << 31);
+            }
+            const uint32_t K = (uint32_t)(127 - alpha) * 0x01010101u;          // byte > alpha  <=>  bit 7 of byte + 127 - alpha
+            const int nlev = __popc((S0 + K) & 0x80808080u) + __popc((S1 + K) & 0x80808080u) + __popc((S2 + K) & 0x80808080u);
+            cut = nlev > 0;
+            pc = cut ? nlev - 1 : 0;
+            const int idx = pc + 1;                                             // count at levels > pc
+            const uint32_t w = idx < 4 ? S0 : (idx < 8 ? S1 : S2);
+            const int above = idx >= 12 ? 0 : (int)((w >> (8 * (idx & 3))) & 0xFFu);
+            r = alpha - above;
+        } else {
+            uint32_t W[NW];                              // two T masks per word, for the counting probes
+            if (use_lut) {                               // one branch per group, one LDS per value (32-bit shared address)
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    uint32_t neg;
+                    const uint32_t q = quantize_any<float, FAST>(x[j], k, relu, neg);
+                    uint32_t e;
+                    asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lut_base + q * 4u));
+                    if (j & 1) W[j >> 1] |= e << 16; else W[j >> 1] = e & 0xFFFFu;
+                    tn[j] = e | (neg << 31);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    uint32_t neg;
+                    const uint32_t q = quantize_any<float, FAST>(x[j], k, relu, neg);
+                    uint32_t T, N;
+                    term_masks(q, p.enc, T, N);
+                    const uint32_t e = T | (N << 16);
+                    if (j & 1) W[j >> 1] |= e << 16; else W[j >> 1] = e & 0xFFFFu;
+                    tn[j] = e | (neg << 31);
+                }
+            }
+            // cut level: largest pc with (#terms at level >= pc) > alpha; none -> keep everything.
+            // Branch-free (selects, no divergence between the groups of a warp): 4-probe binary search over levels 0..15.
+            cut = count_at_or_above<NW>(W, 0) > alpha;
+            pc = 0;
+#pragma unroll
+            for (int step = 8; step >= 1; step >>= 1) {
+                const int cand = pc + step;
+                const int c = count_at_or_above<NW>(W, cand);
+                pc = (cand <= bits && c > alpha) ? cand : pc;
+            }
+            r = alpha - count_at_or_above<NW>(W, pc + 1);                       // (pc + 1 == 16 -> empty mask -> 0)
         }
-        const int r = alpha - count_at_or_above<NW>(W, pc + 1);      // (pc + 1 == 16 -> empty mask -> 0)
         const uint32_t cutbit = cut ? (1u << pc) : 0u;
         const uint32_t himask = cut ? (0xFFFFu & ~((2u << pc) - 1u)) : 0xFFFFu;
 
@@ -406,8 +442,13 @@ static int launch_group_f32(const void *in, void *out, int64_t B, int64_t C, int
     const int grid = grid_for(total, GROUP_THREADS, 8);
     const bool contig = (WH == 1);
     // the term-mask table pays for itself once a CTA has a few thousand values to encode
-    const int use_lut = (p.bits <= GROUP_LUT_MAX_BITS && total * g >= (int64_t)grid * (8 << p.bits)) ? 1 : 0;
-    const size_t lut_bytes = use_lut ? (sizeof(uint32_t) << p.bits) : 0;
+    int use_lut = (p.bits <= GROUP_LUT_MAX_BITS && total * g >= (int64_t)grid * (8 << p.bits)) ? 1 : 0;
+    // 16-byte entries (cumulative term counts per level): bits <= 10 (levels 0..10 in 12 bytes, 16 KB); alpha <= 127
+    // keeps the compare trick inside a byte.  Pays for g <= 8 (measured: g=8 4.18 -> 4.55 TB/s, g=4 3.45 -> 3.91);
+    // at g = 16 the six popcount probes are amortised over 16 values and the 4-byte table wins (4.59 vs 3.93 TB/s)
+    static const bool no_lut16 = getenv("TQ_GROUP_NO_LUT16") != nullptr;
+    if (use_lut && !no_lut16 && p.bits <= 10 && g <= 8 && p.alpha <= 127) use_lut = 2;
+    const size_t lut_bytes = use_lut == 2 ? ((size_t)16 << p.bits) : (use_lut ? (sizeof(uint32_t) << p.bits) : 0);
 #define TQ_LAUNCH_GF(GG, CT, FD)                                                                \
     tr_group_kernel<GG, CT, Tout, DEQ, FD><<<grid, GROUP_THREADS, lut_bytes, s>>>(              \
         (const float *)in, (Tout *)out, B, C, WH, p, use_lut, overflow)
