@@ -439,7 +439,7 @@ static int launch_group_f32(const void *in, void *out, int64_t B, int64_t C, int
                             const EncParams &p, int *overflow, cudaStream_t s)
 {
     const int64_t total = B * (C / g) * WH;
-    const int grid = grid_for(total, GROUP_THREADS, 8);
+    const int grid = grid_for(total, GROUP_THREADS, 16);
     const bool contig = (WH == 1);
     // the term-mask table pays for itself once a CTA has a few thousand values to encode
     int use_lut = (p.bits <= GROUP_LUT_MAX_BITS && total * g >= (int64_t)grid * (8 << p.bits)) ? 1 : 0;
