@@ -59,7 +59,24 @@ FUSED = [(2, 56, 56, 64, 64, 3, 1, 1), (3, 28, 28, 128, 128, 3, 1, 1), (2, 56, 5
          (2, 20, 33, 32, 40, 3, 1, 1), (1, 57, 29, 64, 64, 3, 1, 1), (2, 30, 27, 128, 192, 3, 1, 1)]
 
 
-@pytest.mark.parametrize("case", FUSED)
+def _random_fused_cases(n, seed=31):
+    rng = np.random.default_rng(seed)
+    cases = []
+    while len(cases) < n:
+        k = int(rng.choice([1, 3, 3, 3, 5]))
+        stride = int(rng.choice([1, 1, 2]))
+        pad = int(rng.integers(0, k // 2 + 1))
+        H, W = int(rng.integers(max(k, 4), 61)), int(rng.integers(max(k, 4), 61))
+        C = 8 * int(rng.integers(1, 9))                  # accumulators stay below 2^24 with 9-bit codes
+        Cout = 8 * int(rng.integers(1, 33))              # code output needs Cout % 8 == 0
+        N = int(rng.integers(1, 4))
+        if 513 * 256 * C * k * k >= 2 ** 24:
+            continue
+        cases.append((N, H, W, C, Cout, k, stride, pad))
+    return cases
+
+
+@pytest.mark.parametrize("case", FUSED + _random_fused_cases(16))
 def test_conv_fused_epilogue(case):
     """scale -> fma(BN) -> + residual -> ReLU -> fp32 out + fp16 term codes of the result, each
     step against plain torch / the CPU oracle."""
@@ -172,3 +189,33 @@ def test_stem_conv_pool_fused_equals_two_pass():
         assert torch.equal(codes, want_codes)
         got2, none, _ = conv_codes.stem_conv_pool(x, w2s, bns, relu=relu)
         assert none is None and torch.equal(got2, want)
+
+
+def test_conv_codes_random_geometries():
+    """Seeded sweep over conv geometries (image sizes, channel counts, filter sizes, strides, paddings, batch) to
+    exercise every operand-movement mode of the kernel (streamed, resident weights, halo, streamed-weight halo) and
+    their edge tiles: exact accumulators against an fp64 conv of the same integer tensors."""
+    from term_quantization_b200 import conv_codes
+    rng = np.random.default_rng(2024)
+    g = torch.Generator(device="cuda").manual_seed(99)
+    done = 0
+    while done < 60:
+        k = int(rng.choice([1, 2, 3, 3, 3, 5, 7]))
+        stride = int(rng.choice([1, 1, 2]))
+        pad = int(rng.integers(0, k // 2 + 2))
+        H, W = int(rng.integers(max(k, 3), 71)), int(rng.integers(max(k, 3), 71))
+        C = 8 * int(rng.integers(1, 26))
+        Cout = 4 * int(rng.integers(1, 66))
+        N = int(rng.integers(1, 5))
+        if (H + 2 * pad - k) // stride + 1 < 1 or (W + 2 * pad - k) // stride + 1 < 1:
+            continue
+        act = torch.randint(0, 513, (N, H, W, C), device="cuda", generator=g)
+        act = act * (torch.rand(N, H, W, C, device="cuda", generator=g) < 0.6)
+        amp = max(1, min(256, int((2 ** 24 - 1) // (513 * C * k * k))))      # keep every partial sum below 2^24
+        wgt = torch.randint(-amp, amp + 1, (k * k, Cout, C), device="cuda", generator=g)
+        out = conv_codes.conv2d_codes(act.half(), wgt.half(), None, (k, k), stride, pad, 1.0)
+        w_oihw = wgt.view(k, k, Cout, C).permute(2, 3, 0, 1).double()
+        want = F.conv2d(act.permute(0, 3, 1, 2).double(), w_oihw, None, stride, pad).permute(0, 2, 3, 1)
+        assert out.shape == want.shape, (N, H, W, C, Cout, k, stride, pad)
+        assert torch.equal(out.double(), want), (N, H, W, C, Cout, k, stride, pad, float((out.double() - want).abs().max()))
+        done += 1
