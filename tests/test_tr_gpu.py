@@ -266,5 +266,10 @@ def test_matches_reference_kernel_on_the_gpu_at_full_sizes():
     sf = float(w2.abs().max()) / 128
     for g_, a_ in ((2, 3), (4, 6), (8, 12), (16, 20), (32, 40)):
         assert torch.equal(tr_cuda.tr(w2, sf, 8, g_, a_).view(torch.int32), O.ref_gpu_tr(w2, sf, 8, g_, a_).view(torch.int32))
+    # table paths of the grouped kernel: cumulative-count table (g <= 8, bits <= 10, alpha <= 127), 4-byte table else
+    for bits_, g_, a_ in ((10, 8, 12), (10, 4, 5), (11, 8, 12), (12, 8, 9), (7, 8, 200), (6, 2, 1), (9, 8, 0), (10, 8, 127)):
+        sf_ = float(w2.abs().max()) / 2 ** (bits_ - 1)
+        assert torch.equal(tr_cuda.tr(w2, sf_, bits_, g_, a_).view(torch.int32),
+                           O.ref_gpu_tr(w2, sf_, bits_, g_, a_).view(torch.int32)), (bits_, g_, a_)
     xd = torch.randn(2048, 512, device="cuda", generator=gen, dtype=torch.float64)
     assert torch.equal(tr_cuda.tr(xd, 0.01, 8, 8, 12).view(torch.int64), O.ref_gpu_tr(xd, 0.01, 8, 8, 12).view(torch.int64))
