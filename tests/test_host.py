@@ -145,3 +145,28 @@ def test_models_build_on_cpu():
     assert out.shape == (15, 100) and m.decoder.weight is m.encoder.weight
     with pytest.raises(ValueError):
         RNNModel('LSTM', 100, 16, 32, 2, tie_weights=True)
+
+
+def test_bench_line_contract_on_committed_profile():
+    """The bench line committed under profiles/ (written by bench.py on a B200) carries every key of the driver's
+    contract, and bench.py's ncu-traffic parser reads the committed launch list."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = json.load(open(os.path.join(root, "profiles", "r01_bench_final_n1.json")))
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["unit"] == "images/s" and d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"])
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["gpu_launches"] > 0
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
+    r = d["roofline"]
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(r) and r["bound"] in ("hbm", "tensor")
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    c = d["cpu_baseline"]
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(c) and c["kind"] in ("reference", "port")
+    import bench
+    traffic, src = bench.ncu_conv_traffic()
+    assert traffic is not None and traffic > 1e7 and src.endswith(".csv")
