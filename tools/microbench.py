@@ -59,27 +59,6 @@ def main():
             rows.append({"case": label, "n": n, "ms_best": best, "ms_med": med,
                          "GBs_best": n * bytes_per / best / 1e6, "GBs_med": n * bytes_per / med / 1e6})
             print(json.dumps(rows[-1]))
-        # the reference's own kernel, recompiled for sm_100a (oracle/_ref/libtq_ref_gpu.so), same tensors
-        try:
-            from oracle import tq_oracle as O
-            if O.have_ref_gpu() and n < (1 << 31):
-                for label, shape_fn, bits, g, alpha in (("REFERENCE kernel act g=1 k=3 b=9", lambda t: t, 9, 1, 3),
-                                                        ("REFERENCE kernel wgt g=8 a=12 b=8 contiguous", lambda t: t.view(-1, 512), 8, 8, 12)):
-                    views = [shape_fn(t) for t in xs]
-                    sf = float(xs[0].max()) / 2 ** bits
-                    o = out.view(views[0].shape)
-                    state = {"i": 0}
-
-                    def fn_ref():
-                        v = views[state["i"] % nbuf]
-                        state["i"] += 1
-                        O.ref_gpu_tr(v, sf, bits, g, alpha, out=o)
-                    best, med = time_call(fn_ref, iters=5, warm=2)
-                    rows.append({"case": label, "n": n, "ms_best": best, "ms_med": med,
-                                 "GBs_best": n * 8 / best / 1e6, "GBs_med": n * 8 / med / 1e6})
-                    print(json.dumps(rows[-1]))
-        except Exception as e:                                  # measurement aid only
-            print(json.dumps({"case": "REFERENCE kernel", "error": str(e)}))
         # copy baseline for context
         best, med = time_call(lambda: out.copy_(xs[0]))
         rows.append({"case": "torch copy_", "n": n, "ms_best": best, "GBs_best": n * 8 / best / 1e6})
