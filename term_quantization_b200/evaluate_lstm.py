@@ -57,11 +57,9 @@ def main(argv=None):
     parser.add_argument('--tied', action='store_false')
     parser.add_argument('--seed', type=int, default=1111)
     parser.add_argument('--cuda', action='store_false')
-    parser.add_argument('--wb', nargs='+', type=int, help='weight bits')
-    parser.add_argument('--wt', nargs='+', type=int, help='weight terms')
-    parser.add_argument('--db', nargs='+', type=int, help='data bits')
-    parser.add_argument('--dt', nargs='+', type=int, help='data terms')
-    parser.add_argument('--gs', nargs='+', type=int, help='group sizes')
+    for flag, what in (('--wb', 'weight bits'), ('--wt', 'weight terms'), ('--db', 'data bits'),
+                       ('--dt', 'data terms'), ('--gs', 'group sizes')):       # one value per setting
+        parser.add_argument(flag, nargs='+', type=int, help=what)
     parser.add_argument('--out-file', help='Output file')
     parser.add_argument('--eval-batch-size', type=int, default=10)
     parser.add_argument('--tokens', type=int, default=35 * 10 * 4 + 10, help='synthetic test tokens')

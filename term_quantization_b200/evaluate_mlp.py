@@ -55,14 +55,14 @@ class _SyntheticMNIST(torch.utils.data.Dataset):
 
 def main(argv=None):
     parser = argparse.ArgumentParser(description='TQ MNIST MLP evaluation')
+    # the reference's flags (evaluate_mlp.py:43-54): one value per setting in each list
+    for flag, what in (('--wb', 'weight bits'), ('--wt', 'weight terms'), ('--db', 'data bits'),
+                       ('--dt', 'data terms'), ('--gs', 'group sizes')):
+        parser.add_argument(flag, nargs='+', type=int, help=what)
     parser.add_argument('--test-batch-size', type=int, default=128, metavar='N')
     parser.add_argument('--no-cuda', action='store_true', default=False)
-    parser.add_argument('--wb', nargs='+', type=int, help='weight bits')
-    parser.add_argument('--wt', nargs='+', type=int, help='weight terms')
-    parser.add_argument('--db', nargs='+', type=int, help='data bits')
-    parser.add_argument('--dt', nargs='+', type=int, help='data terms')
-    parser.add_argument('--gs', nargs='+', type=int, help='group sizes')
     parser.add_argument('--out-file', help='Output file')
+    # additions: synthetic data (no MNIST in this image), optional weights
     parser.add_argument('--synthetic', action='store_true', default=True)
     parser.add_argument('--samples', type=int, default=2048, help='synthetic test-set size')
     parser.add_argument('--weights', default=None, help='optional state_dict (.pt)')

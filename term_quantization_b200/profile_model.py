@@ -46,17 +46,14 @@ def tr_lstm_ops(m, x, y):
     return None
 
 
+_ZERO_COUNTED = (nn.Conv2d, nn.BatchNorm2d, nn.Linear, nn.AvgPool2d, nn.AdaptiveAvgPool2d)     # inner / free layers
+
+
 def get_model_ops(model, inputs):
-    custom_ops = {
-        tr_layer.TRConv2dLayer: tr_conv2d_ops,
-        tr_layer.TRLinearLayer: tr_linear_ops,
-        tr_layer.TRLSTMLayer: tr_lstm_ops,
-        nn.Conv2d: thop.count_hooks.zero_ops,
-        nn.BatchNorm2d: thop.count_hooks.zero_ops,
-        nn.Linear: thop.count_hooks.zero_ops,
-        nn.AvgPool2d: thop.count_hooks.zero_ops,
-        nn.AdaptiveAvgPool2d: thop.count_hooks.zero_ops,
-    }
+    """(term-pair multiplications, parameter bits) of one forward of `model` on `inputs`."""
+    counters = {layer_type: thop.count_hooks.zero_ops for layer_type in _ZERO_COUNTED}
     if Conv2dStaticSamePadding is not None:
-        custom_ops[Conv2dStaticSamePadding] = thop.count_hooks.zero_ops
-    return thop.profile(model, inputs=inputs, custom_ops=custom_ops)
+        counters[Conv2dStaticSamePadding] = thop.count_hooks.zero_ops
+    counters.update({tr_layer.TRConv2dLayer: tr_conv2d_ops, tr_layer.TRLinearLayer: tr_linear_ops,
+                     tr_layer.TRLSTMLayer: tr_lstm_ops})
+    return thop.profile(model, inputs=inputs, custom_ops=counters)
