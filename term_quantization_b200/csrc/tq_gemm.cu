@@ -20,6 +20,17 @@
 // Warp roles (384 threads, persistent CTAs, one per SM): warp 0 TMA producer, warp 1 MMA
 // issuer (one thread), warp 2 TMEM allocator, warps 4-7 / 8-11 two epilogue groups, one per
 // accumulator stage (TMEM -> registers -> fused tail -> swizzled smem -> TMA store).
+//
+// Measurement / experiment switches (environment, read once; none is needed in normal use):
+//   TQ_CONV_SKIP_EPI / _SKIP_MMA / _SKIP_TMA   run without the epilogue / the MMAs / the TMA loads (results are garbage):
+//                                              isolates which pipeline paces a layer (tools/conv_microbench.py)
+//   TQ_CONV_STAGES=n, TQ_CONV_ASTAGES=n        cap the stage ring / set the halo-buffer ring depth (MODE 4)
+//   TQ_CONV_WBOX / TQ_CONV_HBOX                force the pixel box of MODE 0 tiles
+//   TQ_CONV_NO_PROG / _NO_HALO / _NO_HALO4     fall back from resident weights / halo loads to per-tap streaming
+//   TQ_CONV_N256=1                             BLOCK_N = 256 tiles where Cout % 256 == 0 (slower on ResNet shapes)
+//   TQ_CONV_HALO_BASEOFF=1                     set the UMMA descriptor base-offset field in halo mode (WRONG results:
+//                                              kept as the record of how the swizzle was found to be address-based)
+//   TQ_STEM_GROUPS=1..3                        accumulator groups of the hi/lo stem conv (accuracy vs TMEM reads)
 #include <cuda.h>
 
 #include <cstdlib>
