@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define TQ_VERSION 100
+#define TQ_VERSION 200
 
 /* status codes */
 #define TQ_OK               0
@@ -141,39 +141,78 @@ int tq_hese_term_count(const void *w, int dtype, int64_t n, float sf, unsigned f
  * Convolution on term codes with tcgen05 tensor cores (replaces the cuDNN fp32 conv under
  * TRConv2dLayer.forward, tr_layer.py:124-126, computed on the integer codes instead of the
  * dequantised values):
- *     out[n,ho,wo,co] = scale * sum_{r,s,ci} act[n, ho*stride+r-pad, wo*stride+s-pad, ci] * wgt[r*S+s, co, ci]  (+ bias[co])
+ *     acc[n,ho,wo,co] = sum_{r,s,ci} act[n, ho*stride+r-pad, wo*stride+s-pad, ci] * wgt[r*S+s, co, ci]     (int32, exact)
+ *     out             = float(acc) * scale (+ bias[co])
  * act  fp16 NHWC [N,H,W,C] holding integer codes (TQ_F16C), C % 8 == 0
  * wgt  fp16 [R*S][Cout][C] holding integer codes, Cout % 4 == 0
- * out  fp32 NHWC [N,Ho,Wo,Cout]; bias fp32 [Cout] or NULL; scale = sf_x * sf_w.
- * The fp32 accumulator equals the exact integer accumulator whenever sum |act*wgt| < 2^24 per
- * output.  groups = 1, dilation = 1.
+ * out  fp32 NHWC [N,Ho,Wo,Cout]; bias fp32 [Cout] or NULL; scale = sf_x * sf_w.  groups = 1, dilation = 1.
+ *
+ * EXACTNESS CONTRACT (kind::f16 MMAs accumulate in fp32, exact for integers below 2^24).  The K dimension is
+ * cut into acc_groups chunks of (C / 64) / acc_groups consecutive 64-channel blocks (all taps); every chunk
+ * accumulates in its own tensor-memory accumulator and the epilogue adds the chunks in int32.  The result is
+ * the exact int32 accumulator if, for every output channel and every chunk,
+ *     act_max * max(sum of positive weight codes, sum of negative weight codes) < 2^24
+ * (non-negative activations <= act_max; for signed activations use the sum of |w|): no partial sum of such a
+ * chunk can leave the exact range whatever the activations are.  tq_conv_weight_l1() returns those sums; the
+ * caller passes the smallest acc_groups that satisfies the bound (acc_groups must divide C / 64 and
+ * acc_groups * min(128, roundup64(Cout)) <= 512 tensor-memory columns).  Weights that cannot be proven go to
+ * tq_conv2d_planes_i8(), which is exact for every input.  The Python layer (conv_codes.plan_weight) does this
+ * per layer at pack time and refuses to run an unproven layer on this entry point.
  */
 int tq_conv2d_codes_f16(const void *act, const void *wgt, const float *bias, float *out,
                         int N, int H, int W, int C, int Cout, int R, int S, int stride, int pad,
-                        float scale, void *stream);
+                        float scale, int acc_groups, void *stream);
 
 /*
  * Same contraction with the layer's whole tail fused into the epilogue (verilog/systolic_dla_top.v
  * pipeline order: accumulate -> ReLU/requantise -> encode -> truncate; tr_layer.py:124-126 plus the
  * BatchNorm / residual / ReLU that follow a conv in the CNNs of cnn_models/):
- *     t = acc * scale (+ bias[co]);  t = fma(t, bn_a[co], bn_b[co]);  t += residual[n,ho,wo,co];
+ *     t = float(acc) * scale (+ bias[co]);  t = fma(t, bn_a[co], bn_b[co]);  t += residual[n,ho,wo,co];
  *     t = max(t, 0) if relu;  out_f32 = t;  out_codes = term code of t under the consumer's quantiser
  *     (next_sf, next_bits <= 10, next_terms; g = 1, HESE) stored as fp16 NHWC.
  * Every step is optional (NULL pointer / relu = 0); at least one of out_f32, out_codes is given.
- * Outputs are written with TMA stores from swizzled shared memory (fully coalesced, clipped at
- * the tensor edge).
+ * Every step is one IEEE fp32 operation in this order, so the result is reproducible bit for bit on a CPU
+ * (oracle/fused_emul.py).  Outputs are written with TMA stores from swizzled shared memory (fully coalesced,
+ * clipped at the tensor edge).
  */
 int tq_conv2d_codes_fused(const void *act, const void *wgt, float *out_f32, void *out_codes,
                           const float *bias, const float *bn_a, const float *bn_b, const float *residual,
                           int N, int H, int W, int C, int Cout, int R, int S, int stride, int pad,
                           float scale, int relu, float next_sf, int next_bits, int next_terms,
-                          void *stream);
+                          int acc_groups, void *stream);
+
+/*
+ * The same fused conv on SIGNED 8-BIT OPERAND PLANES with tcgen05.mma kind::i8 and int32 accumulators in
+ * tensor memory: exact for every input (the north star's "tcgen05 int8 implicit-GEMM ... int32 accumulators").
+ * A code v (|v| <= 2047) is split as v = 16 * hi + lo with hi = v >> 4 (arithmetic) and lo = v & 15; an operand
+ * whose codes all fit -128..127 is a single plane.
+ *   act_planes  int8 [planes_a][N][H][W][C]   (plane 0 = hi or the code itself, plane 1 = lo), C % 16 == 0
+ *   wgt_planes  int8 [planes_w][R*S][Cout][C]
+ * Plane pair (pa, pw) accumulates into TMEM accumulator pa + pw; the epilogue recombines them by Horner's rule
+ * with the plane shift in int32 and continues exactly as tq_conv2d_codes_fused.  K * max|a| * max|w| < 2^31 is
+ * checked from the shapes.  tq_codes_to_planes() produces the planes from fp16 codes.
+ */
+int tq_conv2d_planes_i8(const void *act_planes, const void *wgt_planes, int planes_a, int planes_w,
+                        float *out_f32, void *out_codes, const float *bias, const float *bn_a,
+                        const float *bn_b, const float *residual, int N, int H, int W, int C, int Cout,
+                        int R, int S, int stride, int pad, float scale, int relu, float next_sf,
+                        int next_bits, int next_terms, void *stream);
+
+/* fp16 integer codes (n elements, n % 8 == 0) -> `planes` signed 8-bit planes of n bytes each, plane p at
+ * planes_s8 + p * n.  planes = 1 stores the code itself; a value that does not fit sets *overflow (device int,
+ * may be NULL) to 1. */
+int tq_codes_to_planes(const void *codes_f16, void *planes_s8, int64_t n, int planes, int *overflow, void *stream);
+
+/* Static accumulator bound of a packed weight (see the exactness contract above): for every output channel co
+ * and every 64-channel block kb, pos[co * kcb + kb] = sum of the positive codes of wgt[:, co, 64 kb .. 64 kb + 63]
+ * over all taps and neg[...] = minus the sum of the negative ones (kcb = ceil(C / 64); device int64 arrays). */
+int tq_conv_weight_l1(const void *wgt_f16, int RS, int Cout, int C, long long *pos, long long *neg, void *stream);
 
 /*
  * Fused tail of the unquantised stem (torchvision ResNet: bn1 -> relu -> maxpool(3, 2, 1), then
  * the first wrapped conv's LinearQuantize, tr_layer.py:96-99): x fp32 NHWC [N,H,W,C] ->
  * out fp32 NHWC [N,Ho,Wo,C] = maxpool3x3s2p1(relu(fma(x, bn_a, bn_b))) and, if out_codes != NULL,
- * the fp16 term codes of `out` under (next_sf, next_bits <= 12, next_terms).  C % 4 == 0.
+ * the fp16 term codes of `out` under (next_sf, next_bits <= 11, next_terms).  C % 4 == 0.
  */
 int tq_bn_relu_maxpool_encode(const float *x, const float *bn_a, const float *bn_b, float *out,
                               void *out_codes, int N, int H, int W, int C, int relu,

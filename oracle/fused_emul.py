@@ -1,0 +1,70 @@
+"""CPU emulation of the FUSED arithmetic (csrc/tq_gemm.cu epilogue), bit for bit.
+
+TEST INFRASTRUCTURE ONLY (see oracle/tq_oracle.py).  The fused engine replaces, per wrapped conv, the
+reference's  TR encode -> fp32 conv -> BatchNorm -> (+ residual) -> ReLU  (tr_layer.py:124-126 inside a
+torchvision BasicBlock) by ONE kernel whose every step is a single IEEE fp32 operation on an exact integer
+accumulator.  That chain is reproducible on a CPU without any tolerance, which no float convolution is:
+
+    acc   = sum_k a_k * w_k            exact integer (here: fp64 convolution of integer tensors, < 2^53)
+    t     = fl32(acc) * scale          RN conversion (exact below 2^24), RN multiply;  scale = fl32(sf_x) * fl32(sf_w)
+    t     = t + bias[co]               RN add                     (if the conv has a bias)
+    t     = fmaf(t, bn_a[co], bn_b[co])  one rounding             (if a BatchNorm follows)
+    t     = t + residual               RN add                     (block output)
+    t     = max(t, 0)                  (if a ReLU follows)
+    codes = tr(t; next_sf, bits, g=1, terms)   oracle.tr: the reference's quantise / HESE / truncate
+
+`run_resnet_chain` chains this over every BasicBlock of a ResNet exactly as fused.FusedResNet does.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import tq_oracle as O
+
+
+def encode(x_nhwc, quant):
+    """fp32 [N,H,W,C] -> int32 term codes under quant = (sf, bits, terms), g = 1 (tr_layer.py:96-99)."""
+    sf, bits, terms = quant
+    x = np.ascontiguousarray(x_nhwc, dtype=np.float32)
+    _, codes = O.tr(x.reshape(1, -1, 1, 1), sf, bits, 1, terms, return_codes=True)
+    return codes.reshape(x.shape)
+
+
+def conv_exact(codes_nhwc, w_codes, ks, stride, pad):
+    """Exact integer convolution: int codes [N,H,W,C] x [R*S, Cout, C] -> float64 [N,Ho,Wo,Cout] holding integers."""
+    R, S = ks
+    RS, Cout, C = w_codes.shape
+    w = torch.from_numpy(np.asarray(w_codes, dtype=np.float64)).view(R, S, Cout, C).permute(2, 3, 0, 1).contiguous()
+    a = torch.from_numpy(np.asarray(codes_nhwc, dtype=np.float64)).permute(0, 3, 1, 2).contiguous()
+    acc = F.conv2d(a, w, None, stride, pad).permute(0, 2, 3, 1).contiguous().numpy()
+    assert float(np.abs(acc).max(initial=0.0)) < 2.0 ** 31, "int32 accumulator overflow"
+    return acc
+
+
+def fused_conv(codes_nhwc, conv, residual=None, relu=False, next_quant=None):
+    """One fused conv.  conv: dict(w=[R*S,Cout,C] int codes, ks, stride, pad, scale (python float of an fp32),
+    bias=None|[Cout], bn=None|(a, b)).  Returns (t fp32 [N,Ho,Wo,Cout], codes int32 or None)."""
+    acc = conv_exact(codes_nhwc, conv["w"], conv["ks"], conv["stride"], conv["pad"])
+    t = acc.astype(np.float32) * np.float32(conv["scale"])
+    if conv.get("bias") is not None:
+        t = t + np.asarray(conv["bias"], dtype=np.float32)
+    if conv.get("bn") is not None:
+        t = O.fma_channels(t, conv["bn"][0], conv["bn"][1])
+    if residual is not None:
+        t = t + np.asarray(residual, dtype=np.float32)
+    if relu:
+        t = np.maximum(t, np.float32(0.0))
+    t = np.ascontiguousarray(t, dtype=np.float32)
+    return t, (encode(t, next_quant) if next_quant is not None else None)
+
+
+def run_resnet_chain(blocks, stem_out):
+    """blocks: list of (conv1, conv2, down-or-None) dicts, each with a 'quant' = (sf, bits, terms) of its input
+    quantiser; stem_out: fp32 [N,H,W,C] -- the tensor that reaches layer1 (after the unquantised stem, which is
+    outside the TQ path: cnn_models/__init__.py:34-36).  Returns the fp32 [N,h,w,C'] output of the last block."""
+    cur = np.ascontiguousarray(stem_out, dtype=np.float32)
+    for c1, c2, down in blocks:
+        identity = cur if down is None else fused_conv(encode(cur, down["quant"]), down)[0]
+        _, mid = fused_conv(encode(cur, c1["quant"]), c1, relu=True, next_quant=c2["quant"])
+        cur, _ = fused_conv(mid, c2, residual=identity, relu=True)
+    return cur

@@ -208,3 +208,12 @@ void tqo_gemm_i32(const int16_t *a, const int16_t *w, int32_t *acc,
             acc[m * N + n] = (int32_t)s;
         }
 }
+
+/* ---- fused conv tail: one IEEE fp32 operation per step ------------------- */
+
+/* y[i] = fmaf(x[i], a[i % C], b[i % C]) -- the BatchNorm affine of the fused conv epilogue, a single rounding
+ * (csrc/tq_gemm.cu epi_affine).  glibc's fmaf is correctly rounded with or without a hardware FMA. */
+void tqo_fma_channels_f32(const float *x, const float *a, const float *b, float *y, int64_t n, int64_t C)
+{
+    for (int64_t i = 0; i < n; i++) y[i] = fmaf(x[i], a[i % C], b[i % C]);
+}

@@ -75,6 +75,9 @@ int64_t tqo_hese_term_count_f32(const float *w, int64_t n, float sf);
 void tqo_gemm_i32(const int16_t *a, const int16_t *w, int32_t *acc,
                   int64_t M, int64_t N, int64_t K);
 
+/* y[i] = fmaf(x[i], a[i % C], b[i % C]): the per-channel affine of the fused conv epilogue, one rounding. */
+void tqo_fma_channels_f32(const float *x, const float *a, const float *b, float *y, int64_t n, int64_t C);
+
 #ifdef __cplusplus
 }
 #endif

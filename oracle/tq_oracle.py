@@ -54,6 +54,8 @@ def lib():
         L.tqo_hese_term_count_f32.argtypes = [C.c_void_p, C.c_int64, C.c_float]
         L.tqo_gemm_i32.restype = None
         L.tqo_gemm_i32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]
+        L.tqo_fma_channels_f32.restype = None
+        L.tqo_fma_channels_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
         _lib = L
     return _lib
 
@@ -206,3 +208,14 @@ def gemm_i32(a, w):
     acc = np.empty((M, N), dtype=np.int32)
     lib().tqo_gemm_i32(a.ctypes.data, w.ctypes.data, acc.ctypes.data, M, N, K)
     return acc
+
+
+def fma_channels(x, a, b):
+    """fmaf(x, a[c], b[c]) over the last (channel) axis of a float32 array, one rounding per element."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    assert x.shape[-1] == a.size == b.size
+    y = np.empty_like(x)
+    lib().tqo_fma_channels_f32(x.ctypes.data, a.ctypes.data, b.ctypes.data, y.ctypes.data, x.size, a.size)
+    return y

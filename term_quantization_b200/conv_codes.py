@@ -17,8 +17,143 @@ def pack_conv_weight(w, w_sf, weight_bits, group_size, num_terms):
     return codes.permute(2, 3, 0, 1).reshape(kh * kw, O, I).to(torch.float16).contiguous()
 
 
-def conv2d_codes(act, wgt, bias, kernel_size, stride, pad, scale, out=None):
-    """act: fp16 [N, H, W, C] codes; wgt: fp16 [R*S, Cout, C] codes; returns fp32 [N, Ho, Wo, Cout]."""
+# ---- exact-accumulator contract -------------------------------------------------------------------------
+# The kind::f16 kernel accumulates in fp32: exact only below 2^24.  Whether a layer can run on it is PROVEN here
+# from its weight codes alone, for every possible activation (include/tq_b200.h, "EXACTNESS CONTRACT"): a chunk
+# of K whose activations lie in [0, act_max] has every partial sum inside
+# [-act_max * sum(w-), +act_max * sum(w+)].  A layer that cannot be proven with the accumulator groups tensor
+# memory offers runs on the kind::i8 plane engine (int32 accumulators, exact for every input).
+
+EXACT_LIMIT = 1 << 24
+
+
+class WeightPlan:
+    """How one packed weight [R*S, Cout, C] runs exactly: engine 'f16' with `groups` K chunks, or 'i8' with the
+    signed 8-bit planes of the weight codes.  Built once per weight by `plan_weight`."""
+
+    def __init__(self, engine, groups, bound, act_max, signed, wgt, planes=None, planes_w=0):
+        self.engine, self.groups, self.bound, self.act_max, self.signed = engine, groups, bound, act_max, signed
+        self.wgt, self.planes, self.planes_w = wgt, planes, planes_w
+
+    def __repr__(self):
+        return (f"WeightPlan({self.engine}, groups={self.groups}, bound={self.bound:.3e}, act_max={self.act_max}, "
+                f"signed={self.signed}, planes_w={self.planes_w})")
+
+
+def weight_l1(wgt):
+    """(pos, neg): int64 [Cout, ceil(C/64)] sums of the positive / negative weight codes per output channel and
+    64-channel block over all taps (tq_conv_weight_l1)."""
+    RS, Cout, C = wgt.shape
+    kcb = (C + 63) // 64
+    pos = torch.empty((Cout, kcb), dtype=torch.int64, device=wgt.device)
+    neg = torch.empty_like(pos)
+    with torch.cuda.device(wgt.device):
+        rc = _lib.lib().tq_conv_weight_l1(wgt.data_ptr(), RS, Cout, C, pos.data_ptr(), neg.data_ptr(),
+                                          torch.cuda.current_stream(wgt.device).cuda_stream)
+    _lib.check(rc)
+    return pos, neg
+
+
+def codes_to_planes(codes, planes):
+    """fp16 integer codes (any shape, numel % 8 == 0) -> int8 [planes, *shape]: plane 0 = code >> 4 and plane 1 =
+    code & 15, or the code itself for planes == 1 (raises if a code does not fit)."""
+    if codes.dtype != torch.float16 or not codes.is_contiguous() or not codes.is_cuda:
+        raise RuntimeError("codes_to_planes expects a contiguous fp16 CUDA tensor")
+    out = torch.empty((planes,) + tuple(codes.shape), dtype=torch.int8, device=codes.device)
+    ovf = torch.zeros(1, dtype=torch.int32, device=codes.device)
+    with torch.cuda.device(codes.device):
+        rc = _lib.lib().tq_codes_to_planes(codes.data_ptr(), out.data_ptr(), codes.numel(), planes, ovf.data_ptr(),
+                                           torch.cuda.current_stream(codes.device).cuda_stream)
+    _lib.check(rc)
+    return out, ovf
+
+
+def _planes_needed(max_abs_code):
+    if max_abs_code <= 127:
+        return 1
+    if max_abs_code <= 2047:
+        return 2
+    raise NotImplementedError(f"codes up to {max_abs_code} do not fit two signed 8-bit planes")
+
+
+def plan_weight(wgt, act_max, signed_act=False, engine="auto"):
+    """Static exactness proof for a packed weight `wgt` (fp16 codes [R*S, Cout, C]) under activations in
+    [0, act_max] (or [-act_max, act_max] when signed_act).  engine: 'auto' (kind::f16 with the fewest accumulator
+    groups that can be proven, else the kind::i8 plane engine), 'f16' (raise if it cannot be proven), 'i8'."""
+    if wgt.dtype != torch.float16 or wgt.dim() != 3 or not wgt.is_contiguous():
+        raise RuntimeError("plan_weight expects a contiguous fp16 [R*S, Cout, C] code tensor")
+    RS, Cout, C = wgt.shape
+    bound = float("inf")
+    if engine in ("auto", "f16"):
+        pos, neg = weight_l1(wgt)
+        kcb = pos.shape[1]
+        block_n = 64 if Cout <= 64 else 128
+        for groups in (1, 2, 4, 8):
+            if kcb % groups or groups * block_n > 512:
+                continue
+            p = pos.view(Cout, groups, kcb // groups).sum(2)
+            n = neg.view(Cout, groups, kcb // groups).sum(2)
+            worst = (p + n) if signed_act else torch.maximum(p, n)
+            b = float(act_max) * float(worst.max().item())
+            bound = min(bound, b)
+            if b < EXACT_LIMIT:
+                return WeightPlan("f16", groups, b, act_max, signed_act, wgt)
+        if engine == "f16":
+            raise NotImplementedError(
+                f"kind::f16 conv: cannot prove exact fp32 accumulation for this weight (best bound {bound:.3e} >= 2^24 "
+                f"with act_max = {act_max}); use the kind::i8 plane engine (engine='i8' / 'auto')")
+    if C % 16:
+        raise NotImplementedError("kind::i8 plane engine needs C % 16 == 0")
+    wmax = int(wgt.abs().max().item())
+    pw = _planes_needed(wmax)
+    planes, ovf = codes_to_planes(wgt, pw)
+    if int(ovf.item()):
+        raise RuntimeError("weight codes do not fit their planes")
+    return WeightPlan("i8", 1, bound, act_max, signed_act, wgt, planes=planes, planes_w=pw)
+
+
+_PLANS = {}
+
+
+def _cached_plan(wgt, act_max, signed_act, engine):
+    key = (wgt.data_ptr(), wgt._version, tuple(wgt.shape), int(act_max), bool(signed_act), engine)
+    plan = _PLANS.get(key)
+    if plan is None or plan.wgt is not wgt:
+        if len(_PLANS) > 256:
+            _PLANS.clear()
+        plan = _PLANS[key] = plan_weight(wgt, act_max, signed_act, engine)
+    return plan
+
+
+def _run_conv(act, plan, out, codes, bias, bn, residual, N, H, W, C, Cout, R, S, stride, pad, scale, relu, sf, bits,
+              terms, act_planes=None):
+    ptr = lambda t: t.data_ptr() if t is not None else None   # noqa: E731
+    L = _lib.lib()
+    stream = torch.cuda.current_stream(act.device).cuda_stream
+    with torch.cuda.device(act.device):
+        if plan.engine == "f16":
+            rc = L.tq_conv2d_codes_fused(
+                act.data_ptr(), plan.wgt.data_ptr(), ptr(out), ptr(codes), ptr(bias),
+                ptr(bn[0]) if bn else None, ptr(bn[1]) if bn else None, ptr(residual),
+                N, H, W, C, Cout, R, S, stride, pad, float(scale), int(bool(relu)), float(sf), int(bits),
+                int(terms), int(plan.groups), stream)
+        else:
+            if act_planes is None:
+                pa = _planes_needed(plan.act_max)
+                act_planes, _ = codes_to_planes(act, pa)
+            rc = L.tq_conv2d_planes_i8(
+                act_planes.data_ptr(), plan.planes.data_ptr(), act_planes.shape[0], plan.planes_w, ptr(out), ptr(codes),
+                ptr(bias), ptr(bn[0]) if bn else None, ptr(bn[1]) if bn else None, ptr(residual),
+                N, H, W, C, Cout, R, S, stride, pad, float(scale), int(bool(relu)), float(sf), int(bits), int(terms),
+                stream)
+    _lib.check(rc)
+
+
+def conv2d_codes(act, wgt, bias, kernel_size, stride, pad, scale, out=None, *, act_max=512, signed_act=False,
+                 engine="auto", plan=None):
+    """act: fp16 [N, H, W, C] codes with |code| <= act_max (non-negative unless signed_act); wgt: fp16
+    [R*S, Cout, C] codes; returns fp32 [N, Ho, Wo, Cout] = float(exact int32 accumulator) * scale (+ bias).
+    The engine is chosen by the static proof of `plan_weight` (cached per weight tensor)."""
     if not (act.is_cuda and wgt.is_cuda and act.dtype == torch.float16 and wgt.dtype == torch.float16):
         raise RuntimeError("conv2d_codes expects fp16 CUDA code tensors")
     if not (act.is_contiguous() and wgt.is_contiguous()):
@@ -32,17 +167,15 @@ def conv2d_codes(act, wgt, bias, kernel_size, stride, pad, scale, out=None):
     Wo = (W + 2 * pad - S) // stride + 1
     if out is None:
         out = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=act.device)
-    with torch.cuda.device(act.device):
-        rc = _lib.lib().tq_conv2d_codes_f16(
-            act.data_ptr(), wgt.data_ptr(), bias.data_ptr() if bias is not None else None,
-            out.data_ptr(), N, H, W, C, Cout, R, S, stride, pad, float(scale),
-            torch.cuda.current_stream(act.device).cuda_stream)
-    _lib.check(rc)
+    if plan is None:
+        plan = _cached_plan(wgt, act_max, signed_act, engine)
+    _run_conv(act, plan, out, None, bias, None, None, N, H, W, C, Cout, R, S, stride, pad, scale, False, 1.0, 1, 0)
     return out
 
 
 def conv2d_codes_fused(act, wgt, kernel_size, stride, pad, scale, *, bias=None, bn=None, residual=None,
-                       relu=False, want_f32=True, next_quant=None):
+                       relu=False, want_f32=True, next_quant=None, act_max=512, signed_act=False, engine="auto",
+                       plan=None):
     """Conv on codes with the fused tail (see tq_conv2d_codes_fused in include/tq_b200.h).
 
     bn = (a, b) fp32 [Cout] per-channel affine applied as fma(t, a, b); residual fp32
@@ -61,14 +194,9 @@ def conv2d_codes_fused(act, wgt, kernel_size, stride, pad, scale, *, bias=None, 
                                  or residual.dtype != torch.float32):
         raise RuntimeError("residual must be a contiguous fp32 [N, Ho, Wo, Cout] tensor")
     sf, bits, terms = next_quant if next_quant else (1.0, 1, 0)
-    ptr = lambda t: t.data_ptr() if t is not None else None   # noqa: E731
-    with torch.cuda.device(act.device):
-        rc = _lib.lib().tq_conv2d_codes_fused(
-            act.data_ptr(), wgt.data_ptr(), ptr(out), ptr(codes), ptr(bias),
-            ptr(bn[0]) if bn else None, ptr(bn[1]) if bn else None, ptr(residual),
-            N, H, W, C, Cout, R, S, stride, pad, float(scale), int(bool(relu)), float(sf), int(bits),
-            int(terms), torch.cuda.current_stream(act.device).cuda_stream)
-    _lib.check(rc)
+    if plan is None:
+        plan = _cached_plan(wgt, act_max, signed_act, engine)
+    _run_conv(act, plan, out, codes, bias, bn, residual, N, H, W, C, Cout, R, S, stride, pad, scale, relu, sf, bits, terms)
     return out, codes
 
 

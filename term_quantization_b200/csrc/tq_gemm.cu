@@ -1,12 +1,23 @@
 // tq_gemm.cu -- the contraction that consumes term-revealed operands, on tcgen05 tensor cores.
 //
 // Reference: tr_layer.py:126 / :154 feed the DEQUANTISED fp32 activations and weights to cuDNN /
-// cuBLAS.  Here the operands are the integer term codes themselves (tq_tr_encode_codes), held as
-// fp16 (every |code| <= 2048 is exact in an 11-bit significand), multiplied with
-// tcgen05.mma kind::f16 into an fp32 accumulator in TMEM, and the scale sf_x * sf_w is applied
-// once in the epilogue.  All products (<= 2^17) and all partial sums below 2^24 are exact
-// integers in fp32, so the accumulator equals the int32 accumulator of an integer conv as long as
-// sum_k |a_k w_k| < 2^24 for every output (DESIGN.md section 6 explains how that is checked).
+// cuBLAS.  Here the operands are the integer term codes themselves (tq_tr_encode_codes) and the scale
+// sf_x * sf_w is applied once in the epilogue to the EXACT integer accumulator.  Two operand kinds:
+//
+//   KIND 0  codes held as fp16 (every |code| <= 2048 is exact in an 11-bit significand), multiplied with
+//           tcgen05.mma kind::f16 into fp32 accumulators in TMEM.  All products (<= 2^17) and all partial
+//           sums below 2^24 are exact integers in fp32.  The contract is STATIC: the caller passes
+//           acc_groups = G only after proving, from the weights alone (tq_conv_weight_l1), that every
+//           partial sum of every one of the G channel-block chunks of K stays below 2^24 for ANY
+//           activation codes in [0, act_max] (or [-act_max, act_max]); each chunk then accumulates into
+//           its own TMEM accumulator and the epilogue adds the G exact integers in int32.
+//   KIND 1  codes split into signed 8-bit planes (v = 16 * hi + lo, hi = v >> 4, lo = v & 15), multiplied
+//           with tcgen05.mma kind::i8 into s32 accumulators in TMEM: one accumulator per plane-pair
+//           weight (hi*hi, hi*lo + lo*hi, lo*lo), recombined with shifts in int32 in the epilogue.
+//           Exact for every input (|acc| < 2^31 is checked from the shapes): the unconditional engine.
+//
+// In both kinds the epilogue sees the int32 accumulator of an integer conv and computes
+// t = float(acc) * scale (one RN conversion, exact below 2^24, and one RN multiply).
 //
 // Implicit GEMM, NHWC activations, [R*S][Cout][Cin] weights:
 //   M tile  = a box of  nbox x hbox x wbox  output pixels (<= 128 rows), fetched per filter tap
@@ -17,9 +28,10 @@
 //             tile, both K-major with the 128-byte swizzle TMA and UMMA agree on.
 //   N tile  = BLOCK_N output channels; two accumulator stages in TMEM so the epilogue of tile i
 //             overlaps the MMAs of tile i+1.
-// Warp roles (384 threads, persistent CTAs, one per SM): warp 0 TMA producer, warp 1 MMA
-// issuer (one thread), warp 2 TMEM allocator, warps 4-7 / 8-11 two epilogue groups, one per
-// accumulator stage (TMEM -> registers -> fused tail -> swizzled smem -> TMA store).
+// Warp roles (640 threads, persistent CTAs, one per SM): warp 0 TMA producer (one thread), warp 1 MMA
+// issuer (one thread), warp 2 TMEM allocator, warps 4-19 four epilogue groups of four warps: group
+// (a, h) drains column half h of every second tile (TMEM -> registers -> fused tail -> swizzled smem ->
+// TMA store).
 //
 // Measurement / experiment switches (environment, read once; none is needed in normal use):
 //   TQ_CONV_SKIP_EPI / _SKIP_MMA / _SKIP_TMA   run without the epilogue / the MMAs / the TMA loads (results are garbage):
@@ -34,16 +46,20 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "tq_common.cuh"
 
 namespace tq {
 
 constexpr int GM_BLOCK_M = 128;
-constexpr int GM_BLOCK_K = 64;                  // fp16 elements = 128 bytes = one swizzle row
+constexpr int GM_ROW_BYTES = 128;               // one K block = one 128-byte swizzle row: 64 fp16 or 128 s8 channels
+constexpr int GM_BLOCK_K = 64;                  // fp16 elements per K block (KIND 0)
 constexpr int GM_THREADS = 640;                 // 4 control warps + 4 epilogue groups of 4 warps
-constexpr int GM_A_BYTES = GM_BLOCK_M * GM_BLOCK_K * 2;
+constexpr int GM_A_BYTES = GM_BLOCK_M * GM_ROW_BYTES;
+constexpr int GM_I8_SHIFT = 4;                  // s8 planes: v = (hi << 4) + lo
 
 struct ConvGeom {
     int N, H, W, C, Cout, R, S, stride, pad, Ho, Wo;
@@ -62,6 +78,10 @@ struct ConvGeom {
     // "program" mode for small layers (Cout <= BLOCK_N, all weights resident in shared memory): the K loop is
     // a table of A loads, each followed by 1-2 MMAs against stationary B tiles into an accumulator group
     int prog_steps, nb_tiles, n_groups;
+    // exact-accumulator contract (see the file header).  KIND 0: n_groups = K chunks of kcpg channel blocks each, summed
+    // as integers when acc_int.  KIND 1: planes_a x planes_w signed 8-bit planes (stacked along the image / tap
+    // dimension of the operand tensors), plane pair (pa, pw) accumulates into group pa + pw; kblk = channels per block.
+    int kcpg, acc_int, planes_a, planes_w, kblk;
     int dbg_skip_epilogue;      // profiling aid (TQ_CONV_SKIP_EPI=1): drain accumulators without storing
     int dbg_skip_mma, dbg_skip_tma;   // TQ_CONV_SKIP_MMA / TQ_CONV_SKIP_TMA: isolate the load and the MMA pipelines
     // MODE 2 step table, one packed word per (A plane, filter row), planes stacked along N (coordinate
@@ -136,6 +156,21 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    if constexpr (KIND == 1) umma_i8(tmem_d, desc_a, desc_b, idesc, accumulate);
+    else umma_f16(tmem_d, desc_a, desc_b, idesc, accumulate);
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
@@ -287,13 +322,15 @@ __device__ __forceinline__ void epi_stage(float (&t)[32], const ConvGeom &g, uin
 // filter tap and channel block), each with its own full / empty barriers.
 // RELU: the epilogue's ReLU flag as a compile-time constant (the encode after a ReLU needs no sign handling; a
 // run-time branch would duplicate the staging code inside one kernel and cost instruction-cache misses).
-template <int BLOCK_N, int MODE, bool RELU>
+// KIND: 0 = fp16 codes, kind::f16, fp32 accumulators; 1 = s8 planes, kind::i8, s32 accumulators (MODE 0 only).
+template <int BLOCK_N, int MODE, bool RELU, int KIND>
 __global__ void __launch_bounds__(GM_THREADS, 1)
-conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD,
                       const __grid_constant__ CUtensorMap tmR, const __grid_constant__ ConvGeom g)
 {
-    constexpr int B_BYTES = BLOCK_N * GM_BLOCK_K * 2;
+    static_assert(KIND == 0 || MODE == 0, "the s8-plane engine streams both operands (MODE 0)");
+    constexpr int B_BYTES = BLOCK_N * GM_ROW_BYTES;
     const int STAGES = g.stages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -313,10 +350,12 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = g.m_tiles * g.n_tiles;
-    const int kblocks = g.R * g.S * g.kc_blocks;
+    const int kblocks = g.R * g.S * g.kc_blocks * (KIND == 1 ? g.planes_a * g.planes_w : 1);
     // accumulator stages in TMEM: three when they fit the 512 columns (the MMA issuer may then run two tiles ahead of
-    // an epilogue that holds its accumulator until the last chunk is in registers), else two
-    const int ACC_STAGES = 3 * acc_cols <= 512 ? 3 : 2;
+    // an epilogue that holds its accumulator until the last chunk is in registers), else two; a tile with four K chunks
+    // (or three plane-pair accumulators) of 128 columns owns all of TMEM and runs with ONE stage: its MMAs start when
+    // the previous tile's accumulators are in registers
+    const int ACC_STAGES = 3 * acc_cols <= 512 ? 3 : (2 * acc_cols <= 512 ? 2 : 1);
     uint32_t TMEM_COLS = 32;                            // power of two >= the accumulator stages
     while (TMEM_COLS < (uint32_t)(ACC_STAGES * acc_cols)) TMEM_COLS <<= 1;
 
@@ -398,23 +437,34 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 const int w_in0 = (tw * g.step_w + g.off_w) * g.stride - g.pad, h_in0 = (th * g.step_h + g.off_h) * g.stride - g.pad, n0 = tn * g.nbox;
                 const int nb0 = n_tile * BLOCK_N;
                 int r = 0, sx = 0, kc = 0;                  // tap (r, sx), channel block kc
+                int pa = 0, pw = 0;                         // KIND 1: operand planes of this step (pa outer, pw inner)
+                const int kblk = g.kblk, taps_all = g.R * g.S;
                 for (int st = 0; st < steps; ++st) {
-                    int cc, cw, ch, cn;
+                    int cc, cw, ch, cn, bt;
                     if constexpr (MODE == 2) {
                         cw = w_in0; ch = h_in0; cc = 0; cn = n0 + st * g.N;   // plane st: rows h_in0 .. h_in0 + hbox + R - 2
+                        bt = 0;
                     } else {
-                        cw = w_in0 + sx; ch = h_in0 + r; cc = kc * GM_BLOCK_K; cn = n0;
+                        cw = w_in0 + sx; ch = h_in0 + r; cc = kc * kblk; cn = n0; bt = r * S + sx;
+                        if constexpr (KIND == 1) { cn += pa * g.N; bt += pw * taps_all; }   // planes stacked along image / tap
                     }
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     if (skip_tma) mbar_arrive(&full_bar[stage]);
                     else {
                         mbar_expect_tx(&full_bar[stage], tx_bytes);
                         tma_load_4d(&tmA, &full_bar[stage], sdst, cc, cw, ch, cn);
-                        if constexpr (!prog) tma_load_3d(&tmB, &full_bar[stage], sdst + GM_A_BYTES, cc, nb0, r * S + sx);
+                        if constexpr (!prog) tma_load_3d(&tmB, &full_bar[stage], sdst + GM_A_BYTES, cc, nb0, bt);
                     }
                     sdst += stage_bytes;
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; sdst = ring; }
-                    if (++kc == kc_blocks) { kc = 0; if (++sx == S) { sx = 0; ++r; } }
+                    if (++kc == kc_blocks) {
+                        kc = 0;
+                        if constexpr (KIND == 1) {            // tap outermost, then plane pair, then channel block
+                            if (++pw == g.planes_w) { pw = 0; if (++pa == g.planes_a) { pa = 0; if (++sx == S) { sx = 0; ++r; } } }
+                        } else {
+                            if (++sx == S) { sx = 0; ++r; }
+                        }
+                    }
                 }
             }
             }
@@ -423,8 +473,10 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     } else if (warp == 1) {
         // ================= MMA issuer =================
         // ONE thread issues every tcgen05.mma / tcgen05.commit (see the producer's note).
-        // instruction descriptor: D = F32, A = B = F16, both K-major, N = BLOCK_N, M = 128
-        constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(GM_BLOCK_M >> 4) << 24);
+        // instruction descriptor: both operands K-major, N = BLOCK_N, M = 128;  KIND 0: D = F32 (bits 4-5 = 1),
+        // A = B = F16 (0);  KIND 1: D = S32 (2), A = B = signed 8-bit (a_format bits 7-9 = 1, b_format bits 10-12 = 1)
+        constexpr uint32_t IDESC = (KIND == 1 ? ((2u << 4) | (1u << 7) | (1u << 10)) : (1u << 4)) |
+                                   ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(GM_BLOCK_M >> 4) << 24);
         constexpr uint64_t DESC_HI = ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
         if (elect_one()) {
             int stage = 0;
@@ -451,6 +503,8 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 if constexpr (MODE == 4) {
                     const int taps = g.R * g.S, S = g.S, kcb = g.kc_blocks;
                     const uint32_t row_step = (uint32_t)g.hw * 8u;      // one halo row of pixels, in 16-byte units
+                    int kin = 0;                                        // channel block within the K chunk
+                    uint32_t td = tmem_d;                               // accumulator of the current K chunk
                     for (int kc = 0; kc < kcb; ++kc) {
                         mbar_wait(&afull_bar[as4], aph4);
                         tc_fence_after();
@@ -463,8 +517,8 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                             const uint64_t db = DESC_HI | a_lo;         // weight-tile ring (stage_bytes = B_BYTES)
                             if (!skip_mma) {
 #pragma unroll
-                                for (int k = 0; k < GM_BLOCK_K / 16; ++k)
-                                    umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kc | tap | k) != 0 ? 1u : 0u);
+                                for (int k = 0; k < GM_ROW_BYTES / 32; ++k)
+                                    umma<KIND>(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kin | tap | k) != 0 ? 1u : 0u);
                             }
                             umma_commit(&empty_bar[stage]);             // weight tile consumed
                             a_lo += a_step;
@@ -473,6 +527,7 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         }
                         umma_commit(&aempty_bar[as4]);                  // halo buffer consumed
                         if (++as4 == g.a_stages) { as4 = 0; aph4 ^= 1u; }
+                        if (++kin == g.kcpg) { kin = 0; td += BLOCK_N; }   // next K chunk: next accumulator group
                     }
                 } else if constexpr (MODE == 3) {
                     const int taps = g.R * g.S, S = g.S, kcb = g.kc_blocks;
@@ -489,8 +544,8 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                             const uint64_t db = DESC_HI | b_lo;
                             if (!skip_mma) {
 #pragma unroll
-                                for (int k = 0; k < GM_BLOCK_K / 16; ++k)
-                                    umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kc | tap | k) != 0 ? 1u : 0u);
+                                for (int k = 0; k < GM_ROW_BYTES / 32; ++k)
+                                    umma<KIND>(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kc | tap | k) != 0 ? 1u : 0u);
                             }
                             b_lo += (uint32_t)kcb * (uint32_t)(B_BYTES >> 4);
                             if (++s == S) { s = 0; a_row += row_step; }
@@ -501,20 +556,44 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     }
                 } else if constexpr (MODE != 2) {
                     uint32_t b_lo = b_lo0;                              // MODE 1: resident tile of this step
+                    // accumulator group of a step.  KIND 0: K chunk = kc / kcpg (kc is the fastest index of the step
+                    // order); a group's first MMA is the one of tap 0, first block of the chunk.  KIND 1: plane pair
+                    // (pa, pw) -> group pa + pw; within a tap the pairs run (0,0) (0,1) (1,0) (1,1), so a group is
+                    // first written by the pair with pa == 0 or pw == planes_w - 1 (of tap 0, channel block 0).
+                    int kc = 0, kin = 0, tap0 = 1, pa = 0, pw = 0;
+                    uint32_t grp = 0;
                     for (int st = 0; st < steps; ++st) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
                         const uint64_t da = DESC_HI | a_lo;
                         const uint64_t db = DESC_HI | (MODE == 1 ? b_lo : a_lo + (uint32_t)(GM_A_BYTES >> 4));
+                        uint32_t fresh;                                 // 1: this step's first MMA overwrites the accumulator
+                        if constexpr (KIND == 1) {
+                            grp = (uint32_t)(pa + pw);
+                            fresh = (tap0 && kc == 0 && (pa == 0 || pw == g.planes_w - 1)) ? 1u : 0u;
+                        } else {
+                            fresh = (tap0 && kin == 0) ? 1u : 0u;
+                        }
+                        const uint32_t td = tmem_d + grp * BLOCK_N;
                         if (!skip_mma) {
 #pragma unroll
-                            for (int k = 0; k < GM_BLOCK_K / 16; ++k)   // UMMA_K = 16 fp16 = 32 bytes = +2 in the address field
-                                umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (st | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < GM_ROW_BYTES / 32; ++k)   // UMMA_K = 32 bytes (16 fp16 / 32 s8) = +2 in the address field
+                                umma<KIND>(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (k != 0 || !fresh) ? 1u : 0u);
                         }
                         umma_commit(&empty_bar[stage]);                 // frees the smem stage when the MMAs retire
                         a_lo += a_step;
                         b_lo += (uint32_t)(B_BYTES >> 4);
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; a_lo = a_lo0; }
+                        if constexpr (KIND == 1) {
+                            if (++kc == g.kc_blocks) {
+                                kc = 0;
+                                if (++pw == g.planes_w) { pw = 0; if (++pa == g.planes_a) { pa = 0; tap0 = 0; } }
+                            }
+                        } else {
+                            ++kin; ++kc;
+                            if (kin == g.kcpg) { kin = 0; ++grp; }
+                            if (kc == g.kc_blocks) { kc = 0; kin = 0; grp = 0; tap0 = 0; }
+                        }
                     }
                 } else {
                     uint32_t started = 0;                               // accumulator groups already written in this tile
@@ -630,11 +709,30 @@ conv_igemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     uint32_t v[16];
                     const uint32_t tcol = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * acc_cols + col0 + hh * 16);
                     tmem_ld_32x32b_x16(tcol, v);
-                    for (int gi = 1; gi < g.n_groups; ++gi) {    // accumulator groups are summed here, in fp32 RN
-                        uint32_t u[16];
-                        tmem_ld_32x32b_x16(tcol + (uint32_t)(gi * BLOCK_N), u);
+                    // Accumulator groups.  Exact integer accumulators (K chunks of a kind::f16 conv: fp32 values holding
+                    // integers below 2^24; kind::i8 plane pairs: s32) are combined in int32 -- chunks added, plane pairs by
+                    // Horner with the plane shift ((hi*hi << 4) + hi*lo + lo*hi) << 4) + lo*lo -- and converted to fp32
+                    // ONCE (RN).  The hi/lo planes of the fp32 stem conv are summed in fp32 RN.  All in place in v[].
+                    const bool as_int = KIND == 1 || g.acc_int != 0;
+                    if (g.n_groups > 1) {
+                        if (KIND == 0 && as_int) {
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__fadd_rn(__uint_as_float(v[e]), __uint_as_float(u[e])));
+                            for (int e = 0; e < 16; ++e) v[e] = (uint32_t)__float2int_rn(__uint_as_float(v[e]));
+                        }
+                        for (int gi = 1; gi < g.n_groups; ++gi) {
+                            uint32_t u[16];
+                            tmem_ld_32x32b_x16(tcol + (uint32_t)(gi * BLOCK_N), u);
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) {
+                                if (KIND == 1) v[e] = (v[e] << GM_I8_SHIFT) + u[e];
+                                else if (as_int) v[e] += (uint32_t)__float2int_rn(__uint_as_float(u[e]));
+                                else v[e] = __float_as_uint(__fadd_rn(__uint_as_float(v[e]), __uint_as_float(u[e])));
+                            }
+                        }
+                    }
+                    if (KIND == 1 || (as_int && g.n_groups > 1)) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__int2float_rn((int)v[e]));
                     }
 #pragma unroll
                     for (int e = 0; e < 16; ++e) t[hh * 16 + e] = __fmul_rn(__uint_as_float(v[e]), g.scale);
@@ -813,7 +911,7 @@ static void pick_box(ConvGeom &g)
     g.tiles_h = (g.Ho + g.hbox - 1) / g.hbox;
     g.tiles_n = (g.N + g.nbox - 1) / g.nbox;
     g.m_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
-    g.a_tx_bytes = g.wbox * g.hbox * g.nbox * GM_BLOCK_K * 2;
+    g.a_tx_bytes = g.wbox * g.hbox * g.nbox * GM_ROW_BYTES;
 }
 
 // halo mode: the pixel box (wbox x hbox, one image) whose rows, laid out (wbox + S - 1) pixels apart, fit
@@ -839,14 +937,14 @@ static bool pick_box_halo(ConvGeom &g)
     g.tiles_h = (g.Ho + bh - 1) / bh;
     g.tiles_n = g.N;
     g.m_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
-    g.a_tx_bytes = g.hw * (bh + g.R - 1) * GM_BLOCK_K * 2;
+    g.a_tx_bytes = g.hw * (bh + g.R - 1) * GM_ROW_BYTES;
     return true;
 }
 
 // carve shared memory: [stationary B][stage ring][2 x epilogue staging][LUT][barriers]
 static int plan_smem(ConvGeom &g, int block_n)
 {
-    const int b_bytes = block_n * GM_BLOCK_K * 2;
+    const int b_bytes = block_n * GM_ROW_BYTES;
     const bool prog = g.prog_steps > 0;
     g.stage_bytes = GM_A_BYTES + (prog ? 0 : b_bytes);
     if (g.halo) g.stage_bytes = (g.a_tx_bytes + 1023) & ~1023;
@@ -878,7 +976,7 @@ static int plan_smem(ConvGeom &g, int block_n)
     return TQ_OK;
 }
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, int KIND = 0>
 static int launch_conv_mode(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
                             const CUtensorMap &tmD, const CUtensorMap &tmR, ConvGeom &g, cudaStream_t s)
 {
@@ -887,43 +985,92 @@ static int launch_conv_mode(const CUtensorMap &tmA, const CUtensorMap &tmB, cons
     static const bool skip_mma = getenv("TQ_CONV_SKIP_MMA") != nullptr, skip_tma = getenv("TQ_CONV_SKIP_TMA") != nullptr;
     g.dbg_skip_mma = skip_mma ? 1 : 0;
     g.dbg_skip_tma = skip_tma ? 1 : 0;
-    auto kern = g.relu ? conv_igemm_f16_kernel<BLOCK_N, MODE, true> : conv_igemm_f16_kernel<BLOCK_N, MODE, false>;
+    auto kern = g.relu ? conv_igemm_kernel<BLOCK_N, MODE, true, KIND> : conv_igemm_kernel<BLOCK_N, MODE, false, KIND>;
     static bool attr_set[2][64] = {{false}};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_set[g.relu ? 1 : 0][dev]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_BUDGET) != cudaSuccess)
-            return check_launch("cudaFuncSetAttribute(conv_igemm_f16_kernel)");
+            return check_launch("cudaFuncSetAttribute(conv_igemm_kernel)");
         attr_set[g.relu ? 1 : 0][dev] = true;
     }
     const int total = g.m_tiles * g.n_tiles;
     const int grid = total < num_sms() ? total : num_sms();
     kern<<<grid, GM_THREADS, g.smem_total, s>>>(tmA, tmB, tmC, tmD, tmR, g);
     count_launch();
-    return check_launch("conv_igemm_f16_kernel");
+    return check_launch("conv_igemm_kernel");
 }
 
-// general_prog: the step table (prog_ld / prog_mma) is in use; otherwise resident weights are tile = tap
-template <int BLOCK_N>
-static int launch_conv(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
-                       const CUtensorMap &tmD, const CUtensorMap &tmR, ConvGeom &g, cudaStream_t s,
-                       bool general_prog = false)
+// which kernel instance runs a planned conv
+enum ConvVariant { CV_NONE = 0, CV_64_M0, CV_64_M1, CV_64_M2, CV_64_M3, CV_128_M0, CV_128_M4, CV_256_M0, CV_I8_64, CV_I8_128 };
+
+// general_prog: the step table (prog_mma) is in use; otherwise resident weights are tile = tap
+static int pick_variant(ConvGeom &g, int block_n, int kind, bool general_prog, ConvVariant &v)
 {
     if (g.n_groups < 1) g.n_groups = 1;
-    if (2 * g.n_groups * BLOCK_N > 512) return fail(TQ_ERR_UNSUPPORTED, "accumulator groups exceed tensor memory");
-    int rc = plan_smem(g, BLOCK_N);
+    if (g.n_groups * block_n > 512) return fail(TQ_ERR_UNSUPPORTED, "accumulator groups exceed tensor memory");
+    if (g.kcpg < 1) g.kcpg = g.kc_blocks;
+    int rc = plan_smem(g, block_n);
     if (rc != TQ_OK) return rc;
+    if (kind == 1) {
+        if (g.prog_steps != 0 || g.halo || block_n == 256) return fail(TQ_ERR_UNSUPPORTED, "s8-plane engine: streaming mode only");
+        v = block_n == 64 ? CV_I8_64 : CV_I8_128;
+        return TQ_OK;
+    }
     if (g.prog_steps == 0 && g.halo) {
-        if constexpr (BLOCK_N == 128) return launch_conv_mode<128, 4>(tmA, tmB, tmC, tmD, tmR, g, s);
-        return fail(TQ_ERR_UNSUPPORTED, "streamed-weight halo mode is built for BLOCK_N = 128 only");
+        if (block_n != 128) return fail(TQ_ERR_UNSUPPORTED, "streamed-weight halo mode is built for BLOCK_N = 128 only");
+        v = CV_128_M4;
+        return TQ_OK;
     }
-    if (g.prog_steps == 0) return launch_conv_mode<BLOCK_N, 0>(tmA, tmB, tmC, tmD, tmR, g, s);
-    if constexpr (BLOCK_N == 64) {
-        if (general_prog) return launch_conv_mode<64, 2>(tmA, tmB, tmC, tmD, tmR, g, s);
-        if (g.halo) return launch_conv_mode<64, 3>(tmA, tmB, tmC, tmD, tmR, g, s);
-        return launch_conv_mode<64, 1>(tmA, tmB, tmC, tmD, tmR, g, s);
+    if (g.prog_steps == 0) { v = block_n == 64 ? CV_64_M0 : (block_n == 128 ? CV_128_M0 : CV_256_M0); return TQ_OK; }
+    if (block_n != 64) return fail(TQ_ERR_UNSUPPORTED, "resident-weight mode is built for BLOCK_N = 64 only");
+    v = general_prog ? CV_64_M2 : (g.halo ? CV_64_M3 : CV_64_M1);
+    return TQ_OK;
+}
+
+static int launch_variant(ConvVariant v, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
+                          const CUtensorMap &tmD, const CUtensorMap &tmR, ConvGeom &g, cudaStream_t s)
+{
+    switch (v) {
+    case CV_64_M0: return launch_conv_mode<64, 0>(tmA, tmB, tmC, tmD, tmR, g, s);
+    case CV_64_M1: return launch_conv_mode<64, 1>(tmA, tmB, tmC, tmD, tmR, g, s);
+    case CV_64_M2: return launch_conv_mode<64, 2>(tmA, tmB, tmC, tmD, tmR, g, s);
+    case CV_64_M3: return launch_conv_mode<64, 3>(tmA, tmB, tmC, tmD, tmR, g, s);
+    case CV_128_M0: return launch_conv_mode<128, 0>(tmA, tmB, tmC, tmD, tmR, g, s);
+    case CV_128_M4: return launch_conv_mode<128, 4>(tmA, tmB, tmC, tmD, tmR, g, s);
+    case CV_256_M0: return launch_conv_mode<256, 0>(tmA, tmB, tmC, tmD, tmR, g, s);
+    case CV_I8_64: return launch_conv_mode<64, 0, 1>(tmA, tmB, tmC, tmD, tmR, g, s);
+    case CV_I8_128: return launch_conv_mode<128, 0, 1>(tmA, tmB, tmC, tmD, tmR, g, s);
+    default: return fail(TQ_ERR_UNSUPPORTED, "no kernel variant");
     }
-    return fail(TQ_ERR_UNSUPPORTED, "resident-weight mode is built for BLOCK_N = 64 only");
+}
+
+// ---- plan cache -------------------------------------------------------------------------------
+// Planning a conv (tile search, shared-memory carve-up, five cuTensorMapEncodeTiled calls) costs tens of
+// microseconds on the host; a model calls the same (pointers, shape, epilogue) conv every forward, so finished
+// plans are kept per argument tuple.  Tensor maps hold device ADDRESSES, not contents: a plan stays valid for
+// as long as the caller reuses the same buffers, and any other argument tuple simply plans again.
+struct ConvArgs {
+    const void *act, *wgt, *out_f32, *out_codes, *bias, *bn_a, *bn_b, *residual;
+    int kind, N, H, W, C, Cout, R, S, stride, pad, relu, next_bits, next_terms, acc_groups, planes_a, planes_w, device;
+    float scale, next_sf;
+};
+struct ConvPlan {
+    ConvArgs key;
+    ConvGeom g;
+    CUtensorMap tmA, tmB, tmC, tmD, tmR;
+    ConvVariant variant;
+};
+static std::mutex g_plan_mu;
+static std::vector<ConvPlan> g_plans[64];        // small open hash: bucket = hash % 64
+static size_t g_plan_count = 0;
+
+static uint64_t hash_args(const ConvArgs &a)
+{
+    const unsigned char *p = reinterpret_cast<const unsigned char *>(&a);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(ConvArgs); ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
 }
 
 static int encode_map(EncodeTiledFn enc, CUtensorMap *tm, CUtensorMapDataType dt, int esize, const void *base,
@@ -940,31 +1087,13 @@ static int encode_map(EncodeTiledFn enc, CUtensorMap *tm, CUtensorMapDataType dt
     return TQ_OK;
 }
 
-}  // namespace tq
-
-using namespace tq;
-
-extern "C" int tq_conv2d_codes_fused(const void *act, const void *wgt, float *out_f32, void *out_codes,
-                                     const float *bias, const float *bn_a, const float *bn_b,
-                                     const float *residual, int N, int H, int W, int C, int Cout, int R, int S,
-                                     int stride, int pad, float scale, int relu, float next_sf, int next_bits,
-                                     int next_terms, void *stream)
+// Plans one conv: tile shape, operand-movement mode, shared-memory carve-up, tensor maps.  kind 0: act / wgt are fp16
+// codes ([N,H,W,C], [R*S][Cout][C]) and acc_groups K chunks accumulate apart.  kind 1: act / wgt are s8 planes
+// ([PA][N][H][W][C], [PW][R*S][Cout][C]).
+static int plan_conv(const ConvArgs &a, ConvPlan &pl)
 {
-    if (!act || !wgt || (!out_f32 && !out_codes)) return fail(TQ_ERR_INVALID, "NULL pointer");
-    if (N < 1 || H < 1 || W < 1 || C < 1 || Cout < 1 || R < 1 || S < 1 || stride < 1 || pad < 0)
-        return fail(TQ_ERR_INVALID, "bad convolution geometry");
-    if (C % 8 != 0) return fail(TQ_ERR_UNSUPPORTED, "input channels must be a multiple of 8 (16-byte TMA rows), got %d", C);
-    if (Cout % 4 != 0) return fail(TQ_ERR_UNSUPPORTED, "output channels must be a multiple of 4, got %d", Cout);
-    if (out_codes && Cout % 8 != 0) return fail(TQ_ERR_UNSUPPORTED, "code output needs Cout %% 8 == 0, got %d", Cout);
-    if ((bn_a == nullptr) != (bn_b == nullptr)) return fail(TQ_ERR_INVALID, "bn_a and bn_b go together");
-    if ((((uintptr_t)act | (uintptr_t)wgt | (uintptr_t)out_f32 | (uintptr_t)out_codes | (uintptr_t)bias |
-          (uintptr_t)bn_a | (uintptr_t)bn_b | (uintptr_t)residual) & 15u) != 0)
-        return fail(TQ_ERR_INVALID, "pointers must be 16-byte aligned");
-    if (out_codes) {
-        if (!(next_sf > 0.0f) || !(next_sf < INFINITY)) return fail(TQ_ERR_INVALID, "next_sf must be positive and finite");
-        if (next_bits < 1 || next_bits > GM_LUT_MAX_BITS) return fail(TQ_ERR_UNSUPPORTED, "fused encode supports 1..%d bits", GM_LUT_MAX_BITS);
-        if (next_terms < 0) return fail(TQ_ERR_INVALID, "next_terms must be >= 0");
-    }
+    const int N = a.N, H = a.H, W = a.W, C = a.C, Cout = a.Cout, R = a.R, S = a.S, stride = a.stride, pad = a.pad;
+    const int kind = a.kind;
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return fail(TQ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
 
@@ -973,8 +1102,11 @@ extern "C" int tq_conv2d_codes_fused(const void *act, const void *wgt, float *ou
     g.Ho = (H + 2 * pad - R) / stride + 1;
     g.Wo = (W + 2 * pad - S) / stride + 1;
     if (g.Ho < 1 || g.Wo < 1) return fail(TQ_ERR_INVALID, "empty output");
-    g.scale = scale;
-    g.kc_blocks = (C + GM_BLOCK_K - 1) / GM_BLOCK_K;
+    g.scale = a.scale;
+    g.kblk = kind == 1 ? GM_ROW_BYTES : GM_BLOCK_K;
+    g.kc_blocks = (C + g.kblk - 1) / g.kblk;
+    g.planes_a = kind == 1 ? a.planes_a : 1;
+    g.planes_w = kind == 1 ? a.planes_w : 1;
     pick_box(g);
     g.hw = g.wbox;
     // N tile.  At N = 128 the operand reads from shared memory (A 4 KB + B 4 KB per 64-cycle MMA) plus the TMA writes
@@ -983,21 +1115,35 @@ extern "C" int tq_conv2d_codes_fused(const void *act, const void *wgt, float *ou
     // epilogue staging tiles and 512 tiles are 3.46 waves of 148 CTAs (measured: 14x14 / 7x7 layers 5-13 % slower,
     // only the residual-without-codes layer 8 % faster).  Opt-in: TQ_CONV_N256=1.
     static const int n256 = getenv("TQ_CONV_N256") ? atoi(getenv("TQ_CONV_N256")) : 0;
-    const int block_n = Cout <= 64 ? 64 : ((n256 && Cout % 256 == 0) ? 256 : 128);
+    const int block_n = Cout <= 64 ? 64 : ((n256 && kind == 0 && a.acc_groups == 1 && Cout % 256 == 0) ? 256 : 128);
     g.n_tiles = (Cout + block_n - 1) / block_n;
-    g.bias = bias; g.bn_a = bn_a; g.bn_b = bn_b; g.residual = residual;
-    g.relu = relu ? 1 : 0;
-    g.write_f32 = out_f32 ? 1 : 0;
-    g.write_codes = out_codes ? 1 : 0;
-    g.next_sf = out_codes ? next_sf : 1.0f;
-    g.next_bits = out_codes ? next_bits : 1;
-    g.next_terms = next_terms;
+    g.bias = (const float *)a.bias; g.bn_a = (const float *)a.bn_a; g.bn_b = (const float *)a.bn_b;
+    g.residual = (const float *)a.residual;
+    g.relu = a.relu ? 1 : 0;
+    g.write_f32 = a.out_f32 ? 1 : 0;
+    g.write_codes = a.out_codes ? 1 : 0;
+    g.next_sf = a.out_codes ? a.next_sf : 1.0f;
+    g.next_bits = a.out_codes ? a.next_bits : 1;
+    g.next_terms = a.next_terms;
     g.next_fastdiv = (g.next_sf >= 9.313225746154785e-10f && g.next_sf <= 1073741824.0f) ? 1 : 0;
-    g.n_groups = 1;
+    // accumulator groups
+    if (kind == 1) {
+        g.n_groups = g.planes_a + g.planes_w - 1;
+        g.kcpg = g.kc_blocks;
+        g.acc_int = 1;
+    } else {
+        if (a.acc_groups < 1 || g.kc_blocks % a.acc_groups != 0)
+            return fail(TQ_ERR_INVALID, "acc_groups = %d must divide the %d 64-channel blocks of C", a.acc_groups, g.kc_blocks);
+        g.n_groups = a.acc_groups;
+        g.kcpg = g.kc_blocks / a.acc_groups;
+        g.acc_int = a.acc_groups > 1 ? 1 : 0;
+    }
+    if (g.n_groups * block_n > 512)
+        return fail(TQ_ERR_UNSUPPORTED, "%d accumulator groups of %d columns exceed tensor memory", g.n_groups, block_n);
     // small layers: every weight tile stays resident in shared memory and the K loop is a table of A loads
     const int taps = R * S * g.kc_blocks;
     static const bool no_prog = getenv("TQ_CONV_NO_PROG") != nullptr;
-    if (!no_prog && Cout <= 64 && taps <= 12) {
+    if (kind == 0 && g.n_groups == 1 && !no_prog && Cout <= 64 && taps <= 12) {
         g.prog_steps = taps;
         g.nb_tiles = taps;
         // stride-1 filters wider than 1x1 on maps big enough to fill the tile: one halo load per tile
@@ -1019,7 +1165,7 @@ extern "C" int tq_conv2d_codes_fused(const void *act, const void *wgt, float *ou
     g.step_w = g.wbox; g.step_h = g.hbox; g.off_w = 0; g.off_h = 0;
     // streamed-weight halo mode (MODE 4): stride-1 filters wider than 1x1 on maps that fill the tile
     static const bool no_halo4 = getenv("TQ_CONV_NO_HALO4") != nullptr;
-    if (!no_halo4 && g.prog_steps == 0 && !g.halo && block_n == 128 && stride == 1 && R * S > 1) {
+    if (kind == 0 && !no_halo4 && g.prog_steps == 0 && !g.halo && block_n == 128 && stride == 1 && R * S > 1) {
         ConvGeom h = g;
         if (pick_box_halo(h) && h.m_tiles <= g.m_tiles + g.m_tiles / 8) {
             h.step_w = h.wbox; h.step_h = h.hbox;
@@ -1027,61 +1173,223 @@ extern "C" int tq_conv2d_codes_fused(const void *act, const void *wgt, float *ou
             g.halo = 1;
         }
     }
-    CUtensorMap tmA, tmB, tmC, tmD;
+    const CUtensorMapDataType op_dt = kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const int op_es = kind == 1 ? 1 : 2;
     int rc;
-    {   // activations: (C, W, H, N) fp16; box spans wbox*stride x hbox*stride pixels, element strides = conv stride
-        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-        cuuint32_t box[4] = {(cuuint32_t)GM_BLOCK_K, (cuuint32_t)(g.wbox * stride), (cuuint32_t)(g.hbox * stride), (cuuint32_t)g.nbox};
+    {   // activations: (C, W, H, planes * N); box spans wbox*stride x hbox*stride pixels, element strides = conv stride
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(g.planes_a * N)};
+        cuuint32_t box[4] = {(cuuint32_t)g.kblk, (cuuint32_t)(g.wbox * stride), (cuuint32_t)(g.hbox * stride), (cuuint32_t)g.nbox};
         if (g.halo) { box[1] = (cuuint32_t)g.hw; box[2] = (cuuint32_t)(g.hbox + R - 1); }
         cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-        if ((rc = encode_map(enc, &tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, act, 4, dims, box, estr, "activations")) != TQ_OK) return rc;
+        if ((rc = encode_map(enc, &pl.tmA, op_dt, op_es, a.act, 4, dims, box, estr, "activations")) != TQ_OK) return rc;
     }
-    if (g.prog_steps > 0 && g.kc_blocks == 1) {
-        // resident weights are fetched as tile t = tap: (C, Cout, R*S) with one 64-channel block per tap
-        cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Cout, (cuuint64_t)(R * S)};
-        cuuint32_t box[3] = {(cuuint32_t)GM_BLOCK_K, (cuuint32_t)block_n, 1};
+    {   // weights: (C, Cout, planes * R*S), one K block of one tap per tile
+        if (g.prog_steps > 0 && g.kc_blocks != 1) { g.halo = 0; g.prog_steps = 0; g.nb_tiles = 0; }   // (program mode: one block per tap)
+        cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Cout, (cuuint64_t)(g.planes_w * R * S)};
+        cuuint32_t box[3] = {(cuuint32_t)g.kblk, (cuuint32_t)block_n, 1};
         cuuint32_t estr[3] = {1, 1, 1};
-        if ((rc = encode_map(enc, &tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wgt, 3, dims, box, estr, "weights")) != TQ_OK) return rc;
-    } else {   // weights: (C, Cout, R*S) fp16
-        if (g.prog_steps > 0) g.halo = 0;                  // (program mode needs one channel block per tap)
-        g.prog_steps = 0;
-        g.nb_tiles = 0;
-        cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Cout, (cuuint64_t)(R * S)};
-        cuuint32_t box[3] = {(cuuint32_t)GM_BLOCK_K, (cuuint32_t)block_n, 1};
-        cuuint32_t estr[3] = {1, 1, 1};
-        if ((rc = encode_map(enc, &tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wgt, 3, dims, box, estr, "weights")) != TQ_OK) return rc;
+        if ((rc = encode_map(enc, &pl.tmB, op_dt, op_es, a.wgt, 3, dims, box, estr, "weights")) != TQ_OK) return rc;
     }
     cuuint64_t odims[4] = {(cuuint64_t)Cout, (cuuint64_t)g.Wo, (cuuint64_t)g.Ho, (cuuint64_t)N};
     cuuint32_t one[4] = {1, 1, 1, 1};
-    {   // fp32 output tile: 32 channels (128 B) x pixel box
-        cuuint32_t box[4] = {32, (cuuint32_t)g.wbox, (cuuint32_t)g.hbox, (cuuint32_t)g.nbox};
-        const void *base = out_f32 ? (const void *)out_f32 : act;      // unused map still has to be valid
-        if (out_f32) { if ((rc = encode_map(enc, &tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, 4, odims, box, one, "fp32 output")) != TQ_OK) return rc; }
-        else tmC = tmA;
+    cuuint32_t obox[4] = {32, (cuuint32_t)g.wbox, (cuuint32_t)g.hbox, (cuuint32_t)g.nbox};
+    // fp32 output tile: 32 channels (128 B) x pixel box; fp16 code tile: 32 channels (64 B, 64-byte swizzle);
+    // residual tile: same box as the fp32 output tile.  Unused maps still have to be valid objects.
+    pl.tmC = pl.tmA; pl.tmD = pl.tmA; pl.tmR = pl.tmA;
+    if (a.out_f32 && (rc = encode_map(enc, &pl.tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.out_f32, 4, odims, obox, one, "fp32 output")) != TQ_OK) return rc;
+    if (a.out_codes && (rc = encode_map(enc, &pl.tmD, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a.out_codes, 4, odims, obox, one, "code output",
+                                        CU_TENSOR_MAP_SWIZZLE_64B)) != TQ_OK) return rc;
+    if (a.residual && (rc = encode_map(enc, &pl.tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.residual, 4, odims, obox, one, "residual")) != TQ_OK) return rc;
+    if ((rc = pick_variant(g, block_n, kind, false, pl.variant)) != TQ_OK) return rc;
+    pl.g = g;
+    pl.key = a;
+    return TQ_OK;
+}
+
+static int run_conv(ConvArgs &a, cudaStream_t s)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    a.device = dev;
+    const uint64_t h = hash_args(a);
+    static const bool no_cache = getenv("TQ_CONV_NO_PLAN_CACHE") != nullptr;
+    ConvPlan pl;
+    bool hit = false;
+    if (!no_cache) {
+        std::lock_guard<std::mutex> lk(g_plan_mu);
+        for (const ConvPlan &c : g_plans[h & 63])
+            if (memcmp(&c.key, &a, sizeof(ConvArgs)) == 0) { pl = c; hit = true; break; }
     }
-    {   // fp16 code output tile: 32 channels (64 B, 64-byte swizzle) x pixel box
-        cuuint32_t box[4] = {32, (cuuint32_t)g.wbox, (cuuint32_t)g.hbox, (cuuint32_t)g.nbox};
-        if (out_codes) { if ((rc = encode_map(enc, &tmD, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, out_codes, 4, odims, box, one, "code output", CU_TENSOR_MAP_SWIZZLE_64B)) != TQ_OK) return rc; }
-        else tmD = tmA;
+    if (!hit) {
+        int rc = plan_conv(a, pl);
+        if (rc != TQ_OK) return rc;
+        if (!no_cache) {
+            std::lock_guard<std::mutex> lk(g_plan_mu);
+            if (g_plan_count >= 4096) { for (auto &b : g_plans) b.clear(); g_plan_count = 0; }
+            g_plans[h & 63].push_back(pl);
+            ++g_plan_count;
+        }
     }
-    CUtensorMap tmR = tmA;
-    if (residual) {   // residual tile: same box as the fp32 output tile
-        cuuint32_t box[4] = {32, (cuuint32_t)g.wbox, (cuuint32_t)g.hbox, (cuuint32_t)g.nbox};
-        if ((rc = encode_map(enc, &tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, residual, 4, odims, box, one, "residual")) != TQ_OK) return rc;
+    return launch_variant(pl.variant, pl.tmA, pl.tmB, pl.tmC, pl.tmD, pl.tmR, pl.g, s);
+}
+
+static int check_conv_args(const void *act, const void *wgt, const void *out_f32, const void *out_codes, const void *bias,
+                           const void *bn_a, const void *bn_b, const void *residual, int N, int H, int W, int C, int Cout,
+                           int R, int S, int stride, int pad, float next_sf, int next_bits, int next_terms, int c_align)
+{
+    if (!act || !wgt || (!out_f32 && !out_codes)) return fail(TQ_ERR_INVALID, "NULL pointer");
+    if (N < 1 || H < 1 || W < 1 || C < 1 || Cout < 1 || R < 1 || S < 1 || stride < 1 || pad < 0)
+        return fail(TQ_ERR_INVALID, "bad convolution geometry");
+    if (C % c_align != 0) return fail(TQ_ERR_UNSUPPORTED, "input channels must be a multiple of %d (16-byte TMA rows), got %d", c_align, C);
+    if (Cout % 4 != 0) return fail(TQ_ERR_UNSUPPORTED, "output channels must be a multiple of 4, got %d", Cout);
+    if (out_codes && Cout % 8 != 0) return fail(TQ_ERR_UNSUPPORTED, "code output needs Cout %% 8 == 0, got %d", Cout);
+    if ((bn_a == nullptr) != (bn_b == nullptr)) return fail(TQ_ERR_INVALID, "bn_a and bn_b go together");
+    if ((((uintptr_t)act | (uintptr_t)wgt | (uintptr_t)out_f32 | (uintptr_t)out_codes | (uintptr_t)bias |
+          (uintptr_t)bn_a | (uintptr_t)bn_b | (uintptr_t)residual) & 15u) != 0)
+        return fail(TQ_ERR_INVALID, "pointers must be 16-byte aligned");
+    if (out_codes) {
+        if (!(next_sf > 0.0f) || !(next_sf < INFINITY)) return fail(TQ_ERR_INVALID, "next_sf must be positive and finite");
+        if (next_bits < 1 || next_bits > GM_LUT_MAX_BITS) return fail(TQ_ERR_UNSUPPORTED, "fused encode supports 1..%d bits", GM_LUT_MAX_BITS);
+        if (next_terms < 0) return fail(TQ_ERR_INVALID, "next_terms must be >= 0");
     }
-    cudaStream_t s = (cudaStream_t)stream;
-    if (block_n == 64) return launch_conv<64>(tmA, tmB, tmC, tmD, tmR, g, s);
-    if (block_n == 256) return launch_conv<256>(tmA, tmB, tmC, tmD, tmR, g, s);
-    return launch_conv<128>(tmA, tmB, tmC, tmD, tmR, g, s);
+    return TQ_OK;
+}
+
+}  // namespace tq
+
+using namespace tq;
+
+extern "C" int tq_conv2d_codes_fused(const void *act, const void *wgt, float *out_f32, void *out_codes,
+                                     const float *bias, const float *bn_a, const float *bn_b,
+                                     const float *residual, int N, int H, int W, int C, int Cout, int R, int S,
+                                     int stride, int pad, float scale, int relu, float next_sf, int next_bits,
+                                     int next_terms, int acc_groups, void *stream)
+{
+    int rc = check_conv_args(act, wgt, out_f32, out_codes, bias, bn_a, bn_b, residual, N, H, W, C, Cout, R, S, stride, pad,
+                             next_sf, next_bits, next_terms, 8);
+    if (rc != TQ_OK) return rc;
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));                       // (padding bytes take part in the cache key)
+    a.act = act; a.wgt = wgt; a.out_f32 = out_f32; a.out_codes = out_codes; a.bias = bias; a.bn_a = bn_a; a.bn_b = bn_b;
+    a.residual = residual;
+    a.kind = 0; a.N = N; a.H = H; a.W = W; a.C = C; a.Cout = Cout; a.R = R; a.S = S; a.stride = stride; a.pad = pad;
+    a.relu = relu ? 1 : 0; a.next_bits = out_codes ? next_bits : 1; a.next_terms = next_terms;
+    a.acc_groups = acc_groups < 1 ? 1 : acc_groups; a.planes_a = 1; a.planes_w = 1;
+    a.scale = scale; a.next_sf = out_codes ? next_sf : 1.0f;
+    return run_conv(a, (cudaStream_t)stream);
 }
 
 extern "C" int tq_conv2d_codes_f16(const void *act, const void *wgt, const float *bias, float *out,
                                    int N, int H, int W, int C, int Cout, int R, int S, int stride, int pad,
-                                   float scale, void *stream)
+                                   float scale, int acc_groups, void *stream)
 {
     if (!out) return fail(TQ_ERR_INVALID, "NULL pointer");
     return tq_conv2d_codes_fused(act, wgt, out, nullptr, bias, nullptr, nullptr, nullptr, N, H, W, C, Cout, R, S,
-                                 stride, pad, scale, 0, 1.0f, 1, 0, stream);
+                                 stride, pad, scale, 0, 1.0f, 1, 0, acc_groups, stream);
+}
+
+extern "C" int tq_conv2d_planes_i8(const void *act_planes, const void *wgt_planes, int planes_a, int planes_w,
+                                   float *out_f32, void *out_codes, const float *bias, const float *bn_a,
+                                   const float *bn_b, const float *residual, int N, int H, int W, int C, int Cout,
+                                   int R, int S, int stride, int pad, float scale, int relu, float next_sf,
+                                   int next_bits, int next_terms, void *stream)
+{
+    int rc = check_conv_args(act_planes, wgt_planes, out_f32, out_codes, bias, bn_a, bn_b, residual, N, H, W, C, Cout, R, S,
+                             stride, pad, next_sf, next_bits, next_terms, 16);
+    if (rc != TQ_OK) return rc;
+    if (planes_a < 1 || planes_a > 2 || planes_w < 1 || planes_w > 2) return fail(TQ_ERR_INVALID, "1 or 2 planes per operand");
+    // |acc| <= K * (2^7 << 4 + 15)^2-ish; with two planes an operand reaches 16 * 127 + 15 = 2047
+    const double amax = planes_a == 2 ? 2047.0 : 127.0, wmax = planes_w == 2 ? 2047.0 : 127.0;
+    if ((double)C * R * S * amax * wmax >= 2147483648.0)
+        return fail(TQ_ERR_UNSUPPORTED, "K = %d is too deep for an int32 accumulator at these plane counts", C * R * S);
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.act = act_planes; a.wgt = wgt_planes; a.out_f32 = out_f32; a.out_codes = out_codes; a.bias = bias; a.bn_a = bn_a;
+    a.bn_b = bn_b; a.residual = residual;
+    a.kind = 1; a.N = N; a.H = H; a.W = W; a.C = C; a.Cout = Cout; a.R = R; a.S = S; a.stride = stride; a.pad = pad;
+    a.relu = relu ? 1 : 0; a.next_bits = out_codes ? next_bits : 1; a.next_terms = next_terms;
+    a.acc_groups = 1; a.planes_a = planes_a; a.planes_w = planes_w;
+    a.scale = scale; a.next_sf = out_codes ? next_sf : 1.0f;
+    return run_conv(a, (cudaStream_t)stream);
+}
+
+// ---- operand planes and the static accumulator bound ------------------------------------------------
+namespace tq {
+
+// fp16 integer codes -> signed 8-bit planes: code = 16 * hi + lo, hi = code >> 4 (floor), lo = code & 15.
+// planes == 1: the code itself as s8 (the caller knows |code| <= 127; a code outside sets *overflow).
+__global__ void __launch_bounds__(256)
+codes_to_planes_kernel(const __half *__restrict__ codes, int8_t *__restrict__ planes, int64_t n8, int64_t plane_stride,
+                       int nplanes, int *__restrict__ overflow)
+{
+    bool ovf = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(codes) + i);      // 8 codes
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t hi[2] = {0u, 0u}, lo[2] = {0u, 0u};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = __half2int_rn(__ushort_as_half((unsigned short)(w[e >> 1] >> (16 * (e & 1)))));
+            int h, l;
+            if (nplanes == 2) { h = c >> GM_I8_SHIFT; l = c & ((1 << GM_I8_SHIFT) - 1); }
+            else { h = c; l = 0; }
+            ovf |= (h < -128 || h > 127);
+            hi[e >> 2] |= (uint32_t)(h & 0xFF) << (8 * (e & 3));
+            lo[e >> 2] |= (uint32_t)(l & 0xFF) << (8 * (e & 3));
+        }
+        reinterpret_cast<uint2 *>(planes)[i] = make_uint2(hi[0], hi[1]);
+        if (nplanes == 2) reinterpret_cast<uint2 *>(planes + plane_stride)[i] = make_uint2(lo[0], lo[1]);
+    }
+    if (ovf && overflow) atomicExch(overflow, 1);
+}
+
+// per (output channel, 64-channel block): sum of the positive and of the negative weight codes over all taps
+__global__ void __launch_bounds__(128)
+weight_l1_kernel(const __half *__restrict__ wgt, int RS, int Cout, int C, int kcb, long long *__restrict__ pos, long long *__restrict__ neg)
+{
+    const int co = blockIdx.x, kb = blockIdx.y;
+    long long p = 0, m = 0;
+    const int c0 = kb * GM_BLOCK_K, c1 = min(C, c0 + GM_BLOCK_K);
+    for (int t = threadIdx.x; t < RS * (c1 - c0); t += blockDim.x) {
+        const int tap = t / (c1 - c0), c = c0 + t % (c1 - c0);
+        const int v = __half2int_rn(wgt[((int64_t)tap * Cout + co) * C + c]);
+        if (v > 0) p += v; else m -= v;
+    }
+    __shared__ long long sp[128], sm[128];
+    sp[threadIdx.x] = p; sm[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { sp[threadIdx.x] += sp[threadIdx.x + o]; sm[threadIdx.x] += sm[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { pos[(int64_t)co * kcb + kb] = sp[0]; neg[(int64_t)co * kcb + kb] = sm[0]; }
+}
+
+}  // namespace tq
+
+extern "C" int tq_codes_to_planes(const void *codes_f16, void *planes_s8, int64_t n, int planes, int *overflow, void *stream)
+{
+    if (!codes_f16 || !planes_s8) return fail(TQ_ERR_INVALID, "NULL pointer");
+    if (n < 0 || n % 8 != 0) return fail(TQ_ERR_INVALID, "element count must be a multiple of 8");
+    if (planes != 1 && planes != 2) return fail(TQ_ERR_INVALID, "1 or 2 planes");
+    if ((((uintptr_t)codes_f16 | (uintptr_t)planes_s8) & 15u) != 0) return fail(TQ_ERR_INVALID, "pointers must be 16-byte aligned");
+    if (n == 0) return TQ_OK;
+    int64_t blocks = (n / 8 + 255) / 256;
+    if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
+    codes_to_planes_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __half *)codes_f16, (int8_t *)planes_s8, n / 8, n,
+                                                                        planes, overflow);
+    count_launch();
+    return check_launch("codes_to_planes_kernel");
+}
+
+extern "C" int tq_conv_weight_l1(const void *wgt_f16, int RS, int Cout, int C, long long *pos, long long *neg, void *stream)
+{
+    if (!wgt_f16 || !pos || !neg) return fail(TQ_ERR_INVALID, "NULL pointer");
+    if (RS < 1 || Cout < 1 || C < 1) return fail(TQ_ERR_INVALID, "bad weight shape");
+    const int kcb = (C + GM_BLOCK_K - 1) / GM_BLOCK_K;
+    weight_l1_kernel<<<dim3((unsigned)Cout, (unsigned)kcb), 128, 0, (cudaStream_t)stream>>>((const __half *)wgt_f16, RS, Cout, C, kcb, pos, neg);
+    count_launch();
+    return check_launch("weight_l1_kernel");
 }
 
 
@@ -1256,7 +1564,10 @@ static int stem_impl(const void *x, int x_dtype, void *x2_scratch, const void *w
     }
     if (g.nbox != 1) return fail(TQ_ERR_UNSUPPORTED, "stem conv expects images of at least 128 output pixels");
     if (block_n != 64) return fail(TQ_ERR_UNSUPPORTED, "stem conv supports Cout <= 64");
-    return launch_conv<64>(tmA, tmB, tmC, tmD, tmA, g, s, true);
+    g.kblk = GM_BLOCK_K; g.kcpg = 1; g.planes_a = g.planes_w = 1; g.acc_int = 0;   // hi/lo groups are summed in fp32
+    ConvVariant variant = CV_NONE;
+    if ((rc = pick_variant(g, 64, 0, true, variant)) != TQ_OK) return rc;
+    return launch_variant(variant, tmA, tmB, tmC, tmD, tmA, g, s);
 }
 
 extern "C" int tq_stem_conv7x7s2_dt(const void *x, int x_dtype, void *x2_scratch, const void *w2, float *out,

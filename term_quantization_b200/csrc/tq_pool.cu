@@ -93,7 +93,8 @@ extern "C" int tq_bn_relu_maxpool_encode(const float *x, const float *bn_a, cons
     p.next_terms = next_terms;
     if (out_codes) {
         if (!(next_sf > 0.0f) || !(next_sf < INFINITY)) return fail(TQ_ERR_INVALID, "next_sf must be positive and finite");
-        if (next_bits < 1 || next_bits > 12 || next_terms < 0) return fail(TQ_ERR_UNSUPPORTED, "fused encode supports 1..12 bits");
+        // codes are stored as fp16: |code| <= 2^bits must stay exactly representable (11-bit significand)
+        if (next_bits < 1 || next_bits > 11 || next_terms < 0) return fail(TQ_ERR_UNSUPPORTED, "fused encode supports 1..11 bits");
     }
     p.next_fastdiv = (p.next_sf >= 9.313225746154785e-10f && p.next_sf <= 1073741824.0f) ? 1 : 0;
     const int64_t total = (int64_t)N * p.Ho * p.Wo * (C / 4);

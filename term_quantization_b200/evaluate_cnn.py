@@ -60,7 +60,8 @@ def select_engine(qmodel, engine):
 
 def main(argv=None):
     parser = argparse.ArgumentParser(description='TQ CNN evaluation')
-    parser.add_argument('val_dir', nargs='?', default=None, help='unused: data is synthetic')
+    parser.add_argument('val_dir', nargs='?', default=None,
+                        help='dataset root holding imagenet/val (evaluate_cnn.py:50); synthetic images when absent')
     parser.add_argument('-a', '--arch', default='resnet18', choices=cnn_models.model_names())
     parser.add_argument('-j', '--workers', default=0, type=int)
     parser.add_argument('-b', '--batch-size', default=256, type=int)
@@ -76,7 +77,7 @@ def main(argv=None):
     if not torch.cuda.is_available():
         raise SystemExit("the TR op is CUDA-only: no CPU path")
     torch.cuda.set_device(args.gpu)
-    val_loader = util.synthetic_loader(args.images, args.batch_size, workers=args.workers)
+    val_loader = util.get_imagenet_validation(args)        # evaluate_cnn.py:62; synthetic without the dataset
     criterion = nn.CrossEntropyLoss().cuda(args.gpu)
     torch.manual_seed(0)
     if args.arch == 'efficientnet_b0':

@@ -35,18 +35,22 @@ def _quant_key(layer):
 
 
 class _Conv:
-    """Packed operands of one TRConv2dLayer + the BatchNorm that follows it."""
+    """Packed operands of one TRConv2dLayer + the BatchNorm that follows it, and the exactness plan of its
+    contraction (conv_codes.plan_weight).  `post_relu`: the executor guarantees non-negative input codes, which
+    halves the static accumulator bound (only one sign of the weights can pile up)."""
 
-    def __init__(self, layer, bn):
+    def __init__(self, layer, bn, post_relu=True, engine="auto"):
         why = layer.tensor_core_blocker()
         if why is not None:
             raise NotImplementedError(f"fused path: {why}")
         if layer.input_quant.tracking:
             raise RuntimeError("calibrate the model (set_tr_tracking(model, False)) before fusing")
-        if layer._tc_weight is None:
-            layer.use_tensor_cores()
+        if layer._tc_weight is None or layer._tc_key != layer._weight_key():
+            layer.use_tensor_cores(True, engine)
         self.layer = layer
         self.w = layer._tc_weight
+        self.plan = conv_codes.plan_weight(self.w, 1 << int(layer.input_quant.data_bits), signed_act=not post_relu,
+                                           engine=engine)
         self.quant = _quant_key(layer)
         sfx32 = torch.tensor(self.quant[0], dtype=torch.float32)
         self.scale = (sfx32 * torch.tensor(layer._tc_wsf32, dtype=torch.float32)).item()
@@ -55,17 +59,26 @@ class _Conv:
         c = layer.conv
         self.ks, self.stride, self.pad = c.kernel_size, c.stride[0], c.padding[0]
 
+    def check_fresh(self):
+        """The packed weight, scale and quantiser are snapshots: refuse to run on stale ones (re-calibration,
+        load_state_dict, .to(device) after fusing)."""
+        layer = self.layer
+        if layer._tc_weight is not self.w or layer._tc_key != layer._weight_key() or _quant_key(layer) != self.quant:
+            raise RuntimeError("the wrapped model changed after fusing (weights, device or scale factors): "
+                               "build the fused executor again")
+
     def __call__(self, codes, residual=None, relu=False, want_f32=True, next_quant=None):
         return conv_codes.conv2d_codes_fused(codes, self.w, self.ks, self.stride, self.pad, self.scale,
                                              bias=self.bias, bn=self.bn, residual=residual, relu=relu,
-                                             want_f32=want_f32, next_quant=next_quant)
+                                             want_f32=want_f32, next_quant=next_quant, plan=self.plan)
 
 
 class FusedResNet(nn.Module):
     """Wraps a calibrated, TQ-converted torchvision ResNet built from BasicBlocks."""
 
-    def __init__(self, model, stem="tcgen05_pool"):
-        """stem: 'tcgen05_pool' (the whole stem -- conv, BatchNorm, ReLU, max-pool, first encode -- in ONE
+    def __init__(self, model, stem="tcgen05_pool", engine="auto"):
+        """engine: how each conv's exact accumulator is obtained ('auto' | 'f16' | 'i8', conv_codes.plan_weight).
+        stem: 'tcgen05_pool' (the whole stem -- conv, BatchNorm, ReLU, max-pool, first encode -- in ONE
         tensor-core kernel, pooling in the conv epilogue: the 822 MB conv output never reaches HBM),
         'tcgen05' (stem conv on the tensor cores, then the fused BN+ReLU+max-pool+encode pass; bit-identical,
         ~1 % slower end to end), or 'cudnn' (cuDNN's fp32 conv)."""
@@ -84,8 +97,9 @@ class FusedResNet(nn.Module):
                 if blk.downsample is not None:
                     if not isinstance(blk.downsample[0], tr_layer.TRConv2dLayer):
                         raise NotImplementedError("downsample conv must be a TRConv2dLayer")
-                    down = _Conv(blk.downsample[0], blk.downsample[1])
-                self.blocks.append((_Conv(blk.conv1, blk.bn1), _Conv(blk.conv2, blk.bn2), down))
+                    down = _Conv(blk.downsample[0], blk.downsample[1], engine=engine)
+                # every conv input of a BasicBlock chain is the output of a ReLU (block input / conv1 output)
+                self.blocks.append((_Conv(blk.conv1, blk.bn1, engine=engine), _Conv(blk.conv2, blk.bn2, engine=engine), down))
         mp = model.maxpool
         self.fuse_stem = (isinstance(mp, nn.MaxPool2d) and mp.kernel_size in (3, (3, 3)) and mp.stride in (2, (2, 2))
                           and mp.padding in (1, (1, 1)) and mp.dilation in (1, (1, 1)) and not mp.ceil_mode
@@ -107,11 +121,30 @@ class FusedResNet(nn.Module):
         return tr_cuda.tr_codes(x_nhwc.view(1, -1, 1, 1), sf, bits, 1, terms,
                                 dtype=torch.float16).view(x_nhwc.shape)
 
+    def chain_description(self):
+        """The fused chain as plain data (integer weight codes, fp32 scale, BatchNorm affine, quantiser per conv):
+        what oracle/fused_emul.run_resnet_chain needs to reproduce the block outputs bit for bit on a CPU."""
+        def d(c):
+            if c is None:
+                return None
+            return {"w": c.w.cpu().numpy().astype("int32"), "ks": tuple(c.ks), "stride": c.stride, "pad": c.pad,
+                    "scale": c.scale, "bias": None if c.bias is None else c.bias.detach().float().cpu().numpy(),
+                    "bn": None if c.bn is None else (c.bn[0].cpu().numpy(), c.bn[1].cpu().numpy()),
+                    "quant": c.quant, "engine": c.plan.engine, "groups": c.plan.groups}
+        return [(d(c1), d(c2), d(down)) for c1, c2, down in self.blocks]
+
     @torch.no_grad()
-    def forward(self, x):
+    def forward(self, x, capture=None):
         """x: [N, 3, H, W] images, fp32 or bf16 / fp16 (16-bit images are used as they are: the values the
-        reference would see after `images.float()`), any memory format (channels_last avoids a copy)."""
+        reference would see after `images.float()`), any memory format (channels_last avoids a copy).
+        capture: optional dict that receives 'stem' (the fp32 NHWC tensor reaching layer1) and 'final' (the
+        last block's fp32 NHWC output) -- the two ends of the chain the CPU emulation checks."""
         m = self.model
+        if not torch.cuda.is_current_stream_capturing():
+            for blk in self.blocks:
+                for c in blk:
+                    if c is not None:
+                        c.check_fresh()
         x = x.contiguous(memory_format=torch.channels_last)
         if self.fuse_stem:
             # stem conv (never wrapped, fp32 arithmetic), then bn1 + relu + maxpool + first encode in one pass
@@ -135,6 +168,8 @@ class FusedResNet(nn.Module):
             x = m.maxpool(m.relu(m.bn1(m.conv1(x.float()))))
             cur = x.permute(0, 2, 3, 1)                  # fp32 [N, H, W, C], contiguous
             codes = {}
+        if capture is not None:
+            capture["stem"] = cur
         for i, (c1, c2, down) in enumerate(self.blocks):
             def get(q):
                 if q not in codes:
@@ -145,6 +180,8 @@ class FusedResNet(nn.Module):
             nxt = self.blocks[i + 1][0].quant if i + 1 < len(self.blocks) else None
             cur, out_codes = c2(mid, residual=identity, relu=True, want_f32=True, next_quant=nxt)
             codes = {nxt: out_codes} if nxt is not None else {}
+        if capture is not None:
+            capture["final"] = cur
         y = cur.permute(0, 3, 1, 2)                      # NCHW shape, channels_last memory
         return m.fc(torch.flatten(m.avgpool(y), 1))
 
@@ -166,8 +203,13 @@ class FusedVGG(nn.Module):
             raise NotImplementedError("FusedVGG expects an unwrapped first conv")
         self.stages = []                     # (kind, payload): 'torch' module | 'conv' (_Conv, relu) | 'pool' module
         i = 0
+        post_relu = False                    # is the tensor reaching the next conv the output of a ReLU (or a pool of one)?
         while i < len(mods):
             m = mods[i]
+            if isinstance(m, nn.ReLU):
+                post_relu = True
+            elif not isinstance(m, nn.MaxPool2d) and not isinstance(m, tr_layer.TRConv2dLayer):
+                post_relu = False
             if isinstance(m, tr_layer.TRConv2dLayer):
                 bn = None
                 relu = False
@@ -178,7 +220,8 @@ class FusedVGG(nn.Module):
                 if j < len(mods) and isinstance(mods[j], nn.ReLU):
                     relu = True
                     j += 1
-                self.stages.append(("conv", (_Conv(m, bn), relu)))
+                self.stages.append(("conv", (_Conv(m, bn, post_relu=post_relu), relu)))
+                post_relu = relu
                 i = j
             elif isinstance(m, nn.MaxPool2d):
                 if m.dilation not in (1, (1, 1)) or m.ceil_mode:

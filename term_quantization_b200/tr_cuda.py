@@ -79,6 +79,11 @@ def tr_codes(input, sf, bitwidth, group_size, num_keep_terms, *, dtype=torch.int
     B, Cc, WH = _dims(input)
     if out is None:
         out = torch.empty(input.shape, dtype=dtype, device=input.device)
+    elif out.shape != input.shape or out.dtype not in _CODE_DTYPES or out.device != input.device \
+            or not out.is_contiguous():
+        raise RuntimeError("out must match input in shape and device, hold a code dtype and be contiguous")
+    if overflow is not None and (overflow.dtype != torch.int32 or overflow.device != input.device):
+        raise RuntimeError("overflow must be an int32 tensor on the input's device")
     with torch.cuda.device(input.device):
         rc = _lib.lib().tq_tr_encode_codes(
             input.data_ptr(), out.data_ptr(), _DTYPES[input.dtype], _CODE_DTYPES[out.dtype],

@@ -97,15 +97,17 @@ def compute_compressed_hese(w, sf, weight_terms):
     return bit_width * int(count.item())
 
 
-def use_tensor_cores(model, enable=True):
+def use_tensor_cores(model, enable=True, engine="auto"):
     """Switch every supported TRConv2dLayer of `model` to the tcgen05 code-domain conv.
+    engine: 'auto' (kind::f16 where exact fp32 accumulation is proven from the weights, else the kind::i8 plane
+    engine), 'f16' (raise for an unprovable layer) or 'i8'.
     Returns (switched, skipped) where skipped is a list of (module name, reason)."""
     switched, skipped = [], []
     for name, layer in model.named_modules():
         if isinstance(layer, TRConv2dLayer):
             why = layer.tensor_core_blocker() if enable else None
             if why is None:
-                layer.use_tensor_cores(enable)
+                layer.use_tensor_cores(enable, engine)
                 switched.append(name)
             else:
                 skipped.append((name, why))
@@ -140,6 +142,15 @@ class LinearQuantize(nn.Module):
 
     def _track(self, x):
         xc = x.detach().contiguous()
+        if xc.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            raise RuntimeError(f"LinearQuantize tracking: unsupported input dtype {xc.dtype} (fp32 / bf16 / fp16)")
+        # the kernel adds fp32 counts into hist_bins through a raw pointer: after model.half() / .to(other device)
+        # the buffer would be too small or live on another GPU, so it is brought back first (counts stay exact
+        # in fp32 up to 2^24 per bin per call)
+        if self.hist_bins.dtype != torch.float32 or self.hist_bins.device != xc.device:
+            self.hist_bins = self.hist_bins.to(device=xc.device, dtype=torch.float32)
+        if not self.hist_bins.is_contiguous() or self.hist_bins.numel() != self.num_bins:
+            raise RuntimeError("LinearQuantize.hist_bins must be a contiguous fp32 tensor of num_bins elements")
         if self._scratch is None or self._scratch.device != xc.device:
             self._scratch = torch.zeros(self.num_bins, dtype=torch.int32, device=xc.device)
         dt = tr_cuda._DTYPES[xc.dtype]
@@ -207,7 +218,11 @@ class TRConv2dLayer(_TRBase):
                     num_terms)
         conv_layer.weight = self._reveal_weight(conv_layer.weight)
         self.conv = conv_layer
-        self._tc_weight = None
+        # packed operands of the tensor-core path: a NON-PERSISTENT buffer, so that .to(device) / .cuda() move it with
+        # the module while state_dict stays the reference's; rebuilt whenever conv.weight or w_sf changed
+        self.register_buffer("_tc_weight", None, persistent=False)
+        self._tc_plan = None
+        self._tc_key = None
 
     def tensor_core_blocker(self):
         """None if the tcgen05 path supports this layer, else the reason it does not."""
@@ -224,19 +239,30 @@ class TRConv2dLayer(_TRBase):
             return "non-zero padding mode"
         if c.in_channels % 8 or c.out_channels % 4:
             return "channel counts must be multiples of 8 (in) and 4 (out)"
-        if self.weight_bits > 11 or self.data_bits > 11:
-            return "codes above 2^11 are not exact in fp16"
+        if self.weight_bits > 10 or self.data_bits > 10:
+            return "codes above 2^10 fit neither fp16 codes with a provable fp32 accumulator nor two 8-bit planes"
         if c.weight.dtype != torch.float32:
             return "fp32 weights only"
         return None
 
-    def use_tensor_cores(self, enable=True):
+    def _weight_key(self):
+        w = self.conv.weight
+        return (w.data_ptr(), w._version, w.device, float(self.w_sf), int(self.data_bits))
+
+    def use_tensor_cores(self, enable=True, engine="auto"):
+        """Pack the term-revealed weight for the tcgen05 conv and PROVE how it can run exactly
+        (conv_codes.plan_weight): kind::f16 with as many K-chunk accumulators as the static bound
+        act_max * max(sum w+, sum w-) < 2^24 needs, else the kind::i8 plane engine.  engine='f16' raises for a layer
+        that cannot be proven, engine='i8' forces the plane engine."""
         if not enable:
             self._tc_weight = None
+            self._tc_plan = None
+            self._tc_key = None
             return self
         why = self.tensor_core_blocker()
         if why is not None:
             raise NotImplementedError(f"tcgen05 conv path: {why}")
+        from . import conv_codes
         w = self.conv.weight.detach()
         sf32 = torch.tensor(self.w_sf, dtype=torch.float32).item()       # what the binding saw
         codes = torch.round(w / sf32)
@@ -245,10 +271,25 @@ class TRConv2dLayer(_TRBase):
         O, I, kh, kw = codes.shape
         self._tc_weight = codes.permute(2, 3, 0, 1).reshape(kh * kw, O, I).to(torch.float16).contiguous()
         self._tc_wsf32 = sf32
+        self._tc_engine = engine
+        # activation codes reach 2^data_bits (HESE rounds 2^bits - 1 up); they are signed unless a ReLU precedes the
+        # layer, which the layer cannot know: the proof assumes signed activations (sum of |w|) -- fused executors
+        # that know the input is post-ReLU re-plan with signed_act=False (fused._Conv)
+        self._tc_plan = conv_codes.plan_weight(self._tc_weight, 1 << self.data_bits, signed_act=True, engine=engine)
+        self._tc_key = self._weight_key()
         return self
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if getattr(self, "_tc_weight", None) is not None:
+            # moved / cast with the module: the plan holds device pointers of the old tensors
+            self.use_tensor_cores(True, getattr(self, "_tc_engine", "auto"))
+        return out
 
     def _forward_tensor_cores(self, x):
         from . import conv_codes
+        if self._tc_key != self._weight_key():                           # load_state_dict / re-reveal since packing
+            self.use_tensor_cores(True, getattr(self, "_tc_engine", "auto"))
         c = self.conv
         q = self.input_quant
         x_nhwc = x.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)   # physical NHWC view
@@ -257,7 +298,7 @@ class TRConv2dLayer(_TRBase):
         sfx32 = torch.tensor(float(q.sf), dtype=torch.float32)
         scale = (sfx32 * torch.tensor(self._tc_wsf32, dtype=torch.float32)).item()   # fp32 product
         out = conv_codes.conv2d_codes(codes, self._tc_weight, c.bias, c.kernel_size, c.stride[0],
-                                      c.padding[0], scale)
+                                      c.padding[0], scale, plan=self._tc_plan)
         return out.permute(0, 3, 1, 2)                                   # NCHW shape, channels_last memory
 
     def forward(self, x):

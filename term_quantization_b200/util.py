@@ -1,6 +1,8 @@
-"""Validation loop and meters (mirror of util.py:39-133).  The ImageNet loader of the
-reference (util.py:11-36) needs a dataset that does not exist here; `synthetic_loader`
-produces batches of the same shape and dtype."""
+"""Validation loop, meters and loaders (mirror of util.py:11-133).  `get_imagenet_validation`
+keeps the reference's signature and transforms (util.py:11-36) and is used when `args.val_dir`
+holds `imagenet/val`; where that dataset does not exist (this container, the GPU box)
+it falls back to `synthetic_loader`, which produces batches of the same shape and dtype."""
+import os
 import time
 
 import torch
@@ -28,6 +30,32 @@ def synthetic_loader(n_images, batch_size, size=224, seed=0, workers=0):
                                        pin_memory=True)
 
 
+def get_imagenet_validation(args):
+    """ImageNet validation loader (util.py:11-36): Resize(256) + CenterCrop(224) + Normalize, or the
+    EfficientNet image size with bicubic resize for `efficientnet_*` (resolved lazily: the third-party
+    package is optional).  Without `<val_dir>/imagenet/val` a synthetic loader of the same shape is
+    returned (`args.images` images if given, else 256)."""
+    val_dir = getattr(args, 'val_dir', None)
+    root = os.path.join(val_dir, 'imagenet', 'val') if val_dir else None
+    image_size, bicubic = 224, False
+    if 'efficientnet' in getattr(args, 'arch', ''):
+        from efficientnet_pytorch import EfficientNet
+        image_size, bicubic = EfficientNet.get_image_size(args.arch.replace('_', '-')), True
+    if root is None or not os.path.isdir(root):
+        return synthetic_loader(getattr(args, 'images', None) or 256, args.batch_size, size=image_size,
+                                workers=getattr(args, 'workers', 0))
+    import PIL
+    import torchvision.datasets as datasets
+    import torchvision.transforms as transforms
+    normalize = transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])
+    resize = (transforms.Resize(image_size, interpolation=PIL.Image.BICUBIC) if bicubic
+              else transforms.Resize(256))
+    tf = transforms.Compose([resize, transforms.CenterCrop(image_size), transforms.ToTensor(), normalize])
+    return torch.utils.data.DataLoader(datasets.ImageFolder(root, tf), batch_size=args.batch_size,
+                                       shuffle=False, num_workers=getattr(args, 'workers', 0),
+                                       pin_memory=True)
+
+
 def accuracy(output, target, topk=1):
     """Top-k accuracy in percent."""
     with torch.no_grad():
@@ -39,6 +67,9 @@ def accuracy(output, target, topk=1):
 class AverageMeter:
     def __init__(self, name, fmt=':f'):
         self.name, self.fmt = name, fmt
+        self.reset()
+
+    def reset(self):
         self.val = self.avg = self.sum = self.count = 0
 
     def update(self, val, n=1):

@@ -270,6 +270,61 @@ def test_fused_resnet_matches_unfused_tensor_core_path():
     assert float((got.argmax(1) == ref.argmax(1)).float().mean()) >= 0.75
 
 
+def _randomise_bn(model, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    with torch.no_grad():
+        for mod in model.modules():
+            if isinstance(mod, nn.BatchNorm2d):
+                n = mod.num_features
+                mod.running_mean.copy_(torch.randn(n, device="cuda", generator=g) * 0.2)
+                mod.running_var.copy_(torch.rand(n, device="cuda", generator=g) + 0.5)
+                mod.weight.copy_(torch.rand(n, device="cuda", generator=g) + 0.5)
+                mod.bias.copy_(torch.randn(n, device="cuda", generator=g) * 0.2)
+
+
+@pytest.mark.parametrize("engine", ["auto", "i8"])
+def test_fused_resnet18_bit_exact_against_cpu_emulation(engine):
+    """BASELINE configs[1] at the benchmarked setting (9-bit, g=8, alpha=12, 3 data terms), batch 8 at 224x224,
+    non-trivial BatchNorm statistics: the output of the 20-launch fused chain (19 wrapped convs with BN / residual /
+    ReLU / next-layer encode in the epilogue) must EQUAL, bit for bit, the CPU emulation of the same arithmetic
+    (oracle/fused_emul.py: exact integer conv -> fl32 -> * scale -> fmaf BN -> + residual -> ReLU -> oracle.tr), and
+    the logits must agree with an fp64 classifier on the emulated features within 1e-5 relative (north star).
+    Both engines: 'auto' = kind::f16 with proven K-chunk accumulators, 'i8' = s8 planes on kind::i8 everywhere."""
+    from torchvision.models import resnet18
+    from oracle import fused_emul
+    from term_quantization_b200 import cnn_models, fused, inference, tr_layer
+    torch.manual_seed(0)
+    base = resnet18(weights=None).cuda().eval()
+    _randomise_bn(base)
+    q = cnn_models.convert_model(base, cnn_models.static_conv_layer_settings(base, 9, 8, 12), 9, 3)
+    x = torch.randn(8, 3, 224, 224, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)).bfloat16()
+    inference.calibrate(q, [x.float()])
+    with torch.no_grad():
+        q = q.to(memory_format=torch.channels_last)
+        f = fused.FusedResNet(q, engine=engine)
+        cap = {}
+        logits = f(x, capture=cap)
+    desc = f.chain_description()
+    used = sorted({(c["engine"], c["groups"]) for blk in desc for c in blk if c is not None})
+    print("engines:", used)
+    if engine == "auto":
+        # the static proof needs 2 / 4 accumulator groups on the K = 2304 / 4608 layers of this random-init model
+        assert all(e == "f16" for e, _ in used) and max(gp for _, gp in used) >= 2, used
+    else:
+        assert used == [("i8", 1)]
+    emu = fused_emul.run_resnet_chain(desc, cap["stem"].cpu().numpy())
+    got = cap["final"].cpu().numpy()
+    assert got.shape == emu.shape
+    assert np.array_equal(got.view(np.uint32), emu.view(np.uint32)) or np.array_equal(got, emu), \
+        f"{int((got != emu).sum())} of {got.size} block outputs differ, max {float(np.abs(got - emu).max())}"
+    # classifier on the emulated features in fp64
+    feat = torch.from_numpy(emu).double().mean(dim=(1, 2))
+    want = feat @ q.fc.weight.detach().double().cpu().t() + q.fc.bias.detach().double().cpu()
+    rel = float((logits.double().cpu() - want).abs().max()) / float(want.abs().max())
+    print(f"logits vs fp64 classifier on emulated features: {rel:.2e}")
+    assert rel < 1e-5
+
+
 @pytest.mark.parametrize("arch,size,expect_grouped", [("vgg16_bn", 64, 0), ("mobilenet_v2", 96, 17)])
 def test_other_cnn_configs_layer_by_layer_on_tensor_cores(arch, size, expect_grouped):
     """BASELINE configs[2] / [3]: every wrapped conv of VGG-16-bn and MobileNet-V2 (random init, reference
