@@ -189,14 +189,15 @@ int tq_conv2d_codes_fused(const void *act, const void *wgt, float *out_f32, void
  *   act_planes  int8 [planes_a][N][H][W][C]   (plane 0 = hi or the code itself, plane 1 = lo), C % 16 == 0
  *   wgt_planes  int8 [planes_w][R*S][Cout][C]
  * Plane pair (pa, pw) accumulates into TMEM accumulator pa + pw; the epilogue recombines them by Horner's rule
- * with the plane shift in int32 and continues exactly as tq_conv2d_codes_fused.  K * max|a| * max|w| < 2^31 is
- * checked from the shapes.  tq_codes_to_planes() produces the planes from fp16 codes.
+ * with the plane shift in int32 and continues exactly as tq_conv2d_codes_fused.  act_max / wgt_max are the caller's
+ * bounds on |code| (2^bits by construction of the term codes); C * R * S * act_max * wgt_max < 2^31 is required.
+ * tq_codes_to_planes() produces the planes from fp16 codes.
  */
 int tq_conv2d_planes_i8(const void *act_planes, const void *wgt_planes, int planes_a, int planes_w,
                         float *out_f32, void *out_codes, const float *bias, const float *bn_a,
                         const float *bn_b, const float *residual, int N, int H, int W, int C, int Cout,
                         int R, int S, int stride, int pad, float scale, int relu, float next_sf,
-                        int next_bits, int next_terms, void *stream);
+                        int next_bits, int next_terms, int act_max, int wgt_max, void *stream);
 
 /* fp16 integer codes (n elements, n % 8 == 0) -> `planes` signed 8-bit planes of n bytes each, plane p at
  * planes_s8 + p * n.  planes = 1 stores the code itself; a value that does not fit sets *overflow (device int,

@@ -28,7 +28,7 @@ SYMBOLS = {
     "tq_hese_term_count": (_i, [_p, _i, _i64, _f, _u, _p, _p]),
     "tq_conv2d_codes_f16": (_i, [_p, _p, _p, _p] + [_i] * 9 + [_f, _i, _p]),
     "tq_conv2d_codes_fused": (_i, [_p] * 8 + [_i] * 9 + [_f, _i, _f, _i, _i, _i, _p]),
-    "tq_conv2d_planes_i8": (_i, [_p, _p, _i, _i] + [_p] * 6 + [_i] * 9 + [_f, _i, _f, _i, _i, _p]),
+    "tq_conv2d_planes_i8": (_i, [_p, _p, _i, _i] + [_p] * 6 + [_i] * 9 + [_f, _i, _f, _i, _i, _i, _i, _p]),
     "tq_codes_to_planes": (_i, [_p, _p, _i64, _i, _p, _p]),
     "tq_conv_weight_l1": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "tq_bn_relu_maxpool_encode": (_i, [_p] * 5 + [_i] * 5 + [_f, _i, _i, _p]),

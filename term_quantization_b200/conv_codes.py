@@ -31,9 +31,9 @@ class WeightPlan:
     """How one packed weight [R*S, Cout, C] runs exactly: engine 'f16' with `groups` K chunks, or 'i8' with the
     signed 8-bit planes of the weight codes.  Built once per weight by `plan_weight`."""
 
-    def __init__(self, engine, groups, bound, act_max, signed, wgt, planes=None, planes_w=0):
+    def __init__(self, engine, groups, bound, act_max, signed, wgt, planes=None, planes_w=0, wgt_max=0):
         self.engine, self.groups, self.bound, self.act_max, self.signed = engine, groups, bound, act_max, signed
-        self.wgt, self.planes, self.planes_w = wgt, planes, planes_w
+        self.wgt, self.planes, self.planes_w, self.wgt_max = wgt, planes, planes_w, wgt_max
 
     def __repr__(self):
         return (f"WeightPlan({self.engine}, groups={self.groups}, bound={self.bound:.3e}, act_max={self.act_max}, "
@@ -109,7 +109,7 @@ def plan_weight(wgt, act_max, signed_act=False, engine="auto"):
     planes, ovf = codes_to_planes(wgt, pw)
     if int(ovf.item()):
         raise RuntimeError("weight codes do not fit their planes")
-    return WeightPlan("i8", 1, bound, act_max, signed_act, wgt, planes=planes, planes_w=pw)
+    return WeightPlan("i8", 1, bound, act_max, signed_act, wgt, planes=planes, planes_w=pw, wgt_max=max(wmax, 1))
 
 
 _PLANS = {}
@@ -145,7 +145,7 @@ def _run_conv(act, plan, out, codes, bias, bn, residual, N, H, W, C, Cout, R, S,
                 act_planes.data_ptr(), plan.planes.data_ptr(), act_planes.shape[0], plan.planes_w, ptr(out), ptr(codes),
                 ptr(bias), ptr(bn[0]) if bn else None, ptr(bn[1]) if bn else None, ptr(residual),
                 N, H, W, C, Cout, R, S, stride, pad, float(scale), int(bool(relu)), float(sf), int(bits), int(terms),
-                stream)
+                int(plan.act_max), int(plan.wgt_max), stream)
     _lib.check(rc)
 
 

@@ -1292,16 +1292,19 @@ extern "C" int tq_conv2d_planes_i8(const void *act_planes, const void *wgt_plane
                                    float *out_f32, void *out_codes, const float *bias, const float *bn_a,
                                    const float *bn_b, const float *residual, int N, int H, int W, int C, int Cout,
                                    int R, int S, int stride, int pad, float scale, int relu, float next_sf,
-                                   int next_bits, int next_terms, void *stream)
+                                   int next_bits, int next_terms, int act_max, int wgt_max, void *stream)
 {
     int rc = check_conv_args(act_planes, wgt_planes, out_f32, out_codes, bias, bn_a, bn_b, residual, N, H, W, C, Cout, R, S,
                              stride, pad, next_sf, next_bits, next_terms, 16);
     if (rc != TQ_OK) return rc;
     if (planes_a < 1 || planes_a > 2 || planes_w < 1 || planes_w > 2) return fail(TQ_ERR_INVALID, "1 or 2 planes per operand");
-    // |acc| <= K * (2^7 << 4 + 15)^2-ish; with two planes an operand reaches 16 * 127 + 15 = 2047
-    const double amax = planes_a == 2 ? 2047.0 : 127.0, wmax = planes_w == 2 ? 2047.0 : 127.0;
-    if ((double)C * R * S * amax * wmax >= 2147483648.0)
-        return fail(TQ_ERR_UNSUPPORTED, "K = %d is too deep for an int32 accumulator at these plane counts", C * R * S);
+    // int32 accumulators: |acc| <= K * act_max * wgt_max (the caller's bounds on |code|: 2^bits by construction of the
+    // term codes; what one / two planes can hold caps them)
+    const int acap = planes_a == 2 ? 2047 : 127, wcap = planes_w == 2 ? 2047 : 127;
+    if (act_max < 1 || act_max > acap || wgt_max < 1 || wgt_max > wcap)
+        return fail(TQ_ERR_INVALID, "act_max / wgt_max must lie in 1..%d / 1..%d for %d / %d planes", acap, wcap, planes_a, planes_w);
+    if ((double)C * R * S * (double)act_max * (double)wgt_max >= 2147483648.0)
+        return fail(TQ_ERR_UNSUPPORTED, "K = %d with |a| <= %d, |w| <= %d can overflow an int32 accumulator", C * R * S, act_max, wgt_max);
     ConvArgs a;
     memset(&a, 0, sizeof(a));
     a.act = act_planes; a.wgt = wgt_planes; a.out_f32 = out_f32; a.out_codes = out_codes; a.bias = bias; a.bn_a = bn_a;

@@ -281,7 +281,8 @@ class TRConv2dLayer(_TRBase):
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
-        if getattr(self, "_tc_weight", None) is not None:
+        tcw = getattr(self, "_tc_weight", None)
+        if tcw is not None and (self._tc_plan is None or self._tc_plan.wgt is not tcw):
             # moved / cast with the module: the plan holds device pointers of the old tensors
             self.use_tensor_cores(True, getattr(self, "_tc_engine", "auto"))
         return out

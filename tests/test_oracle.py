@@ -143,3 +143,36 @@ def test_truncated_hese_code_is_monotone_in_q():
         for k in range(1, 7):
             _, codes = O.tr(q, 1.0, bits, 1, k, return_codes=True)
             assert np.all(np.diff(codes.reshape(-1)) >= 0), (bits, k)
+
+
+def _enc_golden():
+    import os
+    from conftest import ROOT
+    return np.load(os.path.join(ROOT, "tests", "golden", "enc_golden.npz"))
+
+
+def test_binary_encoding_pinned_to_reference_expand_binary_bits():
+    """TQ_ENC_BINARY against bit_utils.expand_binary_bits (bit_utils.py:63-73) run from the reference's text
+    (tests/golden/make_golden_encodings.py): the oracle's quantised value and binary term set are the
+    reference's MSB-first bit planes, and keeping the k most significant terms keeps the first k set planes."""
+    z = _enc_golden()
+    W, sf, bits, planes = z["bin_W"], float(z["bin_sf"]), int(z["bin_bits"]), z["bin_planes"]
+    q_ref = (planes.astype(np.int64) << np.arange(bits - 1, -1, -1)).sum(1)
+    for w, q, row in zip(W[:600], q_ref[:600], planes[:600]):
+        assert O.quantize(abs(float(w)), sf, bits + 1) == q          # reference does not clip: give the quantiser room
+        p, n = O.terms(int(q), O.ENC_BINARY)
+        assert n == 0 and p == q
+    x = W.reshape(1, -1, 1, 1)
+    for k in (1, 2, 3, bits + 1):
+        _, codes = O.tr(x, sf, bits + 1, 1, k, encoding=O.ENC_BINARY, return_codes=True)
+        first_k = (np.cumsum(planes, axis=1) <= k) & (planes > 0)
+        want = (first_k.astype(np.int64) << np.arange(bits - 1, -1, -1)).sum(1) * np.where(W < 0, -1, 1)
+        assert np.array_equal(codes.reshape(-1), want)
+
+
+def test_booth_encoding_pinned_to_verilog_truth_table():
+    """TQ_ENC_BOOTH against verilog/booth_encoder.v:57-78 clocked bit-serially over every 12-bit value
+    (tests/golden/make_golden_encodings.py): same positive / negative digit masks."""
+    z = _enc_golden()
+    for q, P, N in zip(z["booth_q"], z["booth_P"], z["booth_N"]):
+        assert O.terms(int(q), O.ENC_BOOTH) == (int(P), int(N)), q

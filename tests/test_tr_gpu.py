@@ -180,6 +180,38 @@ def test_encodings_and_relu(enc):
                           O.tr(w, 0.03, 8, 3, 5, encoding=code, relu=relu))
 
 
+def test_binary_and_booth_kernels_against_reference_held_fixtures():
+    """The device kernels' BINARY / BOOTH paths against tests/golden/enc_golden.npz directly: BINARY = the bit planes
+    of bit_utils.expand_binary_bits (bit_utils.py:63-73), BOOTH = verilog/booth_encoder.v:57-78 clocked bit-serially
+    (tests/golden/make_golden_encodings.py).  g = 1: keeping k terms keeps the k most significant digits."""
+    import os
+    from conftest import ROOT
+    from term_quantization_b200 import tr_cuda
+    z = np.load(os.path.join(ROOT, "tests", "golden", "enc_golden.npz"))
+    W, sf, bits, planes = z["bin_W"], float(z["bin_sf"]), int(z["bin_bits"]), z["bin_planes"]
+    x = torch.from_numpy(W.reshape(1, -1, 1, 1).copy()).cuda()
+    weights = np.arange(bits - 1, -1, -1)
+    for k in (1, 2, 3, bits + 1):
+        got = tr_cuda.tr_codes(x, sf, bits + 1, 1, k, dtype=torch.int32, encoding="binary").cpu().numpy().reshape(-1)
+        first_k = (np.cumsum(planes, axis=1) <= k) & (planes > 0)
+        want = (first_k.astype(np.int64) << weights).sum(1) * np.where(W < 0, -1, 1)
+        assert np.array_equal(got, want), k
+    # Booth: every 12-bit value as an exactly representable input with sf = 1
+    q, P, N = z["booth_q"], z["booth_P"], z["booth_N"]
+    xq = torch.from_numpy(q.astype(np.float32).reshape(1, -1, 1, 1)).cuda()
+    for k in (1, 2, 4, 13):
+        got = tr_cuda.tr_codes(xq, 1.0, 12, 1, k, dtype=torch.int32, encoding="booth").cpu().numpy().reshape(-1)
+        want = np.zeros_like(q)
+        for i in range(len(q)):
+            kept, left = 0, k
+            for pos in range(12, -1, -1):
+                if left and ((int(P[i]) | int(N[i])) >> pos) & 1:
+                    kept += (1 << pos) if (int(P[i]) >> pos) & 1 else -(1 << pos)
+                    left -= 1
+            want[i] = kept
+        assert np.array_equal(got, want), k
+
+
 @pytest.mark.parametrize("cdtype", [torch.int8, torch.uint8, torch.int16, torch.int32])
 def test_integer_codes(cdtype):
     from term_quantization_b200 import tr_cuda
