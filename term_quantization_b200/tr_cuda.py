@@ -92,3 +92,25 @@ def tr_codes(input, sf, bitwidth, group_size, num_keep_terms, *, dtype=torch.int
             overflow.data_ptr() if overflow is not None else None, _stream_ptr(input.device))
     _lib.check(rc)
     return out
+
+
+_PYBIND = None
+
+
+def pybind():
+    """The compiled torch extension with the reference's exact module surface (`tr(input, sf, bitwidth,
+    group_size, num_keep_terms)`, kernels/tr_cuda.cpp:20-28), built ahead of time from csrc/pybind/tr_cuda_pybind.cpp
+    by `__graft_entry__.build()`; it calls the same C ABI as this module.  Raises if it has not been built."""
+    global _PYBIND
+    if _PYBIND is None:
+        import importlib.util
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tr_cuda_pybind.so")
+        if not os.path.exists(path):
+            raise _lib.TQError(f"{path} is missing: run `python term_quantization_b200/csrc/pybind/build.py`")
+        _lib.lib()                                   # libtq_b200.so first (the adapter links against it)
+        spec = importlib.util.spec_from_file_location("tr_cuda_pybind", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _PYBIND = mod
+    return _PYBIND

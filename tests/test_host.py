@@ -170,3 +170,16 @@ def test_bench_line_contract_on_committed_profile():
     import bench
     traffic, src = bench.ncu_conv_traffic()
     assert traffic is not None and traffic > 1e7 and src.endswith(".csv")
+
+
+def test_pybind_adapter_loads_and_keeps_the_reference_checks():
+    """csrc/pybind/tr_cuda_pybind.cpp built ahead of time: the reference's module surface (kernels/tr_cuda.cpp:20-28)
+    and its precondition messages (kernels/tr_cuda.cpp:12-18).  No compute without a GPU."""
+    import pytest
+    import torch
+    from term_quantization_b200 import _lib, tr_cuda
+    m = tr_cuda.pybind()
+    assert m.version() == _lib.lib().tq_version()
+    assert "Term Revealing (TR) (CUDA)" in m.tr.__doc__
+    with pytest.raises(RuntimeError, match="input must be a CUDA tensor"):
+        m.tr(torch.zeros(2, 8), 1.0, 8, 1, 3)

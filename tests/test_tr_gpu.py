@@ -180,6 +180,29 @@ def test_encodings_and_relu(enc):
                           O.tr(w, 0.03, 8, 3, 5, encoding=code, relu=relu))
 
 
+def test_golden_vectors_through_the_pybind_adapter():
+    """The compiled torch extension (csrc/pybind/tr_cuda_pybind.cpp, the reference's `tr_cuda.tr` signature) over the
+    same C ABI: every golden vector generated from the reference kernel body, new output tensor, input untouched,
+    non-default stream, the reference's error for a non-contiguous input."""
+    from conftest import golden_cases
+    from term_quantization_b200 import tr_cuda
+    m = tr_cuda.pybind()
+    for x, sf, bits, g, alpha, y in golden_cases():
+        xd = torch.from_numpy(x).cuda()
+        keep = xd.clone()
+        out = m.tr(xd, sf, bits, g, alpha)
+        assert out.data_ptr() != xd.data_ptr() and torch.equal(xd, keep)
+        assert bits_equal(out.cpu().numpy(), y), (x.shape, bits, g, alpha)
+    s = torch.cuda.Stream()
+    x = torch.randn(1, 1 << 20, 1, 1, device="cuda")
+    with torch.cuda.stream(s):
+        a = m.tr(x, 0.01, 8, 1, 3)
+    s.synchronize()
+    assert torch.equal(a, tr_cuda.tr(x, 0.01, 8, 1, 3))
+    with pytest.raises(RuntimeError, match="input must be contiguous"):
+        m.tr(torch.randn(4, 8, 3, 3, device="cuda").permute(0, 1, 3, 2), 0.01, 8, 8, 12)
+
+
 def test_binary_and_booth_kernels_against_reference_held_fixtures():
     """The device kernels' BINARY / BOOTH paths against tests/golden/enc_golden.npz directly: BINARY = the bit planes
     of bit_utils.expand_binary_bits (bit_utils.py:63-73), BOOTH = verilog/booth_encoder.v:57-78 clocked bit-serially
