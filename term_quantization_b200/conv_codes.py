@@ -89,7 +89,7 @@ def plan_weight(wgt, act_max, signed_act=False, engine="auto"):
         kcb = pos.shape[1]
         block_n = 64 if Cout <= 64 else 128
         for groups in (1, 2, 4, 8):
-            if kcb % groups or groups * block_n > 512:
+            if kcb % groups or groups * block_n > (512 if block_n == 128 else 256):   # tensor-memory columns (tq_gemm.cu)
                 continue
             p = pos.view(Cout, groups, kcb // groups).sum(2)
             n = neg.view(Cout, groups, kcb // groups).sum(2)

@@ -377,7 +377,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         mbar_init(bfull_bar, 1);
-        for (int i = 0; i < 3; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 256); }   // 256 = two epilogue groups
+        // an accumulator stage is drained by two epilogue groups (256 threads); with a single stage all four groups
+        // drain every tile (a quarter of the columns each)
+        for (int i = 0; i < 3; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], ACC_STAGES == 1 ? 512 : 256); }
         for (int i = 0; i < GM_EPI_GROUPS; ++i) mbar_init(&res_bar[i], 1);
         for (int i = 0; i < 4; ++i) { mbar_init(&afull_bar[i], 1); mbar_init(&aempty_bar[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -662,12 +664,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint8_t *st_codes = st_f32 + g.epi_codes_off;                   // [128][32] fp16,  64B swizzle
         const Quant nq = make_quant(g.write_codes ? g.next_sf : 1.0f, (float)((1u << g.next_bits) - 1u));
         const bool has_res = g.residual != nullptr;
-        constexpr int CHUNKS = BLOCK_N / 64;                    // 32-column chunks per group and tile
+        // With two or three accumulator stages the pairs alternate tiles and group (pair, half) takes half of the columns.
+        // With ONE stage (a tile's accumulator groups fill tensor memory) consecutive completions of the same barrier
+        // cannot be told apart by two waiters that skip every second one, so all four groups take EVERY tile, a quarter
+        // of the columns each (which also drains the accumulator four-wide before the next tile's MMAs may start).
+        const bool single = ACC_STAGES == 1;
+        const int CHUNKS = single ? BLOCK_N / 128 : BLOCK_N / 64;   // 32-column chunks per group and tile
         const uint32_t res_bytes = (uint32_t)(g.wbox * g.hbox * g.nbox) * 128u;
         uint32_t res_phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            if ((it & 1) != pair) continue;
+            if (!single && (it & 1) != pair) continue;
             const int acc = it % ACC_STAGES;                          // accumulator stage of this tile and its use parity
             const uint32_t acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
             const int n_tile = tile % g.n_tiles, m_tile = tile / g.n_tiles;
@@ -683,7 +690,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
 #pragma unroll 1
             for (int cc = 0; cc < CHUNKS; ++cc) {
-                const int col0 = half * (BLOCK_N / 2) + cc * 32;            // column of the tile
+                const int col0 = (single ? grp * (BLOCK_N / 4) : half * (BLOCK_N / 2)) + cc * 32;   // column of the tile
                 const int c0 = n_tile * BLOCK_N + col0;                     // output channel
                 const bool chunk_live = c0 < g.Cout;
                 // (a) residual tile -> fp32 staging (needs the staging tile free: the previous store has read it)
@@ -1138,7 +1145,8 @@ static int plan_conv(const ConvArgs &a, ConvPlan &pl)
         g.kcpg = g.kc_blocks / a.acc_groups;
         g.acc_int = a.acc_groups > 1 ? 1 : 0;
     }
-    if (g.n_groups * block_n > 512)
+    // one accumulator stage (more than 256 columns per tile) is drained by four epilogue groups of 32 columns: N = 128 only
+    if (g.n_groups * block_n > 512 || (2 * g.n_groups * block_n > 512 && block_n != 128))
         return fail(TQ_ERR_UNSUPPORTED, "%d accumulator groups of %d columns exceed tensor memory", g.n_groups, block_n);
     // small layers: every weight tile stays resident in shared memory and the K loop is a table of A loads
     const int taps = R * S * g.kc_blocks;
