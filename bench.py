@@ -126,8 +126,14 @@ class KernelTimer:
                         (conv_codes, "conv2d_codes", "conv",
                          lambda a, k, out: 2 * out.numel() * a[1].shape[0] * a[1].shape[2]),
                         (conv_codes, "conv2d_codes_fused", "conv",
-                         lambda a, k, out: 2 * (out[0] if out[0] is not None else out[1]).numel()
-                         * a[1].shape[0] * a[1].shape[2]),
+                         lambda a, k, out: (2 * (out[0] if out[0] is not None else out[1]).numel()
+                                            * a[1].shape[0] * a[1].shape[2],
+                                            # algorithmic bytes of this launch: codes in, weights in, residual in,
+                                            # fp32 tile out, code tile out -- each tensor once
+                                            a[0].numel() * 2 + a[1].numel() * 2
+                                            + (k["residual"].numel() * 4 if k.get("residual") is not None else 0)
+                                            + (out[0].numel() * 4 if out[0] is not None else 0)
+                                            + (out[1].numel() * 2 if out[1] is not None else 0))),
                         (conv_codes, "stem_conv7x7s2", "stem", lambda a, k, out: 2 * out[0].numel() * 147),
                         (conv_codes, "stem_conv_pool", "stem", lambda a, k, out: 2 * out[0].numel() * 4 * 147),
                         (conv_codes, "bn_relu_maxpool_encode", "pool",
@@ -147,7 +153,8 @@ class KernelTimer:
                 e0.record()
                 out = _orig(*a, **k)
                 e1.record()
-                self.records[_key].append((e0, e1, _work(a, k, out)))
+                w = _work(a, k, out)
+                self.records[_key].append((e0, e1) + (w if isinstance(w, tuple) else (w, 0)))
                 return out
             setattr(mod, attr, timed)
         return self
@@ -158,27 +165,24 @@ class KernelTimer:
 
     def summary(self, key):
         rec = self.records[key]
-        return len(rec), sum(w for _, _, w in rec), sum(a.elapsed_time(b) for a, b, _ in rec)
+        return len(rec), sum(r[2] for r in rec), sum(r[0].elapsed_time(r[1]) for r in rec)
+
+    def bytes(self, key):
+        return sum(r[3] for r in self.records[key])
 
 
 def ncu_conv_traffic():
-    """DRAM bytes per launch of the conv kernel (mean over the wrapped-conv launches of the profiled steps) from
-    the committed ncu launch list of this same command (profiles/r01_launches_final_steps2.csv:
-    dram__bytes_read.sum + dram__bytes_write.sum per launch), or None."""
-    import csv
-    path = os.path.join(ROOT, "profiles", "r01_launches_final_steps2.csv")
+    """DRAM bytes per launch of the conv kernel from this round's ncu capture (profiles/r02_conv_traffic.json, written
+    by tools/ncu_traffic.py from `ncu --set full` of this same command) -- used only while the kernel source it was
+    taken from is unchanged (sha256 of csrc/tq_gemm.cu); otherwise null rather than a stale number."""
+    import hashlib
     try:
-        rows = [r for r in csv.reader(open(path)) if len(r) > 10]
-        h = rows[0]
-        ik, im, iv, iu, iid = (h.index(c) for c in ("Kernel Name", "Metric Name", "Metric Value", "Metric Unit", "ID"))
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        total, ids = 0.0, set()
-        for r in rows[1:]:
-            # wrapped convs only: MODE 2 (<64, 2, ...>) is the unquantised stem conv
-            if "conv_igemm_f16_kernel" in r[ik] and "<64, 2," not in r[ik] and r[im].startswith("dram__bytes_"):
-                total += float(r[iv].replace(",", "")) * scale[r[iu]]
-                ids.add(r[iid])
-        return (total / len(ids), os.path.relpath(path, ROOT)) if ids else (None, None)
+        with open(os.path.join(ROOT, "profiles", "r02_conv_traffic.json")) as f:
+            rec = json.load(f)
+        src = os.path.join(ROOT, "term_quantization_b200", "csrc", "tq_gemm.cu")
+        if hashlib.sha256(open(src, "rb").read()).hexdigest() != rec["tq_gemm_cu_sha256"]:
+            return None, "profiles/r02_conv_traffic.json is from an older tq_gemm.cu: not used"
+        return float(rec["dram_bytes_per_launch"]), "profiles/r02_conv_traffic.json (" + rec.get("how", "ncu --set full") + ")"
     except Exception:
         return None, None
 
@@ -238,14 +242,21 @@ def run_b200(args):
     in_dtype = torch.bfloat16 if (args.input_dtype == "bf16" and args.conv_backend == "fused") else torch.float32
     images = [torch.randn(BATCH, 3, 224, 224, device=dev, generator=gen).bfloat16().float() for _ in range(nbuf)]
     inference.calibrate(model, [images[0][:64]])          # untimed: histograms + fused sweep
+    engines = {}
     if args.conv_backend in ("tcgen05", "fused"):
         from term_quantization_b200 import fused, tr_layer
         model = model.to(memory_format=torch.channels_last)
         images = [im.contiguous(memory_format=torch.channels_last) for im in images]
-        switched, skipped = tr_layer.use_tensor_cores(model)
-        assert len(switched) == 19 and not skipped, (switched, skipped)
+        if args.conv_backend == "tcgen05":
+            switched, skipped = tr_layer.use_tensor_cores(model, engine=args.conv_engine)
+            assert len(switched) == 19 and not skipped, (switched, skipped)
         if args.conv_backend == "fused":
-            model = fused.FusedResNet(model, stem=args.stem)
+            model = fused.FusedResNet(model, stem=args.stem, engine=args.conv_engine)
+            for blk in model.blocks:
+                for c in blk:
+                    if c is not None:
+                        k = f"{c.plan.engine} x{c.plan.groups}" if c.plan.engine == "f16" else f"i8 {c.plan.planes_w}w-plane"
+                        engines[k] = engines.get(k, 0) + 1
     images = [im.to(in_dtype) for im in images]
     use_graphs = args.conv_backend == "fused" and not args.no_cuda_graphs
     runner = inference.ShardedInference(model, dev, cuda_graphs=use_graphs, gather=args.gather)
@@ -347,19 +358,21 @@ def run_b200(args):
     if args.conv_backend in ("tcgen05", "fused"):
         host = [h.contiguous(memory_format=torch.channels_last) for h in host]
     host = [h.to(in_dtype).pin_memory() for h in host]
-    slot = runner.stage(host[0])
+    # three device slots: the copies of shards i+1 and i+2 are in flight while forward i runs
+    s0 = runner.stage(host[0])
+    s1 = runner.stage(host[1])
     for i in range(max(args.warmup, 1)):
-        nxt = runner.stage(host[(i + 1) % 2])
-        runner.run(slot)
-        slot = nxt
+        nxt = runner.stage(host[i % 2])
+        runner.run(s0)
+        s0, s1 = s1, nxt
     runner.finish()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
         nxt = runner.stage(host[i % 2])
-        host_logits = runner.run(slot)
-        slot = nxt
+        host_logits = runner.run(s0)
+        s0, s1 = s1, nxt
     runner.finish()
     e1.record()
     barrier()
@@ -368,6 +381,15 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
     assert bool(torch.isfinite(host_logits).all())
+    # what the box allows: the same host -> device copies alone, all ranks at once (max over ranks)
+    import bench_extra
+    barrier()
+    t = torch.tensor([bench_extra.h2d_ceiling(host, [b for b in runner._stage if b is not None], args.steps, runner.copy_stream)],
+                     dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    h2d_only_ms = float(t.item())
+    barrier()
 
     line = None
     if rank == 0:
@@ -383,18 +405,26 @@ def run_b200(args):
         if n_cv:
             try:
                 with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                    tpeak, tsrc = float(json.load(f)["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained; f16 runs at the bf16 rate)"
+                    pk = json.load(f)
+                # each conv launch is timed alone with CUDA events and the whole pass lasts tens of ms at full clocks:
+                # the applicable ceiling is the BURST figure
+                tpeak, tsrc = float(pk["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst; kind::f16 runs at the bf16 rate)"
+                tsus = float(pk.get("bf16_tflops_sustained", 0)) or None
             except Exception:
-                tpeak, tsrc = 1400.0, "fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)"
+                tpeak, tsrc, tsus = 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s burst)", 1400.0
             tach = cv_flops / (cv_ms * 1e-3) / 1e12
             traffic, traffic_src = ncu_conv_traffic()
-            conv_roof = {"kernel": "tq::conv_igemm_f16_kernel (tcgen05 kind::f16 implicit GEMM on term codes with "
-                                   "fused BN/residual/ReLU/encode epilogue, 19 launches per forward)",
+            conv_roof = {"kernel": "tq::conv_igemm_kernel (tcgen05 implicit GEMM on term codes, exact int32 accumulators, fused "
+                                   "BN/residual/ReLU/encode epilogue, 19 launches per forward)",
                          "bound": "tensor", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s", "frac": tach / tpeak,
+                         "frac_of_sustained": (tach / tsus) if tsus else None,
                          "traffic": traffic, "traffic_source": traffic_src,
-                         "algorithmic_bytes_per_launch": 3.53e9 / 19,
+                         "algorithmic_bytes_per_launch": trt.bytes("conv") / n_cv,
+                         "algorithmic_bytes_model": "per launch, from the launch's own tensor shapes: fp16 codes in + fp16 weight codes "
+                                                    "+ fp32 residual in + fp32 tile out + fp16 codes out, each once",
                          "peak_source": tsrc, "launches_timed": n_cv,
                          "algorithmic_flops": cv_flops, "kernel_ms_total": cv_ms, "share_of_step": cv_ms / ms_instrumented,
+                         "whole_step_TFLOPs": (cv_flops + st_flops) / args.steps / (ms_total / args.steps * 1e-3) / 1e12,
                          "timed": "CUDA events around each launch in an eager pass of the same K steps"}
         dominant, other = (conv_roof, tr_roof) if (conv_roof and cv_ms > tr_ms) else (tr_roof, conv_roof)
         if other is tr_roof and n_tr == 0:
@@ -403,7 +433,8 @@ def run_b200(args):
             "metric": METRIC, "value": BATCH * world * args.steps / (ms_total * 1e-3),
             "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": ("int term codes (TR encode) held in f16, f32 accumulate (exact integers) on tcgen05"
+            "vs_baseline": None, "dtype": ("int term codes (TR encode) -> exact int32 accumulators on tcgen05 (kind::f16 with statically "
+                                       "proven fp32 K-chunk accumulators summed in int32, or kind::i8 planes with s32 accumulators)"
                                        if args.conv_backend != "cudnn_fp32" else "f32 values (TR encode); f32 conv"),
             "data": "synthetic (randn images rounded to bf16, random-init torchvision resnet18, seed 0)",
             "config": {"workload": "ResNet-18 TQ inference, batch 256 per GPU at 3x224x224 "
@@ -412,15 +443,23 @@ def run_b200(args):
                            "step": "every step on the compute stream", "async": "every step on a side stream",
                            "end": "once, after the last step (inside the timed region)"}[args.gather])
                        if world > 1 else "single GPU",
-                       "conv_backend": args.conv_backend, "input_dtype": str(in_dtype).replace("torch.", ""),
+                       "conv_backend": args.conv_backend, "conv_engine": args.conv_engine, "engines_per_layer": engines,
+                       "input_dtype": str(in_dtype).replace("torch.", ""),
                        "cuda_graphs": bool(use_graphs),
                        "numa": (f"rank pinned to the {len(numa_cpus)} CPUs local to its GPU" if numa_cpus else "not pinned"),
                        "l2": "activations per step (2.08 GB fp32 through TR) exceed the 126 MB L2; "
                              "input batches rotate between 2 buffers"},
             "e2e": {"value": BATCH * world * args.steps / (e2e_ms * 1e-3), "unit": "images/s",
-                    "h2d_bytes_per_step": BATCH * 3 * 224 * 224 * host[0].element_size(),
-                    "d2h_bytes_per_step": int(host_logits.numel()) * 4,
-                    "ms_per_step": e2e_ms / args.steps},
+                    "h2d_bytes_per_step": BATCH * 3 * 224 * 224 * host[0].element_size() * world,
+                    "d2h_bytes_per_step": int(host_logits.numel()) * 4 * world,
+                    "ms_per_step": e2e_ms / args.steps,
+                    "note": "bytes are job totals per step (each rank copies its own 256-image shard in and its own "
+                            "logits out; the gathered logits stay on the devices); 3 staging slots per rank",
+                    "h2d_only_ms_per_step": h2d_only_ms,
+                    "h2d_ceiling_gbs": BATCH * 3 * 224 * 224 * host[0].element_size() * world / (h2d_only_ms * 1e-3) / 1e9,
+                    "h2d_ceiling_images_per_s": BATCH * world / (h2d_only_ms * 1e-3),
+                    "h2d_ceiling_note": "the same pinned-host -> device copies with no compute, all ranks at once, max over ranks: "
+                                        "the e2e number cannot exceed this on this box"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             **({"per_rank": per_rank} if per_rank else {}),
@@ -436,6 +475,17 @@ def run_b200(args):
                 "bn_relu_maxpool_encode_GBs": (pl_bytes / (pl_ms * 1e-3) / 1e9) if pl_ms > 0 else None,
                 "tr_elem_standalone": tr_ms / args.steps, "instrumented_step": ms_instrumented / args.steps},
         }
+        if world == 1 and not args.no_extras:
+            # BASELINE.md section 3's grid and the other BASELINE configs, after every headline region; the big buffers of
+            # the headline run are released first
+            del runner, eager, images
+            torch.cuda.empty_cache()
+            grid, beat = bench_extra.tr_grid(dev, peak, with_ref=not args.no_cpu_baseline)
+            line["tr_grid"] = grid
+            line["kernel_to_beat"] = {"what": "the reference's own kernel (kernels/tr_cuda_kernel.cu:58-125, byte-identical body, "
+                                              "recompiled for sm_100a: oracle/_ref/libtq_ref_gpu.so) on the same tensors, same timing",
+                                      "rows": beat} if beat else None
+            line["other_configs"] = bench_extra.other_configs(dev)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_images_per_sec(sample_batch=args.cpu_batch, steps=1)
     if world > 1:
@@ -526,6 +576,10 @@ def main():
     ap.add_argument("--no-cuda-graphs", action="store_true", help="launch the forward kernel by kernel")
     ap.add_argument("--cpu-batch", type=int, default=16, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip tr_grid / kernel_to_beat / other_configs")
+    ap.add_argument("--conv-engine", default="auto", choices=["auto", "f16", "i8"],
+                    help="how the exact accumulator is obtained per layer (conv_codes.plan_weight): auto = kind::f16 where "
+                         "proven from the weights, kind::i8 planes otherwise")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -103,7 +103,7 @@ class ShardedInference:
     copy stream, overlapping the previous step's compute) and the device->host read of the
     gathered logits."""
 
-    def __init__(self, model, device, group=None, cuda_graphs=False, gather="step"):
+    def __init__(self, model, device, group=None, cuda_graphs=False, gather="step", slots=3, d2h="local"):
         """gather: when the logits of the other ranks are collected.
         'step'  -- one all-gather per forward on the compute stream (every rank holds every step's logits before
                    the next forward starts; the ranks re-synchronise on every step);
@@ -113,6 +113,13 @@ class ShardedInference:
                    final NCCL gather of logits")."""
         if gather not in ("step", "async", "end"):
             raise ValueError("gather must be 'step', 'async' or 'end'")
+        if d2h not in ("local", "gathered"):
+            raise ValueError("d2h must be 'local' or 'gathered'")
+        # what `run()` reads back to the host: this rank's own logits (every rank returns its shard's results to its
+        # caller; the gathered tensor stays on the device for whoever consumes all of them) or the gathered logits of
+        # the whole job on EVERY rank (world x the bytes, all through the same host)
+        self.d2h = d2h
+        self._last_local = None
         self.gather = gather
         self._side = None
         self._gathered = [None, None]
@@ -126,8 +133,10 @@ class ShardedInference:
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self.copy_stream = torch.cuda.Stream(device=self.device)
-        self._stage = [None, None]
-        self._stage_evt = [None, None]
+        self.slots = max(2, int(slots))
+        self._stage = [None] * self.slots
+        self._stage_evt = [None] * self.slots
+        self._done_evt = [None] * self.slots                    # recorded after the forward that read the slot
         self._slot = 0
         self._host_out = None
 
@@ -157,6 +166,7 @@ class ShardedInference:
     @torch.no_grad()
     def forward(self, images_dev):
         local = self._local_forward(images_dev)
+        self._last_local = local
         if self.world == 1 or self.gather == "step":
             return gather_logits(local, self.group)
         if self.gather == "end":
@@ -194,15 +204,18 @@ class ShardedInference:
 
     def stage(self, pinned):
         """Start the host->device copy of a pinned shard on the copy stream; returns the slot.
-        Two slots: stage shard i+1, then run(shard i), and the copy overlaps the compute."""
+        `slots` device buffers rotate: stage shards i+1 (and i+2), then run(shard i), and the copies overlap the
+        compute; a slot is rewritten only after the forward that read it has been enqueued."""
         s = self._slot
-        self._slot ^= 1
+        self._slot = (s + 1) % self.slots
         if self._stage[s] is None or self._stage[s].shape != pinned.shape or \
                 self._stage[s].stride() != pinned.stride():
             # same strides as the host tensor (e.g. channels_last): the copy is one plain DMA
             self._stage[s] = torch.empty_like(pinned, device=self.device)
-        # the slot may still be read by the forward enqueued two steps ago
-        self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+        # the slot may still be read by the forward that last used it: wait for THAT forward only, so that the copy
+        # of shard i+2 can run while forward i is still on the device
+        if self._done_evt[s] is not None:
+            self.copy_stream.wait_event(self._done_evt[s])
         with torch.cuda.stream(self.copy_stream):
             self._stage[s].copy_(pinned, non_blocking=True)
             evt = torch.cuda.Event()
@@ -216,9 +229,14 @@ class ShardedInference:
         returns the pinned host tensor (valid after the current stream is synchronised)."""
         torch.cuda.current_stream(self.device).wait_event(self._stage_evt[slot])
         logits = self.forward(self._stage[slot])
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(self.device))
+        self._done_evt[slot] = done
+        if self.d2h == "local":
+            logits = self._last_local                            # this rank's shard; the gathered tensor stays on the device
         if self._host_out is None or self._host_out.shape != logits.shape:
             self._host_out = torch.empty(logits.shape, dtype=logits.dtype, pin_memory=True)
-        if self.gather == "async" and self.world > 1:
+        if self.d2h == "gathered" and self.gather == "async" and self.world > 1:
             with torch.cuda.stream(self._side):                 # behind the gather it reads
                 self._host_out.copy_(logits, non_blocking=True)
         else:
