@@ -149,11 +149,12 @@ def test_models_build_on_cpu():
 
 def test_bench_line_contract_on_committed_profile():
     """The bench line committed under profiles/ (written by bench.py on a B200) carries every key of the driver's
-    contract, and bench.py's ncu-traffic parser reads the committed launch list."""
+    contract plus this round's grid / baselines, and the ncu-traffic reader refuses a capture taken from another
+    version of the kernel source."""
     import json
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    d = json.load(open(os.path.join(root, "profiles", "r01_bench_final_n1.json")))
+    d = json.load(open(os.path.join(root, "profiles", "r02_bench_n1_first.json")))
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
         assert key in d, key
@@ -167,9 +168,12 @@ def test_bench_line_contract_on_committed_profile():
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     c = d["cpu_baseline"]
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(c) and c["kind"] in ("reference", "port")
+    assert len(d["tr_grid"]) >= 12 and all(set(("case", "elements", "GBs_best", "frac_of_nominal_8000")) <= set(r) for r in d["tr_grid"])
+    assert d["kernel_to_beat"]["rows"] and set(d["other_configs"]) == {"vgg16_bn_b128", "mobilenet_v2_b512", "mlp_b256", "lstm_35x80"}
+    assert d["e2e"]["h2d_ceiling_gbs"] > 0
     import bench
     traffic, src = bench.ncu_conv_traffic()
-    assert traffic is not None and traffic > 1e7 and src.endswith(".csv")
+    assert traffic is None or traffic > 1e7           # None unless profiles/r02_conv_traffic.json matches csrc/tq_gemm.cu
 
 
 def test_pybind_adapter_loads_and_keeps_the_reference_checks():
