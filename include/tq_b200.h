@@ -168,7 +168,8 @@ int tq_conv2d_codes_f16(const void *act, const void *wgt, const float *bias, flo
  * pipeline order: accumulate -> ReLU/requantise -> encode -> truncate; tr_layer.py:124-126 plus the
  * BatchNorm / residual / ReLU that follow a conv in the CNNs of cnn_models/):
  *     t = float(acc) * scale (+ bias[co]);  t = fma(t, bn_a[co], bn_b[co]);  t += residual[n,ho,wo,co];
- *     t = max(t, 0) if relu;  out_f32 = t;  out_codes = term code of t under the consumer's quantiser
+ *     t = max(t, 0) if relu (relu = 2: ReLU6, t = min(max(t, 0), 6));  out_f32 = t;
+ *     out_codes = term code of t under the consumer's quantiser
  *     (next_sf, next_bits <= 10, next_terms; g = 1, HESE) stored as fp16 NHWC.
  * Every step is optional (NULL pointer / relu = 0); at least one of out_f32, out_codes is given.
  * Every step is one IEEE fp32 operation in this order, so the result is reproducible bit for bit on a CPU
@@ -251,6 +252,29 @@ int tq_stem_conv7x7s2_pool(const void *x, int x_dtype, void *x2_scratch, const v
                            const float *bn_a, const float *bn_b, int relu, float *out, void *out_codes,
                            int N, int H, int W, int Cout, float next_sf, int next_bits, int next_terms,
                            void *stream);
+
+/*
+ * Depthwise 3x3 conv (pad 1, stride 1 or 2) on term codes, the memory-bound layer of the depthwise CNNs
+ * (BASELINE.json configs[3]; wrapped by the reference with the (16, 1, 16) weight setting, cnn_models/__init__.py:52-65,
+ * and run as TR encode -> cuDNN fp32 conv -> BatchNorm -> ReLU6, tr_layer.py:124-126):
+ *     acc[n,ho,wo,c] = sum_{r,s} act[n, ho*stride+r-1, wo*stride+s-1, c] * wgt[r*3+s, c]        (int32, exact)
+ *     t = float(acc) * scale (+ bias[c]);  t = fma(t, bn_a[c], bn_b[c]);  relu: 0 none, 1 ReLU, 2 ReLU6;
+ *     out_f32 = t and / or out_codes = fp16 term code of t under (next_sf, next_bits <= 11, next_terms), g = 1, HESE.
+ * act fp16 NHWC [N,H,W,C] integer codes, wgt int32 [9][C] integer codes (|a| <= 2^11, |w| <= 2^16), C % 8 == 0.
+ * Algorithmic bytes: 2 B read + 2 B (codes) / 4 B (fp32) written per element.
+ */
+int tq_depthwise3x3_codes(const void *act_codes, const int32_t *wgt_codes, float *out_f32, void *out_codes,
+                          const float *bias, const float *bn_a, const float *bn_b, int N, int H, int W, int C,
+                          int stride, float scale, int relu, float next_sf, int next_bits, int next_terms,
+                          void *stream);
+
+/*
+ * Tail of an unwrapped conv (the first conv of every CNN, cnn_models/__init__.py:34-36) fused with the first wrapped
+ * layer's LinearQuantize (tr_layer.py:96-99): x fp32 [npix][C] -> fma(x, bn_a, bn_b) -> activation (relu as above) ->
+ * out_f32 and / or fp16 term codes.  C % 4 == 0.
+ */
+int tq_bn_act_encode(const float *x, const float *bn_a, const float *bn_b, float *out_f32, void *out_codes,
+                     int64_t npix, int C, int relu, float next_sf, int next_bits, int next_terms, void *stream);
 
 /*
  * Device self-test: quantises n pseudo-random (a, sf) pairs (sf in [2^-30, 2^30], a over all

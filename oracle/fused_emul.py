@@ -68,3 +68,66 @@ def run_resnet_chain(blocks, stem_out):
         _, mid = fused_conv(encode(cur, c1["quant"]), c1, relu=True, next_quant=c2["quant"])
         cur, _ = fused_conv(mid, c2, residual=identity, relu=True)
     return cur
+
+
+def _act(t, relu):
+    if relu:
+        t = np.maximum(t, np.float32(0.0))
+    if relu in ("relu6", 2):
+        t = np.minimum(t, np.float32(6.0))
+    return t
+
+
+def fused_conv_act(codes_nhwc, conv, residual=None, relu=False, next_quant=None):
+    """fused_conv with the activation given as False / True / 'relu6' (the depthwise CNNs clamp at 6)."""
+    acc = conv_exact(codes_nhwc, conv["w"], conv["ks"], conv["stride"], conv["pad"])
+    t = acc.astype(np.float32) * np.float32(conv["scale"])
+    if conv.get("bias") is not None:
+        t = t + np.asarray(conv["bias"], dtype=np.float32)
+    if conv.get("bn") is not None:
+        t = O.fma_channels(t, conv["bn"][0], conv["bn"][1])
+    if residual is not None:
+        t = t + np.asarray(residual, dtype=np.float32)
+    t = np.ascontiguousarray(_act(t, relu), dtype=np.float32)
+    return t, (encode(t, next_quant) if next_quant is not None else None)
+
+
+def depthwise_exact(codes_nhwc, w9c, stride):
+    """Exact depthwise 3x3 / pad 1 conv: int codes [N,H,W,C] x int [9, C] -> float64 [N,Ho,Wo,C] holding integers."""
+    C = w9c.shape[1]
+    w = torch.from_numpy(np.asarray(w9c, dtype=np.float64)).t().contiguous().view(C, 1, 3, 3)
+    a = torch.from_numpy(np.asarray(codes_nhwc, dtype=np.float64)).permute(0, 3, 1, 2).contiguous()
+    acc = F.conv2d(a, w, None, stride, 1, 1, C).permute(0, 2, 3, 1).contiguous().numpy()
+    assert float(np.abs(acc).max(initial=0.0)) < 2.0 ** 31
+    return acc
+
+
+def fused_depthwise(codes_nhwc, dw, relu=False, next_quant=None):
+    """tq_depthwise3x3_codes on the CPU: exact int32 accumulator -> fl32 * scale (+ bias) -> fmaf BN -> activation."""
+    acc = depthwise_exact(codes_nhwc, dw["w"], dw["stride"])
+    t = acc.astype(np.float32) * np.float32(dw["scale"])
+    if dw.get("bias") is not None:
+        t = t + np.asarray(dw["bias"], dtype=np.float32)
+    if dw.get("bn") is not None:
+        t = O.fma_channels(t, dw["bn"][0], dw["bn"][1])
+    t = np.ascontiguousarray(_act(t, relu), dtype=np.float32)
+    return t, (encode(t, next_quant) if next_quant is not None else None)
+
+
+def run_mobilenet_chain(desc, stem_codes):
+    """desc = fused.FusedMobileNet.chain_description(); stem_codes: int codes [N,H,W,C] reaching the first block (the
+    unwrapped stem conv + BN + ReLU6 + first encode are outside the chain).  Returns the fp32 output of the last 1x1
+    conv (+ BN + ReLU6), i.e. the tensor the average pool reads."""
+    codes = np.asarray(stem_codes).astype(np.int32)
+    cur = None
+    blocks = desc["blocks"]
+    for i, (expand, dw, proj, use_res) in enumerate(blocks):
+        h = codes
+        if expand is not None:
+            _, h = fused_conv_act(h, expand, relu="relu6", next_quant=dw["quant"])
+        _, h = fused_depthwise(h, dw, relu="relu6", next_quant=proj["quant"])
+        nxt = blocks[i + 1] if i + 1 < len(blocks) else None
+        nq = (nxt[0] or nxt[1])["quant"] if nxt is not None else desc["last"]["quant"]
+        cur, codes = fused_conv_act(h, proj, residual=cur if use_res else None, relu=False, next_quant=nq)
+    out, _ = fused_conv_act(codes, desc["last"], relu="relu6")
+    return out

@@ -27,6 +27,13 @@ def pack_conv_weight(w, w_sf, weight_bits, group_size, num_terms):
 EXACT_LIMIT = 1 << 24
 
 
+def _relu_code(relu):
+    """Activation of the fused epilogues: False / 0 none, True / 1 ReLU, 'relu6' / 2 ReLU6."""
+    if relu in ("relu6", 2):
+        return 2
+    return 1 if relu else 0
+
+
 class WeightPlan:
     """How one packed weight [R*S, Cout, C] runs exactly: engine 'f16' with `groups` K chunks, or 'i8' with the
     signed 8-bit planes of the weight codes.  Built once per weight by `plan_weight`."""
@@ -135,7 +142,7 @@ def _run_conv(act, plan, out, codes, bias, bn, residual, N, H, W, C, Cout, R, S,
             rc = L.tq_conv2d_codes_fused(
                 act.data_ptr(), plan.wgt.data_ptr(), ptr(out), ptr(codes), ptr(bias),
                 ptr(bn[0]) if bn else None, ptr(bn[1]) if bn else None, ptr(residual),
-                N, H, W, C, Cout, R, S, stride, pad, float(scale), int(bool(relu)), float(sf), int(bits),
+                N, H, W, C, Cout, R, S, stride, pad, float(scale), _relu_code(relu), float(sf), int(bits),
                 int(terms), int(plan.groups), stream)
         else:
             if act_planes is None:
@@ -144,7 +151,7 @@ def _run_conv(act, plan, out, codes, bias, bn, residual, N, H, W, C, Cout, R, S,
             rc = L.tq_conv2d_planes_i8(
                 act_planes.data_ptr(), plan.planes.data_ptr(), act_planes.shape[0], plan.planes_w, ptr(out), ptr(codes),
                 ptr(bias), ptr(bn[0]) if bn else None, ptr(bn[1]) if bn else None, ptr(residual),
-                N, H, W, C, Cout, R, S, stride, pad, float(scale), int(bool(relu)), float(sf), int(bits), int(terms),
+                N, H, W, C, Cout, R, S, stride, pad, float(scale), _relu_code(relu), float(sf), int(bits), int(terms),
                 int(plan.act_max), int(plan.wgt_max), stream)
     _lib.check(rc)
 
@@ -197,6 +204,57 @@ def conv2d_codes_fused(act, wgt, kernel_size, stride, pad, scale, *, bias=None, 
     if plan is None:
         plan = _cached_plan(wgt, act_max, signed_act, engine)
     _run_conv(act, plan, out, codes, bias, bn, residual, N, H, W, C, Cout, R, S, stride, pad, scale, relu, sf, bits, terms)
+    return out, codes
+
+
+def pack_depthwise_weight(w, w_sf):
+    """Term-revealed depthwise weight (C, 1, 3, 3) fp32 (already an integer multiple of w_sf) -> int32 [9, C] codes."""
+    if w.dim() != 4 or w.shape[1] != 1 or tuple(w.shape[2:]) != (3, 3):
+        raise NotImplementedError("depthwise packing expects a (C, 1, 3, 3) weight")
+    sf32 = torch.tensor(w_sf, dtype=torch.float32).item()
+    codes = torch.round(w.detach() / sf32)
+    if not torch.equal(codes * sf32, w.detach()):
+        raise RuntimeError("depthwise weight is not an integer multiple of w_sf any more")
+    return codes.view(w.shape[0], 9).t().contiguous().to(torch.int32), sf32
+
+
+def depthwise3x3_codes(act, wgt, stride, scale, *, bias=None, bn=None, relu=False, want_f32=False, next_quant=None):
+    """Depthwise 3x3 / pad 1 conv on fp16 codes [N, H, W, C] with int32 weight codes [9, C]: exact int32 accumulator,
+    then the fused tail (tq_depthwise3x3_codes).  Returns (out_f32 or None, out_codes or None)."""
+    if act.dtype != torch.float16 or not act.is_contiguous() or wgt.dtype != torch.int32 or not wgt.is_contiguous():
+        raise RuntimeError("depthwise3x3_codes expects contiguous fp16 NHWC codes and int32 [9, C] weights")
+    N, H, W, C = act.shape
+    if tuple(wgt.shape) != (9, C):
+        raise RuntimeError("weight / activation shape mismatch")
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    out = torch.empty((N, Ho, Wo, C), dtype=torch.float32, device=act.device) if want_f32 else None
+    codes = torch.empty((N, Ho, Wo, C), dtype=torch.float16, device=act.device) if next_quant else None
+    sf, bits, terms = next_quant if next_quant else (1.0, 1, 0)
+    ptr = lambda t: t.data_ptr() if t is not None else None   # noqa: E731
+    with torch.cuda.device(act.device):
+        rc = _lib.lib().tq_depthwise3x3_codes(
+            act.data_ptr(), wgt.data_ptr(), ptr(out), ptr(codes), ptr(bias), ptr(bn[0]) if bn else None,
+            ptr(bn[1]) if bn else None, N, H, W, C, stride, float(scale), _relu_code(relu), float(sf), int(bits), int(terms),
+            torch.cuda.current_stream(act.device).cuda_stream)
+    _lib.check(rc)
+    return out, codes
+
+
+def bn_act_encode(x_nhwc, bn=None, relu=False, want_f32=False, next_quant=None):
+    """fp32 [..., C] -> fma(x, a, b) -> activation -> fp32 and / or fp16 term codes (tq_bn_act_encode)."""
+    if x_nhwc.dtype != torch.float32 or not x_nhwc.is_contiguous() or not x_nhwc.is_cuda:
+        raise RuntimeError("bn_act_encode expects a contiguous fp32 CUDA tensor with channels last")
+    C = x_nhwc.shape[-1]
+    out = torch.empty_like(x_nhwc) if want_f32 else None
+    codes = torch.empty(x_nhwc.shape, dtype=torch.float16, device=x_nhwc.device) if next_quant else None
+    sf, bits, terms = next_quant if next_quant else (1.0, 1, 0)
+    ptr = lambda t: t.data_ptr() if t is not None else None   # noqa: E731
+    with torch.cuda.device(x_nhwc.device):
+        rc = _lib.lib().tq_bn_act_encode(
+            x_nhwc.data_ptr(), ptr(bn[0]) if bn else None, ptr(bn[1]) if bn else None, ptr(out), ptr(codes),
+            x_nhwc.numel() // C, C, _relu_code(relu), float(sf), int(bits), int(terms),
+            torch.cuda.current_stream(x_nhwc.device).cuda_stream)
+    _lib.check(rc)
     return out, codes
 
 

@@ -90,7 +90,7 @@ struct ConvGeom {
     // fused epilogue (all optional):  t = acc*scale (+bias) ; t = fma(t, bn_a, bn_b) ; t += residual ;
     // t = max(t, 0) ; fp32 tile out (TMA store) ; fp16 term codes of t for the next layer (TMA store)
     const float *bias, *bn_a, *bn_b, *residual;
-    int relu, write_f32, write_codes;
+    int relu, relu6, write_f32, write_codes;    // relu6: additionally clamp at 6 (ReLU6 of the depthwise CNNs)
     float next_sf;
     int next_bits, next_terms, next_fastdiv;
 };
@@ -286,6 +286,10 @@ __device__ __forceinline__ void epi_stage(float (&t)[32], const ConvGeom &g, uin
         if (RELU) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) t[j + e] = fmaxf(t[j + e], 0.0f);
+            if (g.relu6) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) t[j + e] = fminf(t[j + e], 6.0f);
+            }
         }
         if (wf) *slot = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
         if (wc) {
@@ -1127,6 +1131,7 @@ static int plan_conv(const ConvArgs &a, ConvPlan &pl)
     g.bias = (const float *)a.bias; g.bn_a = (const float *)a.bn_a; g.bn_b = (const float *)a.bn_b;
     g.residual = (const float *)a.residual;
     g.relu = a.relu ? 1 : 0;
+    g.relu6 = a.relu == 2 ? 1 : 0;
     g.write_f32 = a.out_f32 ? 1 : 0;
     g.write_codes = a.out_codes ? 1 : 0;
     g.next_sf = a.out_codes ? a.next_sf : 1.0f;
@@ -1281,7 +1286,7 @@ extern "C" int tq_conv2d_codes_fused(const void *act, const void *wgt, float *ou
     a.act = act; a.wgt = wgt; a.out_f32 = out_f32; a.out_codes = out_codes; a.bias = bias; a.bn_a = bn_a; a.bn_b = bn_b;
     a.residual = residual;
     a.kind = 0; a.N = N; a.H = H; a.W = W; a.C = C; a.Cout = Cout; a.R = R; a.S = S; a.stride = stride; a.pad = pad;
-    a.relu = relu ? 1 : 0; a.next_bits = out_codes ? next_bits : 1; a.next_terms = next_terms;
+    a.relu = relu == 2 ? 2 : (relu ? 1 : 0); a.next_bits = out_codes ? next_bits : 1; a.next_terms = next_terms;
     a.acc_groups = acc_groups < 1 ? 1 : acc_groups; a.planes_a = 1; a.planes_w = 1;
     a.scale = scale; a.next_sf = out_codes ? next_sf : 1.0f;
     return run_conv(a, (cudaStream_t)stream);
@@ -1318,7 +1323,7 @@ extern "C" int tq_conv2d_planes_i8(const void *act_planes, const void *wgt_plane
     a.act = act_planes; a.wgt = wgt_planes; a.out_f32 = out_f32; a.out_codes = out_codes; a.bias = bias; a.bn_a = bn_a;
     a.bn_b = bn_b; a.residual = residual;
     a.kind = 1; a.N = N; a.H = H; a.W = W; a.C = C; a.Cout = Cout; a.R = R; a.S = S; a.stride = stride; a.pad = pad;
-    a.relu = relu ? 1 : 0; a.next_bits = out_codes ? next_bits : 1; a.next_terms = next_terms;
+    a.relu = relu == 2 ? 2 : (relu ? 1 : 0); a.next_bits = out_codes ? next_bits : 1; a.next_terms = next_terms;
     a.acc_groups = 1; a.planes_a = planes_a; a.planes_w = planes_w;
     a.scale = scale; a.next_sf = out_codes ? next_sf : 1.0f;
     return run_conv(a, (cudaStream_t)stream);

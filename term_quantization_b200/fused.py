@@ -269,3 +269,110 @@ class FusedVGG(nn.Module):
                     out = t.contiguous()
         y = out.permute(0, 3, 1, 2)
         return m.classifier(torch.flatten(m.avgpool(y), 1))
+
+
+class _Depthwise:
+    """Packed operands of a wrapped depthwise 3x3 conv (the reference's (16, 1, 16) setting) + its BatchNorm."""
+
+    def __init__(self, layer, bn):
+        c = layer.conv
+        if not (c.groups == c.in_channels == c.out_channels and c.kernel_size == (3, 3) and c.padding == (1, 1)
+                and c.stride in ((1, 1), (2, 2)) and c.dilation == (1, 1) and c.in_channels % 8 == 0):
+            raise NotImplementedError("fused depthwise path: 3x3 / pad 1 / stride 1 or 2 depthwise convs with C % 8 == 0")
+        if layer.input_quant.tracking:
+            raise RuntimeError("calibrate the model (set_tr_tracking(model, False)) before fusing")
+        if layer.data_bits > 11 or layer.weight_bits > 16:
+            raise NotImplementedError("fused depthwise path: int32 accumulator needs data_bits <= 11, weight_bits <= 16")
+        self.layer = layer
+        self.w, wsf32 = conv_codes.pack_depthwise_weight(c.weight, layer.w_sf)
+        self.quant = _quant_key(layer)
+        self.scale = (torch.tensor(self.quant[0], dtype=torch.float32) * torch.tensor(wsf32, dtype=torch.float32)).item()
+        self.bias = c.bias
+        self.bn = _bn_affine(bn) if bn is not None else None
+        self.stride = c.stride[0]
+
+    def __call__(self, codes, relu=False, want_f32=False, next_quant=None):
+        return conv_codes.depthwise3x3_codes(codes, self.w, self.stride, self.scale, bias=self.bias, bn=self.bn, relu=relu,
+                                             want_f32=want_f32, next_quant=next_quant)
+
+
+class FusedMobileNet(nn.Module):
+    """Fused execution of a TQ-converted torchvision MobileNet-V2 (BASELINE.json configs[3]).
+
+    Per InvertedResidual block: the 1x1 expand and project convs run on the tcgen05 kernel (BatchNorm, ReLU6, residual
+    add and the NEXT layer's term encode in the epilogue) and the depthwise 3x3 conv -- the memory-bound layer -- is one
+    kernel from fp16 codes to fp16 codes (tq_depthwise3x3_codes: int32 accumulator, BatchNorm, ReLU6, encode).  The only
+    fp32 activations that reach HBM are the block outputs a later residual add needs.  The reference runs every one of
+    these layers as TR encode -> cuDNN conv -> BatchNorm -> ReLU6 over fp32 tensors (tr_layer.py:124-126).  The first
+    conv (never wrapped, cnn_models/__init__.py:34-36) stays on cuDNN fp32; its BatchNorm + ReLU6 + first encode are one
+    pass (tq_bn_act_encode).  Average pool and classifier stay on PyTorch."""
+
+    def __init__(self, model, engine="auto"):
+        super().__init__()
+        from torchvision.models.mobilenetv2 import InvertedResidual
+        self.model = model.to(memory_format=torch.channels_last).eval()
+        feats = list(model.features.children())
+        stem = list(feats[0].children())
+        if not (isinstance(stem[0], nn.Conv2d) and not isinstance(stem[0], tr_layer.TRConv2dLayer)
+                and isinstance(stem[1], nn.BatchNorm2d) and isinstance(stem[2], nn.ReLU6)):
+            raise NotImplementedError("FusedMobileNet expects an unwrapped conv-BN-ReLU6 stem")
+        self.stem_conv, self.stem_bn = stem[0], _bn_affine(stem[1])
+        self.blocks = []                                    # (expand | None, depthwise, project, use_res)
+        post_relu = True                                    # the stem ends in ReLU6
+        for blk in feats[1:-1]:
+            if not isinstance(blk, InvertedResidual):
+                raise NotImplementedError("FusedMobileNet expects InvertedResidual blocks")
+            mods = list(blk.conv.children())
+            expand = None
+            if len(mods) == 4:                              # Conv2dNormActivation(expand), Conv2dNormActivation(dw), conv, bn
+                e = list(mods[0].children())
+                expand = _Conv(e[0], e[1], post_relu=post_relu, engine=engine)
+                mods = mods[1:]
+            d = list(mods[0].children())
+            dw = _Depthwise(d[0], d[1])
+            proj = _Conv(mods[1], mods[2], post_relu=True, engine=engine)      # its input is the depthwise ReLU6 output
+            self.blocks.append((expand, dw, proj, blk.use_res_connect))
+            post_relu = False                               # block outputs are linear (no activation after the projection)
+        last = list(feats[-1].children())
+        self.last = _Conv(last[0], last[1], post_relu=False, engine=engine)
+
+    def chain_description(self):
+        """Plain data for oracle/fused_emul.run_mobilenet_chain."""
+        def conv(c):
+            if c is None:
+                return None
+            return {"w": c.w.cpu().numpy().astype("int32"), "ks": tuple(c.ks), "stride": c.stride, "pad": c.pad,
+                    "scale": c.scale, "bias": None if c.bias is None else c.bias.detach().float().cpu().numpy(),
+                    "bn": None if c.bn is None else (c.bn[0].cpu().numpy(), c.bn[1].cpu().numpy()),
+                    "quant": c.quant, "engine": c.plan.engine, "groups": c.plan.groups}
+
+        def dwd(d):
+            return {"w": d.w.cpu().numpy(), "stride": d.stride, "scale": d.scale,
+                    "bias": None if d.bias is None else d.bias.detach().float().cpu().numpy(),
+                    "bn": None if d.bn is None else (d.bn[0].cpu().numpy(), d.bn[1].cpu().numpy()), "quant": d.quant}
+        return {"blocks": [(conv(e), dwd(d), conv(p), bool(r)) for e, d, p, r in self.blocks], "last": conv(self.last)}
+
+    @torch.no_grad()
+    def forward(self, x, capture=None):
+        m = self.model
+        x = x.contiguous(memory_format=torch.channels_last)
+        y = self.stem_conv(x.float()).permute(0, 2, 3, 1)                       # fp32 NHWC (channels_last memory)
+        first = self.blocks[0][0] or self.blocks[0][1]
+        _, codes = conv_codes.bn_act_encode(y.contiguous(), self.stem_bn, relu="relu6", next_quant=first.quant)
+        if capture is not None:
+            capture["stem_codes"] = codes
+        cur = None                                                              # fp32 block output, when a residual needs it
+        for i, (expand, dw, proj, use_res) in enumerate(self.blocks):
+            h = codes
+            if expand is not None:
+                _, h = expand(h, relu="relu6", want_f32=False, next_quant=dw.quant)
+            _, h = dw(h, relu="relu6", next_quant=proj.quant)
+            nxt = self.blocks[i + 1] if i + 1 < len(self.blocks) else None
+            nq = ((nxt[0] or nxt[1]).quant if nxt is not None else self.last.quant)
+            need_f32 = nxt is not None and nxt[3]                               # the next block adds this output back
+            cur, codes = proj(h, residual=cur if use_res else None, relu=False, want_f32=need_f32, next_quant=nq)
+        out, _ = self.last(codes, relu="relu6", want_f32=True)
+        if capture is not None:
+            capture["final"] = out
+        y = out.permute(0, 3, 1, 2)
+        return m.classifier(torch.flatten(nn.functional.adaptive_avg_pool2d(y, (1, 1)), 1))

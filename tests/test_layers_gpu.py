@@ -325,6 +325,66 @@ def test_fused_resnet18_bit_exact_against_cpu_emulation(engine):
     assert rel < 1e-5
 
 
+def test_depthwise_and_bn_act_kernels_against_cpu_emulation():
+    """tq_depthwise3x3_codes / tq_bn_act_encode (the memory-bound layers of the depthwise CNNs) bit for bit against
+    the CPU emulation: exact int32 accumulator, fl32 * scale, fmaf BN, ReLU / ReLU6, oracle.tr codes."""
+    from oracle import fused_emul
+    from term_quantization_b200 import conv_codes
+    g = torch.Generator(device="cuda").manual_seed(12)
+    for (N, H, W, C, stride, relu) in ((2, 14, 14, 96, 1, "relu6"), (3, 17, 9, 32, 2, True), (1, 7, 7, 960, 1, "relu6"),
+                                       (2, 112, 112, 32, 1, "relu6"), (2, 5, 4, 8, 2, False), (1, 56, 57, 144, 2, "relu6")):
+        act = (torch.randint(0, 513, (N, H, W, C), device="cuda", generator=g) *
+               (torch.rand(N, H, W, C, device="cuda", generator=g) < 0.6)).half()
+        if not relu:
+            act = act * (torch.randint(0, 2, (N, H, W, C), device="cuda", generator=g) * 2 - 1).half()
+        w = torch.randint(-32768, 32769, (9, C), device="cuda", generator=g, dtype=torch.int32)
+        a = torch.rand(C, device="cuda", generator=g) + 0.5
+        b = torch.randn(C, device="cuda", generator=g)
+        scale = float(np.float32(2.3e-8))
+        dw = {"w": w.cpu().numpy(), "stride": stride, "scale": scale, "bias": None, "bn": (a.cpu().numpy(), b.cpu().numpy())}
+        t_ref, _ = fused_emul.fused_depthwise(act.cpu().numpy().astype(np.int32), dw, relu=relu)
+        nq = (max(float(np.abs(t_ref).max()), 1e-3) / 512, 9, 3)
+        t_ref, c_ref = fused_emul.fused_depthwise(act.cpu().numpy().astype(np.int32), dw, relu=relu, next_quant=nq)
+        out, codes = conv_codes.depthwise3x3_codes(act, w, stride, scale, bn=(a, b), relu=relu, want_f32=True, next_quant=nq)
+        assert np.array_equal(out.cpu().numpy(), t_ref), (N, H, W, C, stride)
+        assert np.array_equal(codes.cpu().numpy().astype(np.int32), c_ref), (N, H, W, C, stride)
+        none, codes2 = conv_codes.depthwise3x3_codes(act, w, stride, scale, bn=(a, b), relu=relu, next_quant=nq)
+        assert none is None and torch.equal(codes2, codes)
+        # bn_act_encode on the fp32 tensor
+        x = torch.randn(N, H, W, C, device="cuda", generator=g) * 3
+        want = fused_emul._act(O.fma_channels(x.cpu().numpy(), a.cpu().numpy(), b.cpu().numpy()), relu)
+        o2, c2 = conv_codes.bn_act_encode(x, (a, b), relu=relu, want_f32=True, next_quant=nq)
+        assert np.array_equal(o2.cpu().numpy(), want)
+        assert np.array_equal(c2.cpu().numpy().astype(np.int32), fused_emul.encode(want, nq))
+
+
+def test_fused_mobilenet_v2_bit_exact_against_cpu_emulation():
+    """BASELINE configs[3]: fused.FusedMobileNet (1x1 convs on tcgen05 with BN / ReLU6 / residual / next encode in the
+    epilogue, depthwise convs code-to-code) -- the tensor the average pool reads must EQUAL the CPU emulation of the
+    chain bit for bit; the logits stay close to the reference's float path (cuDNN fp32, re-quantised 52 times)."""
+    import torchvision
+    from oracle import fused_emul
+    from term_quantization_b200 import cnn_models, fused, inference
+    torch.manual_seed(0)
+    base = torchvision.models.mobilenet_v2(weights=None).cuda().eval()
+    _randomise_bn(base, seed=5)
+    q = cnn_models.convert_model(base, cnn_models.static_conv_layer_settings(base, 9, 8, 12), 9, 3)
+    x = torch.randn(4, 3, 96, 128, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+    inference.calibrate(q, [x])
+    with torch.no_grad():
+        ref = q(x)
+        f = fused.FusedMobileNet(q)
+        cap = {}
+        got = f(x, capture=cap)
+    emu = fused_emul.run_mobilenet_chain(f.chain_description(), cap["stem_codes"].cpu().numpy())
+    final = cap["final"].cpu().numpy()
+    assert final.shape == emu.shape
+    assert np.array_equal(final, emu), f"{int((final != emu).sum())} of {emu.size} differ"
+    rel = float((got - ref).abs().max()) / float(ref.abs().max())
+    print(f"mobilenet_v2 fused vs float path: {rel:.2e}")
+    assert got.shape == ref.shape and rel < 5e-2
+
+
 @pytest.mark.parametrize("arch,size,expect_grouped", [("vgg16_bn", 64, 0), ("mobilenet_v2", 96, 17)])
 def test_other_cnn_configs_layer_by_layer_on_tensor_cores(arch, size, expect_grouped):
     """BASELINE configs[2] / [3]: every wrapped conv of VGG-16-bn and MobileNet-V2 (random init, reference
