@@ -261,12 +261,14 @@ int tq_stem_conv7x7s2_pool(const void *x, int x_dtype, void *x2_scratch, const v
  *     t = float(acc) * scale (+ bias[c]);  t = fma(t, bn_a[c], bn_b[c]);  relu: 0 none, 1 ReLU, 2 ReLU6;
  *     out_f32 = t and / or out_codes = fp16 term code of t under (next_sf, next_bits <= 11, next_terms), g = 1, HESE.
  * act fp16 NHWC [N,H,W,C] integer codes, wgt int32 [9][C] integer codes (|a| <= 2^11, |w| <= 2^16), C % 8 == 0.
- * Algorithmic bytes: 2 B read + 2 B (codes) / 4 B (fp32) written per element.
+ * act_unsigned != 0: the caller guarantees 0 <= act <= 1023 (the output of a ReLU under a quantiser of <= 9 bits), which
+ * lets the kernel extract the integers without conversion instructions.  Input tiles (with their zero halo) are staged
+ * into shared memory by TMA.  Algorithmic bytes: 2 B read + 2 B (codes) / 4 B (fp32) written per element.
  */
 int tq_depthwise3x3_codes(const void *act_codes, const int32_t *wgt_codes, float *out_f32, void *out_codes,
                           const float *bias, const float *bn_a, const float *bn_b, int N, int H, int W, int C,
-                          int stride, float scale, int relu, float next_sf, int next_bits, int next_terms,
-                          void *stream);
+                          int stride, float scale, int relu, int act_unsigned, float next_sf, int next_bits,
+                          int next_terms, void *stream);
 
 /*
  * Tail of an unwrapped conv (the first conv of every CNN, cnn_models/__init__.py:34-36) fused with the first wrapped

@@ -218,9 +218,11 @@ def pack_depthwise_weight(w, w_sf):
     return codes.view(w.shape[0], 9).t().contiguous().to(torch.int32), sf32
 
 
-def depthwise3x3_codes(act, wgt, stride, scale, *, bias=None, bn=None, relu=False, want_f32=False, next_quant=None):
+def depthwise3x3_codes(act, wgt, stride, scale, *, bias=None, bn=None, relu=False, want_f32=False, next_quant=None,
+                       act_unsigned=False):
     """Depthwise 3x3 / pad 1 conv on fp16 codes [N, H, W, C] with int32 weight codes [9, C]: exact int32 accumulator,
-    then the fused tail (tq_depthwise3x3_codes).  Returns (out_f32 or None, out_codes or None)."""
+    then the fused tail (tq_depthwise3x3_codes).  act_unsigned: the codes are known to lie in [0, 1023] (post-ReLU
+    input under a quantiser of at most 9 bits).  Returns (out_f32 or None, out_codes or None)."""
     if act.dtype != torch.float16 or not act.is_contiguous() or wgt.dtype != torch.int32 or not wgt.is_contiguous():
         raise RuntimeError("depthwise3x3_codes expects contiguous fp16 NHWC codes and int32 [9, C] weights")
     N, H, W, C = act.shape
@@ -234,8 +236,8 @@ def depthwise3x3_codes(act, wgt, stride, scale, *, bias=None, bn=None, relu=Fals
     with torch.cuda.device(act.device):
         rc = _lib.lib().tq_depthwise3x3_codes(
             act.data_ptr(), wgt.data_ptr(), ptr(out), ptr(codes), ptr(bias), ptr(bn[0]) if bn else None,
-            ptr(bn[1]) if bn else None, N, H, W, C, stride, float(scale), _relu_code(relu), float(sf), int(bits), int(terms),
-            torch.cuda.current_stream(act.device).cuda_stream)
+            ptr(bn[1]) if bn else None, N, H, W, C, stride, float(scale), _relu_code(relu), int(bool(act_unsigned)),
+            float(sf), int(bits), int(terms), torch.cuda.current_stream(act.device).cuda_stream)
     _lib.check(rc)
     return out, codes
 

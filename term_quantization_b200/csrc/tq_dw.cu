@@ -8,10 +8,24 @@
 // applies t = float(acc) * (sf_x * sf_w) (+ bias), fma(t, bn_a, bn_b), ReLU / ReLU6, and writes the fp16 term codes of
 // the consumer's quantiser (and / or the fp32 value).  Algorithmic bytes: 2 B read + 2 B written per element.
 //
-// Mapping: NHWC, one thread = 8 channels (one 128-bit load) x DW_PIX consecutive output pixels of a row; the 3 x
-// (DW_PIX-1)*stride+3 input pixels are loaded once and reused across the outputs; weights (int32 [9][C]) and the
-// (q, sign) -> code table sit in shared memory.  Consecutive threads take consecutive channel blocks: coalesced.
+// Mapping: NHWC.  A tile = TH x TW output pixels x 64 channels of one image; its (TH*s+2) x (TW*s+2) x 64 input codes
+// are staged into shared memory by ONE tiled 4-D TMA load (cp.async.bulk.tensor; the halo outside the image arrives as
+// zeros: padding costs nothing), double-buffered so that the load of tile i+1 overlaps the arithmetic of tile i.  One
+// thread = 8 channels (one 128-bit shared-memory read per input pixel) x DW_PIX consecutive output pixels of a row, the
+// 3 x ((DW_PIX-1)*s+3) input pixels read once and reused across the outputs; weights (int32 [9][C]) and the
+// (q, sign) -> code table sit in shared memory; outputs leave as 128-bit stores, 128 contiguous bytes per 8 threads.
+// The first version of this kernel read its inputs with per-thread global loads and was latency-bound (5.9 ms per
+// MobileNet-V2 forward at batch 512 for 4.7 GB of algorithmic traffic); see DESIGN.md.
+#include <cuda.h>
+
 #include "tq_common.cuh"
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+namespace tq {
+EncodeTiledFn encode_tiled();           // tq_gemm.cu
+}
 
 namespace tq {
 
@@ -35,14 +49,36 @@ __device__ __forceinline__ float apply_act(float t, int relu)
     return t;
 }
 
-template <int STRIDE>
-__global__ void __launch_bounds__(256)
-depthwise3x3_codes_kernel(const __half *__restrict__ act, const int32_t *__restrict__ wgt, float *__restrict__ out_f32,
-                          __half *__restrict__ out_codes, DwParams p)
+struct DwTile {
+    int th, tw;                 // output pixels per tile
+    int tiles_h, tiles_w, cblocks;
+    int in_h, in_w;             // input pixels per tile (with halo)
+    int stage_bytes;
+    int unsigned_act;           // input codes are known to lie in [0, 1023] (post-ReLU): integer extraction without cvt
+};
+
+__device__ __forceinline__ uint32_t dw_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint4 dw_lds128(uint32_t saddr)
 {
-    extern __shared__ __align__(16) uint8_t dw_smem[];
-    int32_t *sw = reinterpret_cast<int32_t *>(dw_smem);                        // [9][C]
-    __half *lut = reinterpret_cast<__half *>(dw_smem + (size_t)9 * p.C * 4);   // (q, sign) -> code
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+
+// STRIDE 1 | 2; CB = channels per tile (64, or 32 for channel counts that are odd multiples of 32: no idle lanes);
+// UNSIGNED: input codes lie in [0, 1023] (post-ReLU): integer extraction without cvt; FAST: hoisted-reciprocal quantiser
+template <int STRIDE, int CB, bool UNSIGNED, bool FAST>
+__global__ void __launch_bounds__(256, 2)
+depthwise3x3_codes_kernel(const __grid_constant__ CUtensorMap tmIn, const int32_t *__restrict__ wgt,
+                          float *__restrict__ out_f32, __half *__restrict__ out_codes, DwParams p, DwTile tl)
+{
+    extern __shared__ __align__(128) uint8_t dw_smem[];
+    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(dw_smem) + 127) & ~uintptr_t(127));
+    uint8_t *stage0 = base;                                                     // 2 x [in_h][in_w][64] fp16
+    int32_t *sw = reinterpret_cast<int32_t *>(base + 2 * tl.stage_bytes);       // [9][C]
+    __half *lut = reinterpret_cast<__half *>(sw + 9 * p.C);                     // (q, sign) -> code
+    uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(lut) + (((size_t)(2u << p.next_bits) * 2 + 15) & ~(size_t)15));
     for (int i = threadIdx.x; i < 9 * p.C; i += blockDim.x) sw[i] = wgt[i];
     if (p.write_codes) {
         for (uint32_t i = threadIdx.x; i < (2u << p.next_bits); i += blockDim.x) {
@@ -50,92 +86,147 @@ depthwise3x3_codes_kernel(const __half *__restrict__ act, const int32_t *__restr
             lut[i] = __int2half_rn((i >> p.next_bits) ? -code : code);
         }
     }
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dw_smem_u32(&full[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dw_smem_u32(&full[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmIn) : "memory");
+    }
     __syncthreads();
     const Quant nq = make_quant(p.write_codes ? p.next_sf : 1.0f, (float)((1u << p.next_bits) - 1u));
+    const int tiles_per_img = tl.tiles_h * tl.tiles_w * tl.cblocks;
+    const int64_t total = (int64_t)p.N * tiles_per_img;
+
+    auto issue = [&](int64_t tile, int stage) {             // one thread: TMA the input box of `tile` into `stage`
+        const int cb = (int)(tile % tl.cblocks);
+        const int64_t r = tile / tl.cblocks;
+        const int tw = (int)(r % tl.tiles_w), th = (int)((r / tl.tiles_w) % tl.tiles_h), n = (int)(r / ((int64_t)tl.tiles_w * tl.tiles_h));
+        const uint32_t bar = dw_smem_u32(&full[stage]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)tl.stage_bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+            ::"r"(dw_smem_u32(stage0 + stage * tl.stage_bytes)), "l"(&tmIn), "r"(bar), "r"(cb * CB), "r"(tw * tl.tw * STRIDE - 1),
+              "r"(th * tl.th * STRIDE - 1), "r"(n) : "memory");
+    };
+
     constexpr int IN_PIX = (DW_PIX - 1) * STRIDE + 3;
-    const int c8n = p.C >> 3;
-    const int wq_n = (p.Wo + DW_PIX - 1) / DW_PIX;
-    const int64_t total = (int64_t)p.N * p.Ho * wq_n * c8n;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int c8 = (int)(t % c8n);
-        const int64_t q = t / c8n;
-        const int wq = (int)(q % wq_n), ho = (int)((q / wq_n) % p.Ho), n = (int)(q / ((int64_t)wq_n * p.Ho));
-        const int wo0 = wq * DW_PIX;
-        const int wi0 = wo0 * STRIDE - 1, hi0 = ho * STRIDE - 1;
-        int acc[DW_PIX][8];
+    const int groups_w = tl.tw / DW_PIX;
+    constexpr int C8 = CB / 8;                              // 8-channel blocks per tile
+    const int items = tl.th * groups_w * C8;                // (row, 4-pixel group, 8-channel block) of a tile
+    const uint32_t sw_addr = dw_smem_u32(sw);
+    int stage = 0;
+    uint32_t phases = 0u;                                   // bit s = parity to wait for on stage s
+    if (threadIdx.x == 0 && (int64_t)blockIdx.x < total) issue(blockIdx.x, 0);
+    for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int64_t next = tile + gridDim.x;
+        if (threadIdx.x == 0 && next < total) issue(next, stage ^ 1);      // (stage ^ 1 was released by the barrier below)
+        {   // wait for this tile's box
+            const uint32_t bar = dw_smem_u32(&full[stage]);
+            asm volatile(
+                "{\n\t"
+                ".reg .pred P1;\n\t"
+                "DW_WAIT:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+                "@P1 bra DW_DONE;\n\t"
+                "bra DW_WAIT;\n\t"
+                "DW_DONE:\n\t"
+                "}" ::"r"(bar), "r"((phases >> stage) & 1u) : "memory");
+            phases ^= 1u << stage;
+        }
+        const int cb = (int)(tile % tl.cblocks);
+        const int64_t r = tile / tl.cblocks;
+        const int twi = (int)(r % tl.tiles_w), thi = (int)((r / tl.tiles_w) % tl.tiles_h), n = (int)(r / ((int64_t)tl.tiles_w * tl.tiles_h));
+        const uint32_t sin = dw_smem_u32(stage0 + stage * tl.stage_bytes);
+        for (int item = threadIdx.x; item < items; item += blockDim.x) {
+            const int c8 = item % C8;
+            const int gw = (item / C8) % groups_w, row = (item / C8) / groups_w;
+            const int ch = cb * CB + c8 * 8;
+            const int ho = thi * tl.th + row, wo0 = twi * tl.tw + gw * DW_PIX;
+            if (ch >= p.C || ho >= p.Ho || wo0 >= p.Wo) continue;
+            int acc[DW_PIX][8];
 #pragma unroll
-        for (int j = 0; j < DW_PIX; ++j)
+            for (int j = 0; j < DW_PIX; ++j)
 #pragma unroll
-            for (int c = 0; c < 8; ++c) acc[j][c] = 0;
+                for (int c = 0; c < 8; ++c) acc[j][c] = 0;
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-            const int hi = hi0 + dy;
-            if (hi < 0 || hi >= p.H) continue;
-            int wrow[3][8];
+            for (int dy = 0; dy < 3; ++dy) {
+                int wrow[3][8];
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-                const int4 w0 = *reinterpret_cast<const int4 *>(sw + (dy * 3 + dx) * p.C + c8 * 8);
-                const int4 w1 = *reinterpret_cast<const int4 *>(sw + (dy * 3 + dx) * p.C + c8 * 8 + 4);
-                wrow[dx][0] = w0.x; wrow[dx][1] = w0.y; wrow[dx][2] = w0.z; wrow[dx][3] = w0.w;
-                wrow[dx][4] = w1.x; wrow[dx][5] = w1.y; wrow[dx][6] = w1.z; wrow[dx][7] = w1.w;
-            }
-            const __half *rowp = act + (((int64_t)n * p.H + hi) * p.W) * p.C + c8 * 8;
+                for (int dx = 0; dx < 3; ++dx) {
+                    const uint4 w0 = dw_lds128(sw_addr + (uint32_t)((dy * 3 + dx) * p.C + ch) * 4u);
+                    const uint4 w1 = dw_lds128(sw_addr + (uint32_t)((dy * 3 + dx) * p.C + ch + 4) * 4u);
+                    wrow[dx][0] = w0.x; wrow[dx][1] = w0.y; wrow[dx][2] = w0.z; wrow[dx][3] = w0.w;
+                    wrow[dx][4] = w1.x; wrow[dx][5] = w1.y; wrow[dx][6] = w1.z; wrow[dx][7] = w1.w;
+                }
+                const uint32_t rowp = sin + (uint32_t)(((row * STRIDE + dy) * tl.in_w + gw * DW_PIX * STRIDE) * CB + c8 * 8) * 2u;
 #pragma unroll
-            for (int px = 0; px < IN_PIX; ++px) {
-                const int wi = wi0 + px;
-                if (wi < 0 || wi >= p.W) continue;
-                const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(rowp + (int64_t)wi * p.C));
-                const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
-                int v[8];
+                for (int px = 0; px < IN_PIX; ++px) {
+                    const uint4 raw = dw_lds128(rowp + (uint32_t)px * (CB * 2));
+                    const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+                    int v[8];
+                    if constexpr (UNSIGNED) {
+                        // integer codes 0..1023 held in fp16: x + 1024 is exact and its mantissa field IS the integer
 #pragma unroll
-                for (int c = 0; c < 8; ++c) v[c] = __half2int_rn(__ushort_as_half((unsigned short)(rw[c >> 1] >> (16 * (c & 1)))));
+                        for (int h = 0; h < 4; ++h) {
+                            __half2 x2 = *reinterpret_cast<const __half2 *>(&rw[h]);
+                            x2 = __hadd2(x2, __half2half2(__ushort_as_half((unsigned short)0x6400)));   // 1024.0
+                            const uint32_t b = *reinterpret_cast<const uint32_t *>(&x2);
+                            v[2 * h] = (int)(b & 0x3FFu);
+                            v[2 * h + 1] = (int)((b >> 16) & 0x3FFu);
+                        }
+                    } else {
 #pragma unroll
-                for (int j = 0; j < DW_PIX; ++j) {
-                    const int dx = px - j * STRIDE;              // compile-time after unrolling
-                    if (dx < 0 || dx > 2) continue;
+                        for (int c = 0; c < 8; ++c) v[c] = __half2int_rn(__ushort_as_half((unsigned short)(rw[c >> 1] >> (16 * (c & 1)))));
+                    }
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) acc[j][c] += v[c] * wrow[dx][c];
+                    for (int j = 0; j < DW_PIX; ++j) {
+                        const int dx = px - j * STRIDE;              // compile-time after unrolling
+                        if (dx < 0 || dx > 2) continue;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) acc[j][c] += v[c] * wrow[dx][c];
+                    }
                 }
             }
-        }
-        // epilogue: float(acc) * scale (+ bias) -> fma(BN) -> activation -> fp32 and / or term codes
-        float ba[8], bb[8], bs[8];
-        const int ch = c8 * 8;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            ba[c] = p.bn_a ? __ldg(p.bn_a + ch + c) : 1.0f;
-            bb[c] = p.bn_b ? __ldg(p.bn_b + ch + c) : 0.0f;
-            bs[c] = p.bias ? __ldg(p.bias + ch + c) : 0.0f;
-        }
-#pragma unroll
-        for (int j = 0; j < DW_PIX; ++j) {
-            const int wo = wo0 + j;
-            if (wo >= p.Wo) break;
-            const int64_t o = (((int64_t)n * p.Ho + ho) * p.Wo + wo) * p.C + ch;
-            float tv[8];
+            // epilogue: float(acc) * scale (+ bias) -> fma(BN) -> activation -> fp32 and / or term codes
+            float ba[8], bb[8], bs[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                float x = __fmul_rn(__int2float_rn(acc[j][c]), p.scale);
-                if (p.bias) x = __fadd_rn(x, bs[c]);
-                if (p.bn_a) x = __fmaf_rn(x, ba[c], bb[c]);
-                tv[c] = apply_act(x, p.relu);
+                ba[c] = p.bn_a ? __ldg(p.bn_a + ch + c) : 1.0f;
+                bb[c] = p.bn_b ? __ldg(p.bn_b + ch + c) : 0.0f;
+                bs[c] = p.bias ? __ldg(p.bias + ch + c) : 0.0f;
             }
-            if (p.write_f32) {
-                reinterpret_cast<float4 *>(out_f32 + o)[0] = make_float4(tv[0], tv[1], tv[2], tv[3]);
-                reinterpret_cast<float4 *>(out_f32 + o)[1] = make_float4(tv[4], tv[5], tv[6], tv[7]);
-            }
-            if (p.write_codes) {
-                uint32_t hc[8];
+#pragma unroll
+            for (int j = 0; j < DW_PIX; ++j) {
+                const int wo = wo0 + j;
+                if (wo >= p.Wo) break;
+                const int64_t o = (((int64_t)n * p.Ho + ho) * p.Wo + wo) * p.C + ch;
+                float tv[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const uint32_t neg = __float_as_uint(tv[c]) >> 31;
-                    const uint32_t qi = p.next_fastdiv ? quantize_f32<true>(tv[c], nq) : quantize_f32<false>(tv[c], nq);
-                    hc[c] = __half_as_ushort(lut[qi | (neg << p.next_bits)]);
+                    float x = __fmul_rn(__int2float_rn(acc[j][c]), p.scale);
+                    if (p.bias) x = __fadd_rn(x, bs[c]);
+                    if (p.bn_a) x = __fmaf_rn(x, ba[c], bb[c]);
+                    tv[c] = apply_act(x, p.relu);
                 }
-                *reinterpret_cast<uint4 *>(out_codes + o) =
-                    make_uint4(hc[0] | (hc[1] << 16), hc[2] | (hc[3] << 16), hc[4] | (hc[5] << 16), hc[6] | (hc[7] << 16));
+                if (p.write_f32) {
+                    reinterpret_cast<float4 *>(out_f32 + o)[0] = make_float4(tv[0], tv[1], tv[2], tv[3]);
+                    reinterpret_cast<float4 *>(out_f32 + o)[1] = make_float4(tv[4], tv[5], tv[6], tv[7]);
+                }
+                if (p.write_codes) {
+                    uint32_t hc[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint32_t neg = __float_as_uint(tv[c]) >> 31;
+                        const uint32_t qi = quantize_f32<FAST>(tv[c], nq);
+                        hc[c] = __half_as_ushort(lut[qi | (neg << p.next_bits)]);
+                    }
+                    *reinterpret_cast<uint4 *>(out_codes + o) =
+                        make_uint4(hc[0] | (hc[1] << 16), hc[2] | (hc[3] << 16), hc[4] | (hc[5] << 16), hc[6] | (hc[7] << 16));
+                }
             }
         }
+        __syncthreads();                                    // every thread is done with `stage`: it may be refilled
+        stage ^= 1;
     }
 }
 
@@ -145,7 +236,7 @@ __global__ void __launch_bounds__(256)
 bn_act_encode_kernel(const float *__restrict__ x, float *__restrict__ out_f32, __half *__restrict__ out_codes, int64_t n4, int C,
                      DwParams p)
 {
-    extern __shared__ __align__(16) uint8_t dw_smem[];
+    extern __shared__ __align__(128) uint8_t dw_smem[];
     __half *lut = reinterpret_cast<__half *>(dw_smem);
     if (p.write_codes) {
         for (uint32_t i = threadIdx.x; i < (2u << p.next_bits); i += blockDim.x) {
@@ -203,8 +294,8 @@ using namespace tq;
 
 extern "C" int tq_depthwise3x3_codes(const void *act_codes, const int32_t *wgt_codes, float *out_f32, void *out_codes,
                                      const float *bias, const float *bn_a, const float *bn_b, int N, int H, int W, int C,
-                                     int stride, float scale, int relu, float next_sf, int next_bits, int next_terms,
-                                     void *stream)
+                                     int stride, float scale, int relu, int act_unsigned, float next_sf, int next_bits,
+                                     int next_terms, void *stream)
 {
     if (!act_codes || !wgt_codes || (!out_f32 && !out_codes)) return fail(TQ_ERR_INVALID, "NULL pointer");
     if (N < 1 || H < 1 || W < 1 || C < 8 || C % 8) return fail(TQ_ERR_INVALID, "bad shape (C must be a multiple of 8)");
@@ -213,6 +304,8 @@ extern "C" int tq_depthwise3x3_codes(const void *act_codes, const int32_t *wgt_c
     if (relu < 0 || relu > 2) return fail(TQ_ERR_INVALID, "relu: 0 none, 1 ReLU, 2 ReLU6");
     if ((((uintptr_t)act_codes | (uintptr_t)wgt_codes | (uintptr_t)out_f32 | (uintptr_t)out_codes) & 15u) != 0)
         return fail(TQ_ERR_INVALID, "pointers must be 16-byte aligned");
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return fail(TQ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     DwParams p{};
     p.N = N; p.H = H; p.W = W; p.C = C; p.stride = stride;
     p.Ho = (H + 2 - 3) / stride + 1;
@@ -221,18 +314,62 @@ extern "C" int tq_depthwise3x3_codes(const void *act_codes, const int32_t *wgt_c
     p.write_f32 = out_f32 ? 1 : 0;
     int rc = fill_quant(p, out_codes, next_sf, next_bits, next_terms);
     if (rc != TQ_OK) return rc;
-    const size_t smem = (size_t)9 * C * 4 + (out_codes ? (size_t)(2u << p.next_bits) * sizeof(__half) : 0);
-    if (smem > 200 * 1024) return fail(TQ_ERR_UNSUPPORTED, "depthwise conv: %d channels do not fit shared memory", C);
-    const int64_t total = (int64_t)N * p.Ho * ((p.Wo + DW_PIX - 1) / DW_PIX) * (C / 8);
-    int64_t blocks = (total + 255) / 256;
-    const int64_t cap = (int64_t)num_sms() * 8;
-    if (blocks > cap) blocks = cap;
-    auto kern = stride == 1 ? depthwise3x3_codes_kernel<1> : depthwise3x3_codes_kernel<2>;
-    if (smem > 48 * 1024) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return check_launch("cudaFuncSetAttribute(depthwise3x3_codes_kernel)");
+    // tile: TW a multiple of DW_PIX; small maps take small tiles (a 7x7 map in a 8x16 tile would idle 62 % of the lanes)
+    DwTile tl{};
+    tl.tw = p.Wo > 8 ? 16 : 8;
+    tl.th = p.Ho > 4 ? 8 : 4;
+    if (stride == 2 && tl.tw == 16) tl.th = 4;              // (2*4+2) x (2*16+2) x 128 B = 43.5 KB per stage
+    tl.tiles_w = (p.Wo + tl.tw - 1) / tl.tw;
+    tl.tiles_h = (p.Ho + tl.th - 1) / tl.th;
+    const int cbsz = (C % 64 == 0) ? 64 : 32;               // odd multiples of 32 (and 8/16/24-channel maps): half-width tiles
+    tl.cblocks = (C + cbsz - 1) / cbsz;
+    tl.in_w = tl.tw * stride + 2;
+    tl.in_h = tl.th * stride + 2;
+    tl.stage_bytes = (tl.in_h * tl.in_w * cbsz * 2 + 127) & ~127;
+    tl.unsigned_act = act_unsigned ? 1 : 0;
+    CUtensorMap tm;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+        cuuint32_t box[4] = {(cuuint32_t)cbsz, (cuuint32_t)tl.in_w, (cuuint32_t)tl.in_h, 1};
+        cuuint32_t one[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(act_codes), dims, strides, box, one,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(TQ_ERR_CUDA, "cuTensorMapEncodeTiled(depthwise input) failed: %d", (int)r);
     }
-    kern<<<(int)blocks, 256, smem, (cudaStream_t)stream>>>((const __half *)act_codes, wgt_codes, out_f32, (__half *)out_codes, p);
+    const size_t smem = 128 + 2 * (size_t)tl.stage_bytes + (size_t)9 * C * 4 + (((size_t)(2u << p.next_bits) * 2 + 15) & ~(size_t)15) + 64;
+    if (smem > 220 * 1024) return fail(TQ_ERR_UNSUPPORTED, "depthwise conv: %d channels do not fit shared memory", C);
+    const int64_t total = (int64_t)N * tl.tiles_h * tl.tiles_w * tl.cblocks;
+    // persistent CTAs: as many as fit per SM by shared memory (the tile loop double-buffers its own loads)
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm > 2) per_sm = 2;                             // __launch_bounds__(256, 2)
+    if (per_sm < 1) per_sm = 1;
+    int64_t blocks = (int64_t)num_sms() * per_sm;
+    if (blocks > total) blocks = total;
+    typedef void (*Kern)(const CUtensorMap, const int32_t *, float *, __half *, DwParams, DwTile);
+    // [stride - 1][CB == 32][unsigned][fast]
+    static const Kern table[2][2][2][2] = {
+        {{{depthwise3x3_codes_kernel<1, 64, false, false>, depthwise3x3_codes_kernel<1, 64, false, true>},
+          {depthwise3x3_codes_kernel<1, 64, true, false>, depthwise3x3_codes_kernel<1, 64, true, true>}},
+         {{depthwise3x3_codes_kernel<1, 32, false, false>, depthwise3x3_codes_kernel<1, 32, false, true>},
+          {depthwise3x3_codes_kernel<1, 32, true, false>, depthwise3x3_codes_kernel<1, 32, true, true>}}},
+        {{{depthwise3x3_codes_kernel<2, 64, false, false>, depthwise3x3_codes_kernel<2, 64, false, true>},
+          {depthwise3x3_codes_kernel<2, 64, true, false>, depthwise3x3_codes_kernel<2, 64, true, true>}},
+         {{depthwise3x3_codes_kernel<2, 32, false, false>, depthwise3x3_codes_kernel<2, 32, false, true>},
+          {depthwise3x3_codes_kernel<2, 32, true, false>, depthwise3x3_codes_kernel<2, 32, true, true>}}}};
+    const int i_cb = cbsz == 32 ? 1 : 0, i_un = tl.unsigned_act, i_fast = p.next_fastdiv ? 1 : 0;
+    Kern kern = table[stride - 1][i_cb][i_un][i_fast];
+    static bool attr_set[16][64] = {{false}};
+    const int kidx = ((stride - 1) * 2 + i_cb) * 4 + i_un * 2 + i_fast;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[kidx][dev]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
+            return check_launch("cudaFuncSetAttribute(depthwise3x3_codes_kernel)");
+        attr_set[kidx][dev] = true;
+    }
+    kern<<<(int)blocks, 256, smem, (cudaStream_t)stream>>>(tm, wgt_codes, out_f32, (__half *)out_codes, p, tl);
     count_launch();
     return check_launch("depthwise3x3_codes_kernel");
 }

@@ -882,7 +882,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static EncodeTiledFn encode_tiled()
+EncodeTiledFn encode_tiled()          // shared with tq_dw.cu
 {
     static EncodeTiledFn fn = nullptr;
     static std::once_flag once;

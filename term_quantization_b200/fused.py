@@ -291,9 +291,10 @@ class _Depthwise:
         self.bn = _bn_affine(bn) if bn is not None else None
         self.stride = c.stride[0]
 
-    def __call__(self, codes, relu=False, want_f32=False, next_quant=None):
+    def __call__(self, codes, relu=False, want_f32=False, next_quant=None, post_relu=False):
         return conv_codes.depthwise3x3_codes(codes, self.w, self.stride, self.scale, bias=self.bias, bn=self.bn, relu=relu,
-                                             want_f32=want_f32, next_quant=next_quant)
+                                             want_f32=want_f32, next_quant=next_quant,
+                                             act_unsigned=post_relu and self.quant[1] <= 9)
 
 
 class FusedMobileNet(nn.Module):
@@ -366,7 +367,7 @@ class FusedMobileNet(nn.Module):
             h = codes
             if expand is not None:
                 _, h = expand(h, relu="relu6", want_f32=False, next_quant=dw.quant)
-            _, h = dw(h, relu="relu6", next_quant=proj.quant)
+            _, h = dw(h, relu="relu6", next_quant=proj.quant, post_relu=True)   # its input: ReLU6 of the expand conv / stem
             nxt = self.blocks[i + 1] if i + 1 < len(self.blocks) else None
             nq = ((nxt[0] or nxt[1]).quant if nxt is not None else self.last.quant)
             need_f32 = nxt is not None and nxt[3]                               # the next block adds this output back

@@ -345,7 +345,8 @@ def test_depthwise_and_bn_act_kernels_against_cpu_emulation():
         t_ref, _ = fused_emul.fused_depthwise(act.cpu().numpy().astype(np.int32), dw, relu=relu)
         nq = (max(float(np.abs(t_ref).max()), 1e-3) / 512, 9, 3)
         t_ref, c_ref = fused_emul.fused_depthwise(act.cpu().numpy().astype(np.int32), dw, relu=relu, next_quant=nq)
-        out, codes = conv_codes.depthwise3x3_codes(act, w, stride, scale, bn=(a, b), relu=relu, want_f32=True, next_quant=nq)
+        out, codes = conv_codes.depthwise3x3_codes(act, w, stride, scale, bn=(a, b), relu=relu, want_f32=True, next_quant=nq,
+                                                   act_unsigned=bool(relu))
         assert np.array_equal(out.cpu().numpy(), t_ref), (N, H, W, C, stride)
         assert np.array_equal(codes.cpu().numpy().astype(np.int32), c_ref), (N, H, W, C, stride)
         none, codes2 = conv_codes.depthwise3x3_codes(act, w, stride, scale, bn=(a, b), relu=relu, next_quant=nq)
