@@ -244,10 +244,21 @@ class FusedVGG(nn.Module):
     def forward(self, x):
         m = self.model
         x = x.float().contiguous(memory_format=torch.channels_last)
-        for kind, mod in self.stages[:self.first_tr]:             # unwrapped stem: conv / BN / ReLU (/ pool) on torch
-            x = mod(x)
         convs = [k for k, (kind, _) in enumerate(self.stages) if kind == "conv"]
-        codes = FusedResNet._encode(x.permute(0, 2, 3, 1), self.stages[convs[0]][1][0].quant)   # NHWC fp16 codes
+        q0 = self.stages[convs[0]][1][0].quant
+        stem = [mod for _, mod in self.stages[:self.first_tr]]
+        if (len(stem) == 3 and isinstance(stem[0], nn.Conv2d) and isinstance(stem[1], nn.BatchNorm2d)
+                and isinstance(stem[2], nn.ReLU) and stem[0].out_channels % 4 == 0):
+            # unwrapped first conv on cuDNN fp32; its BatchNorm + ReLU + the first wrapped conv's encode in ONE pass
+            # (tq_bn_act_encode) instead of three passes over the largest activation of the network
+            y = stem[0](x).permute(0, 2, 3, 1).contiguous()
+            if getattr(self, "_stem_bn", None) is None:
+                self._stem_bn = _bn_affine(stem[1])
+            _, codes = conv_codes.bn_act_encode(y, self._stem_bn, relu=True, next_quant=q0)
+        else:
+            for mod in stem:                                      # any other stem: module by module on torch
+                x = mod(x)
+            codes = FusedResNet._encode(x.permute(0, 2, 3, 1), q0)                  # NHWC fp16 codes
         out = None
         for k in range(self.first_tr, len(self.stages)):
             kind, payload = self.stages[k]
