@@ -207,6 +207,47 @@ def conv2d_codes_fused(act, wgt, kernel_size, stride, pad, scale, *, bias=None, 
     return out, codes
 
 
+def pack_linear_weight(w, w_sf):
+    """Term-revealed (out, in) fp32 weight (an integer multiple of w_sf) -> fp16 codes [1, out_pad, in_pad] for the conv
+    kernel run as a GEMM (1x1 conv over a 1 x M "image"): `in` padded to a multiple of 16 with zero codes (TMA rows are
+    16 bytes; 650 -> 656 for the LSTM), `out` to a multiple of 4.  Returns (packed, fp32 w_sf)."""
+    sf32 = torch.tensor(w_sf, dtype=torch.float32).item()
+    codes = torch.round(w.detach() / sf32)
+    if not torch.equal(codes * sf32, w.detach()):
+        raise RuntimeError("weight is not an integer multiple of w_sf any more")
+    O, I = codes.shape
+    Op, Ip = (O + 3) // 4 * 4, (I + 15) // 16 * 16
+    packed = torch.zeros((1, Op, Ip), dtype=torch.float16, device=w.device)
+    packed[0, :O, :I] = codes.to(torch.float16)
+    return packed, sf32
+
+
+def linear_codes(x_codes, wgt, scale, *, bias=None, out_features=None, plan=None, act_max=512, signed_act=True,
+                 engine="auto"):
+    """x_codes fp16 [M, K] integer codes times packed weight codes [1, out_pad, K_pad] (pack_linear_weight):
+    float(exact int32 accumulator) * scale (+ bias) -> fp32 [M, out_features].  The GEMM runs on the tcgen05 conv
+    kernel as a 1x1 conv over a 1 x M image; the engine (kind::f16 with proven K chunks / kind::i8 planes) comes from
+    `plan_weight`."""
+    if x_codes.dtype != torch.float16 or x_codes.dim() != 2:
+        raise RuntimeError("linear_codes expects fp16 [M, K] codes")
+    M, K = x_codes.shape
+    _, Op, Kp = wgt.shape
+    if K > Kp:
+        raise RuntimeError("weight / activation shape mismatch")
+    if K != Kp:
+        xp = torch.zeros((M, Kp), dtype=torch.float16, device=x_codes.device)
+        xp[:, :K] = x_codes
+        x_codes = xp
+    bias_p = bias
+    if bias is not None and bias.numel() != Op:
+        bias_p = torch.zeros(Op, dtype=torch.float32, device=wgt.device)
+        bias_p[:bias.numel()] = bias.detach().float()
+    out = conv2d_codes(x_codes.contiguous().view(1, 1, M, Kp), wgt, bias_p, (1, 1), 1, 0, scale, plan=plan, act_max=act_max,
+                       signed_act=signed_act, engine=engine).view(M, Op)
+    n = out_features if out_features is not None else Op
+    return out if n == Op else out[:, :n]
+
+
 def pack_depthwise_weight(w, w_sf):
     """Term-revealed depthwise weight (C, 1, 3, 3) fp32 (already an integer multiple of w_sf) -> int32 [9, C] codes."""
     if w.dim() != 4 or w.shape[1] != 1 or tuple(w.shape[2:]) != (3, 3):

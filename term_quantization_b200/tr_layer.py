@@ -111,6 +111,12 @@ def use_tensor_cores(model, enable=True, engine="auto"):
                 switched.append(name)
             else:
                 skipped.append((name, why))
+        elif isinstance(layer, (TRLinearLayer, TRLSTMLayer)):
+            try:
+                layer.use_tensor_cores(enable, engine)
+                switched.append(name)
+            except NotImplementedError as e:
+                skipped.append((name, str(e)))
     return switched, skipped
 
 
@@ -309,7 +315,12 @@ class TRConv2dLayer(_TRBase):
 
 
 class TRLinearLayer(_TRBase):
-    """Linear on term-revealed weights (tr_layer.py:134-160)."""
+    """Linear on term-revealed weights (tr_layer.py:134-160).
+
+    Default forward = the reference's, quirk included: with STRICT_REFERENCE the quantised input is discarded and the
+    float linear runs on the raw input (tr_layer.py:152-154), so there is no integer contraction to run.  After
+    ``use_tensor_cores()`` the layer computes what the wrapper evidently intends -- linear(q(x)) -- on the integer term
+    codes with the tcgen05 kernel (exact int32 accumulator, sf_x * w_sf and the bias in the epilogue)."""
 
     def __init__(self, linear_layer, data_bits=8, data_terms=4, weight_bits=8, group_size=1,
                  num_terms=8):
@@ -318,8 +329,45 @@ class TRLinearLayer(_TRBase):
                     num_terms)
         linear_layer.weight = self._reveal_weight(linear_layer.weight)
         self.linear = linear_layer
+        self.register_buffer("_tc_weight", None, persistent=False)
+        self._tc_plan = None
+
+    def use_tensor_cores(self, enable=True, engine="auto"):
+        if not enable:
+            self._tc_weight, self._tc_plan = None, None
+            return self
+        from . import conv_codes
+        if self.data_bits > 10 or self.weight_bits > 10:
+            raise NotImplementedError("tcgen05 linear path: codes above 2^10")
+        self._tc_weight, self._tc_wsf32 = conv_codes.pack_linear_weight(self.linear.weight, self.w_sf)
+        self._tc_engine = engine
+        self._tc_plan = conv_codes.plan_weight(self._tc_weight, 1 << self.data_bits, signed_act=True, engine=engine)
+        self._tc_key = (self.linear.weight.data_ptr(), self.linear.weight._version, float(self.w_sf))
+        return self
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        tcw = getattr(self, "_tc_weight", None)
+        if tcw is not None and (self._tc_plan is None or self._tc_plan.wgt is not tcw):
+            self.use_tensor_cores(True, getattr(self, "_tc_engine", "auto"))
+        return out
+
+    def _forward_tensor_cores(self, x):
+        from . import conv_codes
+        if self._tc_key != (self.linear.weight.data_ptr(), self.linear.weight._version, float(self.w_sf)):
+            self.use_tensor_cores(True, getattr(self, "_tc_engine", "auto"))
+        q = self.input_quant
+        lead = x.shape[:-1]
+        x2 = x.contiguous().view(-1, x.shape[-1])
+        codes = tr_cuda.tr_codes(x2.view(1, -1, 1, 1), q.sf, q.data_bits, 1, q.data_terms, dtype=torch.float16).view(x2.shape)
+        scale = (torch.tensor(float(q.sf), dtype=torch.float32) * torch.tensor(self._tc_wsf32, dtype=torch.float32)).item()
+        out = conv_codes.linear_codes(codes, self._tc_weight, scale, bias=self.linear.bias,
+                                      out_features=self.linear.out_features, plan=self._tc_plan)
+        return out.reshape(*lead, self.linear.out_features)
 
     def forward(self, x):
+        if self._tc_weight is not None and not self.input_quant.tracking:
+            return self._forward_tensor_cores(x)
         if STRICT_REFERENCE:
             # tr_layer.py:152-154 quantises x and then ignores the result; only the histogram
             # side effect of tracking mode is observable, so that is all that is kept.
@@ -331,7 +379,13 @@ class TRLinearLayer(_TRBase):
 
 class TRLSTMLayer(_TRBase):
     """nn.LSTM whose layer-0 weights are term-revealed; emb, h0 and c0 share one input
-    quantiser (tr_layer.py:162-201)."""
+    quantiser (tr_layer.py:162-201).
+
+    Default forward = the reference's: quantised emb / h0 / c0 into the stock cuDNN LSTM.  After
+    ``use_tensor_cores()`` the one integer contraction the layer contains -- layer 0's input projection
+    W_ih . q(emb_t) for all T x B tokens at once (the recurrent products see fp32 hidden states after t = 0) -- runs on
+    the tcgen05 kernel on term codes (exact int32 accumulators, K = 650 zero-padded to 656), layer 0's recurrence is
+    evaluated step by step on that projection, and the remaining layers stay on cuDNN."""
 
     def __init__(self, lstm_layer, data_bits=8, data_terms=4, weight_bits=8, group_size=1,
                  num_terms=8):
@@ -339,11 +393,72 @@ class TRLSTMLayer(_TRBase):
         self._setup(lstm_layer.weight_ih_l0.device, data_bits, data_terms, weight_bits, group_size,
                     num_terms)
         lstm_layer.weight_ih_l0 = self._reveal_weight(lstm_layer.weight_ih_l0)
+        self.w_sf_ih = self.w_sf                                                 # (w_sf itself ends up as hh's, like the reference)
         lstm_layer.weight_hh_l0 = self._reveal_weight(lstm_layer.weight_hh_l0)   # w_sf := hh's
         self.lstm = lstm_layer
         self.lstm.flatten_parameters()
+        self.register_buffer("_tc_weight", None, persistent=False)
+        self._tc_plan = None
+
+    def use_tensor_cores(self, enable=True, engine="auto"):
+        if not enable:
+            self._tc_weight, self._tc_plan = None, None
+            return self
+        from . import conv_codes
+        m = self.lstm
+        if not isinstance(m, nn.LSTM) or m.bidirectional or m.batch_first or m.proj_size != 0:
+            raise NotImplementedError("tcgen05 LSTM path: unidirectional, time-major nn.LSTM without projections")
+        self._tc_weight, self._tc_wsf32 = conv_codes.pack_linear_weight(m.weight_ih_l0, self.w_sf_ih)
+        self._tc_engine = engine
+        self._tc_plan = conv_codes.plan_weight(self._tc_weight, 1 << self.data_bits, signed_act=True, engine=engine)
+        return self
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        tcw = getattr(self, "_tc_weight", None)
+        if tcw is not None and (self._tc_plan is None or self._tc_plan.wgt is not tcw):
+            self.use_tensor_cores(True, getattr(self, "_tc_engine", "auto"))
+        return out
+
+    def input_projection(self, emb):
+        """W_ih . q(emb) for every token, [T, B, 4H] fp32 = float(exact int32 accumulator) * (sf_x * w_sf_ih)."""
+        from . import conv_codes
+        q = self.input_quant
+        T, B, I = emb.shape
+        codes = tr_cuda.tr_codes(emb.contiguous().view(1, -1, 1, 1), q.sf, q.data_bits, 1, q.data_terms,
+                                 dtype=torch.float16).view(T * B, I)
+        scale = (torch.tensor(float(q.sf), dtype=torch.float32) * torch.tensor(self._tc_wsf32, dtype=torch.float32)).item()
+        g = conv_codes.linear_codes(codes, self._tc_weight, scale, out_features=4 * self.lstm.hidden_size, plan=self._tc_plan)
+        return g.view(T, B, -1)
+
+    def _forward_tensor_cores(self, emb, hidden):
+        m = self.lstm
+        h0, c0 = (self.input_quant(h) for h in hidden)                           # shared quantiser (tr_layer.py:193-194)
+        gin = self.input_projection(emb)
+        bias = (m.bias_ih_l0 + m.bias_hh_l0) if m.bias else None
+        w_hh_t = m.weight_hh_l0.t()
+        h, c = h0[0], c0[0]
+        outs = []
+        for t in range(gin.shape[0]):                                            # layer 0: i, f, g, o (torch gate order)
+            gates = torch.addmm(gin[t] if bias is None else gin[t] + bias, h, w_hh_t)
+            i, f, g, o = gates.chunk(4, dim=1)
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            outs.append(h)
+        y = torch.stack(outs)
+        hn, cn = [h], [c]
+        if m.num_layers > 1:                                                     # upper layers: cuDNN, unchanged weights
+            per = 4 if m.bias else 2
+            y, h_up, c_up = torch._VF.lstm(y, (h0[1:].contiguous(), c0[1:].contiguous()), m._flat_weights[per:], m.bias,
+                                           m.num_layers - 1, 0.0, False, False, False)
+            hn.append(h_up)
+            cn.append(c_up)
+            return y, (torch.cat([hn[0].unsqueeze(0), h_up]), torch.cat([cn[0].unsqueeze(0), c_up]))
+        return y, (h.unsqueeze(0), c.unsqueeze(0))
 
     def forward(self, emb, hidden):
+        if self._tc_weight is not None and not self.input_quant.tracking and not self.lstm.training:
+            return self._forward_tensor_cores(emb, hidden)
         embq = self.input_quant(emb)
         hidden_qs = tuple(self.input_quant(h) for h in hidden)
         return self.lstm(embq, hidden_qs)

@@ -496,3 +496,56 @@ def test_fused_vgg_pools_on_codes():
     pc = torch.nn.functional.max_pool2d(codes.permute(0, 3, 1, 2), 2, 2)
     pv = torch.nn.functional.max_pool2d(vals.permute(0, 3, 1, 2), 2, 2)
     assert torch.equal(pc.float() * 0.0371, pv)
+
+
+def test_linear_and_lstm_input_projection_on_tensor_cores():
+    """BASELINE configs[0] / [4]: the Linear layers of the MLP and the LSTM's layer-0 input projection
+    W_ih . q(emb) (T x B = 2,800 tokens, K = 650 zero-padded to 656, 4H = 2,600; evaluate_lstm.py:17-37,
+    tr_layer.py:174-195) on the tcgen05 kernel: exact int32 accumulators against an integer GEMM of the same codes, and
+    the layers' outputs against the float path on the same quantised inputs."""
+    from term_quantization_b200 import conv_codes, tr_cuda, tr_layer
+    g = torch.Generator(device="cuda").manual_seed(2)
+    # raw op: exact accumulators, ragged K and out
+    for (M, K, N, amax, wmax) in ((2800, 650, 2600, 256, 128), (256, 784, 512, 64, 8), (256, 512, 10, 64, 8), (35, 650, 33278, 256, 128)):
+        x = torch.randint(-amax, amax + 1, (M, K), device="cuda", generator=g)
+        w = torch.randint(-wmax, wmax + 1, (N, K), device="cuda", generator=g)
+        packed, _ = conv_codes.pack_linear_weight(w.float(), 1.0)
+        out = conv_codes.linear_codes(x.half(), packed, 1.0, out_features=N, act_max=amax, signed_act=True)
+        want = (x.double() @ w.double().t())
+        assert out.shape == (M, N) and torch.equal(out, want.float()), (M, K, N)
+    # TRLinearLayer: linear(q(x)) on codes == the float linear on the dequantised input, up to fp32 summation order
+    torch.manual_seed(0)
+    lin = nn.Linear(784, 512).cuda()
+    layer = tr_layer.TRLinearLayer(lin, 6, 6, 4, 8, 12)
+    x = torch.randn(256, 784, device="cuda", generator=g)
+    with torch.no_grad():
+        layer(x)
+        tr_layer.set_tr_tracking(layer, False)
+        ref = layer.linear(layer.input_quant(x))
+        layer.use_tensor_cores()
+        got = layer(x)
+    assert got.shape == ref.shape
+    assert float((got - ref).abs().max()) <= 2e-6 * float(ref.abs().max()) * 784 ** 0.5
+    # TRLSTMLayer: integer input projection + step-wise layer 0 + cuDNN upper layer vs the reference forward
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    lstm = nn.LSTM(650, 650, 2).cuda().eval()
+    L = tr_layer.TRLSTMLayer(lstm, 8, 8, 8, 8, 12)
+    emb = torch.randn(35, 80, 650, device="cuda", generator=g) * 0.1
+    hid = (torch.randn(2, 80, 650, device="cuda", generator=g) * 0.1, torch.randn(2, 80, 650, device="cuda", generator=g) * 0.1)
+    with torch.no_grad():
+        L(emb, hid)
+        tr_layer.set_tr_tracking(L, False)
+        y_ref, (h_ref, c_ref) = L(emb, hid)
+        L.use_tensor_cores()
+        # the projection itself: exact against the integer GEMM of the same codes
+        q = L.input_quant
+        codes = tr_cuda.tr_codes(emb.view(1, -1, 1, 1), q.sf, 8, 1, 8, dtype=torch.int32).view(-1, 650)
+        wc = torch.round(lstm.weight_ih_l0 / np.float32(L.w_sf_ih))
+        acc = codes.double() @ wc.double().t()
+        scale = np.float32(q.sf) * np.float32(L.w_sf_ih)
+        assert torch.equal(L.input_projection(emb).view(-1, 2600), acc.float() * scale)
+        y, (h, c) = L(emb, hid)
+    for a, b in ((y, y_ref), (h, h_ref), (c, c_ref)):
+        assert a.shape == b.shape
+        assert float((a - b).abs().max()) <= 1e-5 * max(float(b.abs().max()), 1.0), float((a - b).abs().max())
