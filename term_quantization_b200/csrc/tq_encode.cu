@@ -176,11 +176,19 @@ __device__ __forceinline__ int count_at_or_above(const uint32_t (&W)[NW], int p)
 
 constexpr int GROUP_LUT_MAX_BITS = 12;          // 2^bits entries of (T | N << 16) in shared memory: 16 KB at most
 
-template <int G, bool CONTIG, typename Tout, bool DEQ, bool FAST>
+// LAYOUT 0: groups strided by WH in global memory (large planes: consecutive threads take consecutive wh, coalesced);
+// LAYOUT 1: contiguous groups (WH == 1): 128-bit loads / stores per group;
+// LAYOUT 2: small planes (conv weights, WH = kh * kw = 9, 25, 49: the reference's real weight layout, tr_layer.py:117-120):
+//           a block of G * WH consecutive elements holds exactly WH complete groups, so a CTA copies whole blocks into
+//           shared memory with coalesced 128-bit loads, every thread picks its group out of shared memory (stride WH,
+//           conflict-free across the threads of a warp), writes the result back in place, and the tile leaves with
+//           coalesced 128-bit stores.  The strided variant touches ~8 sectors per warp load on such tensors (1.1 TB/s).
+template <int G, int LAYOUT, typename Tout, bool DEQ, bool FAST>
 __global__ void __launch_bounds__(GROUP_THREADS)
 tr_group_kernel(const float *__restrict__ in, Tout *__restrict__ out,
-                int64_t B, int64_t C, int64_t WH, EncParams p, int use_lut, int *__restrict__ overflow)
+                int64_t B, int64_t C, int64_t WH, EncParams p, int use_lut, int lut_bytes, int *__restrict__ overflow)
 {
+    constexpr bool CONTIG = LAYOUT == 1;
     static_assert(G >= 2 && G <= 32 && (G & (G - 1)) == 0, "G must be a power of two");
     constexpr int NW = G / 2;
     extern __shared__ uint32_t tn_lut[];            // q -> T | N << 16 (term presence / negative-term masks)
@@ -210,38 +218,8 @@ tr_group_kernel(const float *__restrict__ in, Tout *__restrict__ out,
     }
     const uint32_t lut_base = (uint32_t)__cvta_generic_to_shared(tn_lut);
 
-    for (int64_t t = (int64_t)blockIdx.x * GROUP_THREADS + threadIdx.x; t < total;
-         t += (int64_t)gridDim.x * GROUP_THREADS) {
-        int64_t base, stride;
-        if (CONTIG) {
-            base = t * G;
-            stride = 1;
-        } else {
-            const int64_t wh = t % WH;
-            const int64_t bc = t / WH;              // = b * CG + cg
-            base = bc * G * WH + wh;
-            stride = WH;
-        }
-
-        float x[G];
-        if (CONTIG) {
-            constexpr int NV = (G * 4) / 16 ? (G * 4) / 16 : 1;
-            if constexpr (G >= 4) {
-                const int4 *src = reinterpret_cast<const int4 *>(in + base);
-#pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    const int4 raw = __ldcs(src + v);
-                    memcpy(&x[v * 4], &raw, 16);
-                }
-            } else {
-                const float2 raw = __ldcs(reinterpret_cast<const float2 *>(in + base));
-                x[0] = raw.x; x[1] = raw.y;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < G; ++j) x[j] = __ldg(in + base + j * stride);
-        }
-
+    // quantise the g values of one group, find the cut level of its term budget, rebuild the surviving codes
+    auto select = [&](const float (&x)[G], Tout (&y)[G]) {
         uint32_t tn[G];                              // T | N << 16 | sign << 31   (T, N < 2^15)
         const bool relu = p.relu != 0;
         int pc, r;
@@ -308,7 +286,6 @@ tr_group_kernel(const float *__restrict__ in, Tout *__restrict__ out,
         const uint32_t himask = cut ? (0xFFFFu & ~((2u << pc) - 1u)) : 0xFFFFu;
 
         int cnt = 0;
-        Tout y[G];
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             const uint32_t e = tn[j];
@@ -320,6 +297,76 @@ tr_group_kernel(const float *__restrict__ in, Tout *__restrict__ out,
             if constexpr (DEQ) y[j] = dequant<Tout>(code, p.sf);
             else y[j] = pack_code<Tout>(code, ovf);
         }
+    };
+
+    if constexpr (LAYOUT == 2) {
+        // tile = nb blocks of G * WH floats = nb * WH groups (nb * WH <= GROUP_THREADS); fp32 in, fp32 out only
+        float *tile = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(tn_lut) + lut_bytes);
+        const int wh_i = (int)WH, blk_elems = G * wh_i;
+        const int nb_max = GROUP_THREADS / wh_i;
+        const int64_t n_blocks = B * CG;
+        const int64_t n_tiles = (n_blocks + nb_max - 1) / nb_max;
+        for (int64_t tix = blockIdx.x; tix < n_tiles; tix += gridDim.x) {
+            const int64_t blk0 = tix * nb_max;
+            const int nb = (int)((n_blocks - blk0) < nb_max ? (n_blocks - blk0) : nb_max);
+            const int elems = nb * blk_elems;                     // a multiple of 4 (G >= 4) and 16-byte aligned in memory
+            const float *src = in + blk0 * blk_elems;
+            float *dst = reinterpret_cast<float *>(out) + blk0 * blk_elems;
+            for (int i = threadIdx.x * 4; i < elems; i += GROUP_THREADS * 4)
+                *reinterpret_cast<int4 *>(tile + i) = __ldcs(reinterpret_cast<const int4 *>(src + i));
+            __syncthreads();
+            if ((int)threadIdx.x < nb * wh_i) {
+                const int blk = (int)threadIdx.x / wh_i, wh = (int)threadIdx.x % wh_i;
+                float *gp = tile + blk * blk_elems + wh;
+                float x[G];
+#pragma unroll
+                for (int j = 0; j < G; ++j) x[j] = gp[j * wh_i];
+                Tout y[G];
+                select(x, y);
+#pragma unroll
+                for (int j = 0; j < G; ++j) gp[j * wh_i] = (float)y[j];
+            }
+            __syncthreads();
+            for (int i = threadIdx.x * 4; i < elems; i += GROUP_THREADS * 4)
+                __stcs(reinterpret_cast<int4 *>(dst + i), *reinterpret_cast<const int4 *>(tile + i));
+            __syncthreads();
+        }
+        return;
+    }
+    for (int64_t t = (int64_t)blockIdx.x * GROUP_THREADS + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * GROUP_THREADS) {
+        int64_t base, stride;
+        if (CONTIG) {
+            base = t * G;
+            stride = 1;
+        } else {
+            const int64_t wh = t % WH;
+            const int64_t bc = t / WH;              // = b * CG + cg
+            base = bc * G * WH + wh;
+            stride = WH;
+        }
+
+        float x[G];
+        if (CONTIG) {
+            constexpr int NV = (G * 4) / 16 ? (G * 4) / 16 : 1;
+            if constexpr (G >= 4) {
+                const int4 *src = reinterpret_cast<const int4 *>(in + base);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const int4 raw = __ldcs(src + v);
+                    memcpy(&x[v * 4], &raw, 16);
+                }
+            } else {
+                const float2 raw = __ldcs(reinterpret_cast<const float2 *>(in + base));
+                x[0] = raw.x; x[1] = raw.y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < G; ++j) x[j] = __ldg(in + base + j * stride);
+        }
+
+        Tout y[G];
+        select(x, y);
         constexpr int OUT_BYTES = (int)sizeof(Tout) * G;
         if (CONTIG && OUT_BYTES % 16 == 0) {
             int4 *dst = reinterpret_cast<int4 *>(out + base);
@@ -449,13 +496,31 @@ static int launch_group_f32(const void *in, void *out, int64_t B, int64_t C, int
     static const bool no_lut16 = getenv("TQ_GROUP_NO_LUT16") != nullptr;
     if (use_lut && !no_lut16 && p.bits <= 10 && g <= 8 && p.alpha <= 127) use_lut = 2;
     const size_t lut_bytes = use_lut == 2 ? ((size_t)16 << p.bits) : (use_lut ? (sizeof(uint32_t) << p.bits) : 0);
-#define TQ_LAUNCH_GF(GG, CT, FD)                                                                \
-    tr_group_kernel<GG, CT, Tout, DEQ, FD><<<grid, GROUP_THREADS, lut_bytes, s>>>(              \
-        (const float *)in, (Tout *)out, B, C, WH, p, use_lut, overflow)
+    // small planes (conv weights): staged through shared memory.  fp32 -> fp32, g >= 4 (blocks of g * WH floats stay
+    // 16-byte aligned), whole tensor 16-byte aligned
+    static const bool no_staged = getenv("TQ_GROUP_NO_STAGED") != nullptr;
+    const bool staged = !no_staged && !contig && DEQ && std::is_same<Tout, float>::value && WH <= 64 && g >= 4 &&
+                        (((uintptr_t)in | (uintptr_t)out) & 15u) == 0;
+    size_t smem = lut_bytes;
+    int grid_l = grid;
+    if (staged) {
+        const int nb_max = GROUP_THREADS / (int)WH;
+        smem += (size_t)nb_max * g * WH * sizeof(float);
+        const int64_t n_tiles = (B * (C / g) + nb_max - 1) / nb_max;
+        const int64_t cap = (int64_t)num_sms() * 8;
+        grid_l = (int)(n_tiles < cap ? n_tiles : cap);
+        if (use_lut && total * g < (int64_t)grid_l * (8 << p.bits)) { use_lut = 0; smem -= lut_bytes; }
+    }
+    if (smem > 48 * 1024) return fail(TQ_ERR_UNSUPPORTED, "internal: grouped kernel shared memory");
+    const int lutb = (int)(use_lut ? lut_bytes : 0);
+#define TQ_LAUNCH_GF(GG, LY, FD)                                                                \
+    tr_group_kernel<GG, LY, Tout, DEQ, FD><<<grid_l, GROUP_THREADS, smem, s>>>(                 \
+        (const float *)in, (Tout *)out, B, C, WH, p, use_lut, lutb, overflow)
 #define TQ_LAUNCH_G(GG)                                                                         \
     case GG:                                                                                    \
-        if (contig) { if (p.fastdiv) TQ_LAUNCH_GF(GG, true, true); else TQ_LAUNCH_GF(GG, true, false); }   \
-        else        { if (p.fastdiv) TQ_LAUNCH_GF(GG, false, true); else TQ_LAUNCH_GF(GG, false, false); } \
+        if (contig) { if (p.fastdiv) TQ_LAUNCH_GF(GG, 1, true); else TQ_LAUNCH_GF(GG, 1, false); }          \
+        else if (staged && GG >= 4) { if (p.fastdiv) TQ_LAUNCH_GF(GG, (GG >= 4 ? 2 : 0), true); else TQ_LAUNCH_GF(GG, (GG >= 4 ? 2 : 0), false); } \
+        else        { if (p.fastdiv) TQ_LAUNCH_GF(GG, 0, true); else TQ_LAUNCH_GF(GG, 0, false); }          \
         break;
     switch (g) {
         TQ_LAUNCH_G(2)
