@@ -498,8 +498,12 @@ static int launch_group_f32(const void *in, void *out, int64_t B, int64_t C, int
     const size_t lut_bytes = use_lut == 2 ? ((size_t)16 << p.bits) : (use_lut ? (sizeof(uint32_t) << p.bits) : 0);
     // small planes (conv weights): staged through shared memory.  fp32 -> fp32, g >= 4 (blocks of g * WH floats stay
     // 16-byte aligned), whole tensor 16-byte aligned
-    static const bool no_staged = getenv("TQ_GROUP_NO_STAGED") != nullptr;
-    const bool staged = !no_staged && !contig && DEQ && std::is_same<Tout, float>::value && WH <= 64 && g >= 4 &&
+    // MEASURED (B200, 9-bit, g = 8): slower than the strided variant, whose sector over-fetch is absorbed by L1 --
+    // OIHW 512x512x3x3: 735 vs 965 GB/s, 2048x1024x3x3: 2.5 vs 3.5 TB/s (three barriers per 4 KB tile, the term table
+    // rebuilt per CTA for ~4 tiles of work).  Kept as an opt-in experiment (TQ_GROUP_STAGED=1); weights are term-revealed
+    // once per model conversion, not per forward.
+    static const bool want_staged = getenv("TQ_GROUP_STAGED") != nullptr;
+    const bool staged = want_staged && !contig && DEQ && std::is_same<Tout, float>::value && WH <= 64 && g >= 4 &&
                         (((uintptr_t)in | (uintptr_t)out) & 15u) == 0;
     size_t smem = lut_bytes;
     int grid_l = grid;
