@@ -226,8 +226,9 @@ int tq_bn_relu_maxpool_encode(const float *x, const float *bn_a, const float *bn
  * tensor-core kernel with fp32-level accuracy (hi/lo fp16 operand pairs, fp32 accumulation).
  *   x          fp32 NHWC [N, H, W, 3] (H, W even)
  *   x2_scratch 2 * N * (H/2+3) * (W/2+3) * 16 fp16 of scratch (folded hi / lo image planes)
- *   w2         fp16 [8][Cout][64]: rows R = 0..3 of the 8x8-padded kernel folded 2x2, as
- *              (hi, lo) planes (conv_codes.pack_stem_weight builds it); Cout <= 64
+ *   w2         fp16 [4][128][64]: tile R = filter row R of the 8x8-padded kernel folded 2x2 (64 = 4 taps x (2x2x4)
+ *              folded channels); rows 0..Cout-1 of a tile hold the fp16 hi plane of the weights, rows 64..64+Cout-1
+ *              the lo plane (w = hi + lo), the rest zeros (conv_codes.pack_stem_weight builds it); Cout <= 64
  *   out        fp32 NHWC [N, H/2, W/2, Cout]
  */
 int tq_stem_conv7x7s2(const float *x, void *x2_scratch, const void *w2, float *out,

@@ -321,14 +321,14 @@ def bn_relu_maxpool_encode(x_nhwc, bn, relu=True, next_quant=None):
 
 
 def pack_stem_weight(w, channel_sign=None):
-    """(Cout, 3, 7, 7) fp32 -> fp16 [8][Cout][64] for tq_stem_conv7x7s2: the kernel padded to 8x8 and
-    folded 2x2 (r = 2R + dr, s = 2S + ds), row R holding (S, dr, ds, c) with c padded to 4, as the
-    two operand planes (w_hi, w_lo) with w = w_hi + w_lo in fp16 pairs.  `channel_sign` (+1 / -1 per
-    output channel) is folded into the weights (the one-kernel stem pools before the BatchNorm affine and
-    needs non-negative slopes: see stem_conv_pool)."""
+    """(Cout, 3, 7, 7) fp32 -> fp16 [4][128][64] for tq_stem_conv7x7s2: the kernel padded to 8x8 and
+    folded 2x2 (r = 2R + dr, s = 2S + ds), tile R holding (S, dr, ds, c) with c padded to 4; rows 0..Cout-1 of a tile are
+    the fp16 hi plane, rows 64..64+Cout-1 the lo plane (w = w_hi + w_lo), so that one N = 128 MMA multiplies by both.
+    `channel_sign` (+1 / -1 per output channel) is folded into the weights (the one-kernel stem pools before the
+    BatchNorm affine and needs non-negative slopes: see stem_conv_pool)."""
     Cout, Cin, kh, kw = w.shape
-    if (Cin, kh, kw) != (3, 7, 7):
-        raise NotImplementedError("stem conv packing expects a (Cout, 3, 7, 7) weight")
+    if (Cin, kh, kw) != (3, 7, 7) or Cout > 64:
+        raise NotImplementedError("stem conv packing expects a (Cout <= 64, 3, 7, 7) weight")
     w8 = torch.zeros(Cout, 4, 8, 8, dtype=torch.float32, device=w.device)
     w8[:, :3, :7, :7] = w.detach().float()
     if channel_sign is not None:
@@ -337,18 +337,21 @@ def pack_stem_weight(w, channel_sign=None):
     w2 = w8.view(Cout, 4, 4, 2, 4, 2).permute(2, 0, 4, 3, 5, 1).reshape(4, Cout, 64)
     hi = w2.half()
     lo = (w2 - hi.float()).half()
-    return torch.cat([hi, lo], dim=0).contiguous()
+    out = torch.zeros(4, 128, 64, dtype=torch.float16, device=w.device)
+    out[:, :Cout] = hi
+    out[:, 64:64 + Cout] = lo
+    return out.contiguous()
 
 
 _STEM_DTYPES = {torch.float32: _lib.TQ_F32, torch.bfloat16: _lib.TQ_BF16, torch.float16: _lib.TQ_F16}
 
 
-def stem_conv7x7s2(x_nhwc, w2, scratch=None):
+def stem_conv7x7s2(x_nhwc, w2, scratch=None, cout=None):
     """fp32 / bf16 / fp16 [N, H, W, 3] -> fp32 [N, H/2, W/2, Cout] (7x7 / stride 2 / pad 3, no bias)."""
     if x_nhwc.dtype not in _STEM_DTYPES or not x_nhwc.is_contiguous() or x_nhwc.shape[-1] != 3:
         raise RuntimeError("stem_conv7x7s2 expects a contiguous fp32 / bf16 / fp16 [N, H, W, 3] tensor")
     N, H, W, _ = x_nhwc.shape
-    Cout = w2.shape[1]
+    Cout = cout if cout is not None else 64
     need = (2 if x_nhwc.dtype == torch.float32 else 1) * N * (H // 2 + 3) * (W // 2 + 3) * 16
     if scratch is None or scratch.numel() < need:
         scratch = torch.empty(need, dtype=torch.float16, device=x_nhwc.device)
@@ -371,6 +374,7 @@ def stem_pool_operands(w, bn):
 
 
 def stem_conv_pool(x_nhwc, w2, bn, relu=True, next_quant=None, scratch=None):
+    # (Cout = number of BatchNorm channels: the packed weight tile is always 128 rows)
     """The whole stem in one launch: maxpool3x3/s2/p1(relu(fma(conv7x7s2(x), a, b))) -> fp32
     [N, Hp, Wp, Cout] plus the fp16 term codes of the result (next_quant = (sf, bits, terms)).
     Same values as stem_conv7x7s2 followed by bn_relu_maxpool_encode; the conv output never reaches HBM.
@@ -379,7 +383,7 @@ def stem_conv_pool(x_nhwc, w2, bn, relu=True, next_quant=None, scratch=None):
     if x_nhwc.dtype not in _STEM_DTYPES or not x_nhwc.is_contiguous() or x_nhwc.shape[-1] != 3:
         raise RuntimeError("stem_conv_pool expects a contiguous fp32 / bf16 / fp16 [N, H, W, 3] tensor")
     N, H, W, _ = x_nhwc.shape
-    Cout = w2.shape[1]
+    Cout = bn[0].numel()
     need = (2 if x_nhwc.dtype == torch.float32 else 1) * N * (H // 2 + 3) * (W // 2 + 3) * 16
     if scratch is None or scratch.numel() < need:
         scratch = torch.empty(need, dtype=torch.float16, device=x_nhwc.device)

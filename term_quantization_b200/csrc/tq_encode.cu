@@ -331,8 +331,8 @@ tr_group_kernel(const float *__restrict__ in, Tout *__restrict__ out,
                 __stcs(reinterpret_cast<int4 *>(dst + i), *reinterpret_cast<const int4 *>(tile + i));
             __syncthreads();
         }
-        return;
     }
+    if constexpr (LAYOUT != 2)
     for (int64_t t = (int64_t)blockIdx.x * GROUP_THREADS + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * GROUP_THREADS) {
         int64_t base, stride;

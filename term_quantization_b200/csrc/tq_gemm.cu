@@ -42,7 +42,6 @@
 //   TQ_CONV_N256=1                             BLOCK_N = 256 tiles where Cout % 256 == 0 (slower on ResNet shapes)
 //   TQ_CONV_HALO_BASEOFF=1                     set the UMMA descriptor base-offset field in halo mode (WRONG results:
 //                                              kept as the record of how the swizzle was found to be address-based)
-//   TQ_STEM_GROUPS=1..3                        accumulator groups of the hi/lo stem conv (accuracy vs TMEM reads)
 #include <cuda.h>
 
 #include <cstdlib>
@@ -82,6 +81,7 @@ struct ConvGeom {
     // as integers when acc_int.  KIND 1: planes_a x planes_w signed 8-bit planes (stacked along the image / tap
     // dimension of the operand tensors), plane pair (pa, pw) accumulates into group pa + pw; kblk = channels per block.
     int kcpg, acc_int, planes_a, planes_w, kblk;
+    int b_rows;                                 // rows of a resident weight tile when it is not BLOCK_N (MODE 2: 128)
     int dbg_skip_epilogue;      // profiling aid (TQ_CONV_SKIP_EPI=1): drain accumulators without storing
     int dbg_skip_mma, dbg_skip_tma;   // TQ_CONV_SKIP_MMA / TQ_CONV_SKIP_TMA: isolate the load and the MMA pipelines
     // MODE 2 step table, one packed word per (A plane, filter row), planes stacked along N (coordinate
@@ -334,7 +334,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                       const __grid_constant__ CUtensorMap tmR, const __grid_constant__ ConvGeom g)
 {
     static_assert(KIND == 0 || MODE == 0, "the s8-plane engine streams both operands (MODE 0)");
-    constexpr int B_BYTES = BLOCK_N * GM_ROW_BYTES;
+    // MODE 2 (hi/lo stem conv): a resident weight tile stacks the hi plane (rows 0..63) on the lo plane (rows 64..127) and
+    // ONE N = 128 MMA computes x * w_hi into accumulator columns [c, c + 64) and x * w_lo into [c + 64, c + 128): 64 cycles
+    // instead of two N = 64 MMAs at 57 each.  The epilogue's view stays BLOCK_N = 64 output channels, four column groups.
+    constexpr int MMA_N = MODE == 2 ? 2 * BLOCK_N : BLOCK_N;
+    constexpr int B_BYTES = MMA_N * GM_ROW_BYTES;
     const int STAGES = g.stages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -482,7 +486,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // instruction descriptor: both operands K-major, N = BLOCK_N, M = 128;  KIND 0: D = F32 (bits 4-5 = 1),
         // A = B = F16 (0);  KIND 1: D = S32 (2), A = B = signed 8-bit (a_format bits 7-9 = 1, b_format bits 10-12 = 1)
         constexpr uint32_t IDESC = (KIND == 1 ? ((2u << 4) | (1u << 7) | (1u << 10)) : (1u << 4)) |
-                                   ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(GM_BLOCK_M >> 4) << 24);
+                                   ((uint32_t)(MMA_N >> 3) << 17) | ((uint32_t)(GM_BLOCK_M >> 4) << 24);
         constexpr uint64_t DESC_HI = ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
         if (elect_one()) {
             int stage = 0;
@@ -955,7 +959,7 @@ static bool pick_box_halo(ConvGeom &g)
 // carve shared memory: [stationary B][stage ring][2 x epilogue staging][LUT][barriers]
 static int plan_smem(ConvGeom &g, int block_n)
 {
-    const int b_bytes = block_n * GM_ROW_BYTES;
+    const int b_bytes = (g.b_rows > 0 ? g.b_rows : block_n) * GM_ROW_BYTES;   // (MODE 2 stacks hi | lo: 2 * block_n rows per tile)
     const bool prog = g.prog_steps > 0;
     g.stage_bytes = GM_A_BYTES + (prog ? 0 : b_bytes);
     if (g.halo) g.stage_bytes = (g.a_tx_bytes + 1023) & ~1023;
@@ -1532,16 +1536,15 @@ static int stem_impl(const void *x, int x_dtype, void *x2_scratch, const void *w
     g.write_f32 = 1;
     g.next_sf = out_codes ? next_sf : 1.0f; g.next_bits = out_codes ? next_bits : 1; g.next_terms = next_terms;
     g.next_fastdiv = (g.next_sf >= 9.313225746154785e-10f && g.next_sf <= 1073741824.0f) ? 1 : 0;
-    // program: per filter row R one load of x_hi (MMAs against w_hi -> main accumulator, w_lo -> cross
-    // accumulator) and one of x_lo (w_hi -> cross).  The main accumulator is split in two (rows 0-1 / 2-3):
-    // tensor-core accumulation truncates, so fewer steps per accumulator = less bias; the small cross terms
-    // live apart from the large ones and everything is summed once, in fp32 RN, in the epilogue.
-    static const int stem_groups = getenv("TQ_STEM_GROUPS") ? atoi(getenv("TQ_STEM_GROUPS")) : 3;
-    g.prog_steps = lo_plane ? 8 : 4; g.nb_tiles = 8; g.n_groups = stem_groups < 1 ? 1 : (stem_groups > 3 ? 3 : stem_groups);
-    const uint32_t g_main1 = g.n_groups >= 3 ? 1u : 0u, g_cross = (uint32_t)(g.n_groups - 1);
+    // program: per image plane (x_hi, and x_lo for fp32 images) ONE halo load covering the four folded filter rows; per
+    // filter row R one N = 128 MMA group against the resident tile R = [w_hi (rows 0..63) ; w_lo (rows 64..127)]: columns
+    // [c, c+64) of the accumulator receive x * w_hi, [c+64, c+128) x * w_lo.  Rows 0-1 and rows 2-3 accumulate apart
+    // (c = 0 / 128): tensor-core accumulation truncates, so fewer steps per accumulator = less bias, and the small lo
+    // products live apart from the large ones; the four 64-column groups are summed once, in fp32 RN, in the epilogue.
+    g.prog_steps = lo_plane ? 8 : 4; g.nb_tiles = 4; g.n_groups = 4; g.b_rows = 128;
     for (uint32_t R = 0; R < 4; ++R) {
-        g.prog_mma[R] = 2u | (R << 4) | ((R < 2 ? 0u : g_main1) << 8) | ((4u + R) << 12) | (g_cross << 16);
-        g.prog_mma[4 + R] = 1u | (R << 4) | (g_cross << 8);
+        g.prog_mma[R] = 1u | (R << 4) | ((R < 2 ? 0u : 2u) << 8);
+        g.prog_mma[4 + R] = g.prog_mma[R];                  // x_lo against the same tiles (x_lo * w_lo is 2^-22: harmless)
     }
 
     CUtensorMap tmA, tmB, tmC, tmD;
@@ -1559,8 +1562,8 @@ static int stem_impl(const void *x, int x_dtype, void *x2_scratch, const void *w
         if (r != CUDA_SUCCESS) return fail(TQ_ERR_CUDA, "cuTensorMapEncodeTiled(stem windows) failed: %d", (int)r);
     }
     {
-        cuuint64_t dims[3] = {64, (cuuint64_t)Cout, 8};
-        cuuint32_t box[3] = {64, (cuuint32_t)block_n, 1};
+        cuuint64_t dims[3] = {64, 128, 4};
+        cuuint32_t box[3] = {64, 128, 1};
         cuuint32_t one[3] = {1, 1, 1};
         if ((rc = encode_map(enc, &tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w2, 3, dims, box, one, "stem weights")) != TQ_OK) return rc;
     }

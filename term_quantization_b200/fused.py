@@ -158,7 +158,7 @@ class FusedResNet(nn.Module):
                         scratch=self._stem_scratch)
                 else:
                     y, self._stem_scratch = conv_codes.stem_conv7x7s2(x.permute(0, 2, 3, 1), self.stem_w,
-                                                                      self._stem_scratch)
+                                                                      self._stem_scratch, cout=m.conv1.out_channels)
                     cur, c0 = conv_codes.bn_relu_maxpool_encode(y, self.stem_bn, relu=True, next_quant=q0)
             else:
                 y = m.conv1(x.float()).permute(0, 2, 3, 1)
