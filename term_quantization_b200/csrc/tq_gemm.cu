@@ -265,6 +265,18 @@ __device__ __forceinline__ void epi_affine(float (&t)[32], const ConvGeom &g, in
 
 // residual add (the staging tile holds the residual), ReLU, fp32 tile and / or term codes into the staging tiles.
 // RELU: the values are >= 0 afterwards, so the encode needs neither |x| nor the sign half of the table.
+// Written as PHASES over the 32 values of the chunk, each behind ONE uniform branch (ncu, round 2: with the flags tested
+// inside the per-4-value loop the chunk cost 37 SASS instructions per value against ~12 of arithmetic).  The fused
+// encode always uses the hoisted-reciprocal divide: the host refuses next_sf outside [2^-30, 2^30] (check_conv_args).
+// Table lookup: after the two round-down adds the quantised value sits in the mantissa of t = 2^23 + q, i.e.
+// bits = 0x4B000000 + q, so the byte address of entry (q | sign << bits) is 2 * bits + const: one IMAD + one LDS.
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr)
+{
+    uint16_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr));      // the table is read-only after the prologue barrier
+    return v;
+}
+
 template <bool RELU>
 __device__ __forceinline__ void epi_stage(float (&t)[32], const ConvGeom &g, uint8_t *st_f32, uint8_t *st_codes, int row,
                                           bool has_res, const __half *lut, const Quant &nq)
@@ -272,43 +284,49 @@ __device__ __forceinline__ void epi_stage(float (&t)[32], const ConvGeom &g, uin
     const uint32_t sw128 = (uint32_t)(row & 7);             // 16B piece index ^= row % 8
     const uint32_t sw64 = (uint32_t)((row >> 1) & 3);       // 16B piece index ^= (row / 2) % 4
     uint8_t *frow = st_f32 + row * 128, *crow = st_codes + row * 64;
-    const bool wf = g.write_f32 != 0, wc = g.write_codes != 0, fast = g.next_fastdiv != 0;
-    const uint32_t nbits = (uint32_t)g.next_bits;
-    uint32_t cw[4];                                         // 8 codes = one 16-byte piece
+    if (has_res) {                                          // rows / channels outside the tensor arrive as zeros
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-        float4 *slot = reinterpret_cast<float4 *>(frow + (((uint32_t)(j >> 2) ^ sw128) << 4));
-        if (has_res) {
-            const float4 r = *slot;                         // rows / channels outside the tensor arrive as zeros
+        for (int j = 0; j < 32; j += 4) {
+            const float4 r = *reinterpret_cast<const float4 *>(frow + (((uint32_t)(j >> 2) ^ sw128) << 4));
             t[j] = __fadd_rn(t[j], r.x); t[j + 1] = __fadd_rn(t[j + 1], r.y);
             t[j + 2] = __fadd_rn(t[j + 2], r.z); t[j + 3] = __fadd_rn(t[j + 3], r.w);
         }
-        if (RELU) {
+    }
+    if (RELU) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) t[j + e] = fmaxf(t[j + e], 0.0f);
-            if (g.relu6) {
+        for (int j = 0; j < 32; ++j) t[j] = fmaxf(t[j], 0.0f);          // NaN -> 0
+        if (g.relu6) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) t[j + e] = fminf(t[j + e], 6.0f);
-            }
+            for (int j = 0; j < 32; ++j) t[j] = fminf(t[j], 6.0f);
         }
-        if (wf) *slot = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
-        if (wc) {
-            uint32_t hc[4];
+    }
+    if (g.write_f32) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                uint32_t idx;
-                if (RELU) {
-                    idx = fast ? quantize_f32_nonneg<true>(t[j + e], nq) : quantize_f32_nonneg<false>(t[j + e], nq);
-                } else {
-                    const uint32_t neg = __float_as_uint(t[j + e]) >> 31;
-                    idx = (fast ? quantize_f32<true>(t[j + e], nq) : quantize_f32<false>(t[j + e], nq)) | (neg << nbits);
-                }
-                hc[e] = __half_as_ushort(lut[idx]);
+        for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4 *>(frow + (((uint32_t)(j >> 2) ^ sw128) << 4)) = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
+    }
+    if (g.write_codes) {
+        // entry address = lut + 2 * (q | sign << bits), q = bits(t) - 0x4B000000
+        const uint32_t lut_s = smem_u32(lut) - 2u * 0x4B000000u;
+        const uint32_t sign_off = 2u << g.next_bits;        // byte offset of the negative half of the table
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            uint32_t hc[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float x = t[j + e];
+                float r;
+                if (RELU) r = div_rn_nonneg<true>(x, nq);               // already >= 0 and not NaN
+                else r = div_rn_nonneg<true>(fmaxf(fabsf(x), 0.0f), nq);
+                r = fminf(r, nq.maxv);
+                float q = __fadd_rd(r, 0.5f);
+                q = __fadd_rd(q, 8388608.0f);
+                uint32_t addr = __float_as_uint(q) * 2u + lut_s;
+                if (!RELU) addr += (__float_as_uint(x) >> 31) * sign_off;
+                hc[e] = lds_u16(addr);
             }
-            const int hi = (j >> 2) & 1;
-            cw[2 * hi] = hc[0] | (hc[1] << 16);
-            cw[2 * hi + 1] = hc[2] | (hc[3] << 16);
-            if (hi) *reinterpret_cast<uint4 *>(crow + (((uint32_t)(j >> 3) ^ sw64) << 4)) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+            *reinterpret_cast<uint4 *>(crow + (((uint32_t)(j >> 3) ^ sw64) << 4)) =
+                make_uint4(hc[0] | (hc[1] << 16), hc[2] | (hc[3] << 16), hc[4] | (hc[5] << 16), hc[6] | (hc[7] << 16));
         }
     }
 }
@@ -1268,6 +1286,9 @@ static int check_conv_args(const void *act, const void *wgt, const void *out_f32
         if (!(next_sf > 0.0f) || !(next_sf < INFINITY)) return fail(TQ_ERR_INVALID, "next_sf must be positive and finite");
         if (next_bits < 1 || next_bits > GM_LUT_MAX_BITS) return fail(TQ_ERR_UNSUPPORTED, "fused encode supports 1..%d bits", GM_LUT_MAX_BITS);
         if (next_terms < 0) return fail(TQ_ERR_INVALID, "next_terms must be >= 0");
+        // the fused encode divides with the hoisted reciprocal (tq_common.cuh), exact for 2^-30 <= sf <= 2^30
+        if (!(next_sf >= 9.313225746154785e-10f && next_sf <= 1073741824.0f))
+            return fail(TQ_ERR_UNSUPPORTED, "fused encode needs 2^-30 <= next_sf <= 2^30 (got %g): encode with tq_tr_encode_codes instead", (double)next_sf);
     }
     return TQ_OK;
 }
