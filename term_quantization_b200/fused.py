@@ -243,6 +243,10 @@ class FusedVGG(nn.Module):
     @torch.no_grad()
     def forward(self, x):
         m = self.model
+        if not torch.cuda.is_current_stream_capturing():
+            for kind, payload in self.stages:
+                if kind == "conv":
+                    payload[0].check_fresh()
         x = x.float().contiguous(memory_format=torch.channels_last)
         convs = [k for k, (kind, _) in enumerate(self.stages) if kind == "conv"]
         q0 = self.stages[convs[0]][1][0].quant
@@ -367,6 +371,14 @@ class FusedMobileNet(nn.Module):
     @torch.no_grad()
     def forward(self, x, capture=None):
         m = self.model
+        if not torch.cuda.is_current_stream_capturing():
+            for expand, dw, proj, _ in self.blocks:
+                for c in (expand, proj):
+                    if c is not None:
+                        c.check_fresh()
+                if _quant_key(dw.layer) != dw.quant:
+                    raise RuntimeError("the wrapped model was re-calibrated after fusing: build the fused executor again")
+            self.last.check_fresh()
         x = x.contiguous(memory_format=torch.channels_last)
         y = self.stem_conv(x.float()).permute(0, 2, 3, 1)                       # fp32 NHWC (channels_last memory)
         first = self.blocks[0][0] or self.blocks[0][1]
