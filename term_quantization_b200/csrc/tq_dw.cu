@@ -322,6 +322,9 @@ extern "C" int tq_depthwise3x3_codes(const void *act_codes, const int32_t *wgt_c
     tl.tiles_w = (p.Wo + tl.tw - 1) / tl.tw;
     tl.tiles_h = (p.Ho + tl.th - 1) / tl.th;
     const int cbsz = (C % 64 == 0) ? 64 : 32;               // odd multiples of 32 (and 8/16/24-channel maps): half-width tiles
+    // a 32-channel tile of 8 x 16 pixels is only 128 work items for 256 threads (ncu: 44 % of the stall samples at the
+    // end-of-tile barrier): twice the rows where the stage still fits (stride 1)
+    if (cbsz == 32 && stride == 1 && tl.th == 8 && p.Ho > 8) { tl.th = 16; tl.tiles_h = (p.Ho + tl.th - 1) / tl.th; }
     tl.cblocks = (C + cbsz - 1) / cbsz;
     tl.in_w = tl.tw * stride + 2;
     tl.in_h = tl.th * stride + 2;

@@ -1562,9 +1562,12 @@ static int stem_impl(const void *x, int x_dtype, void *x2_scratch, const void *w
     // [c, c+64) of the accumulator receive x * w_hi, [c+64, c+128) x * w_lo.  Rows 0-1 and rows 2-3 accumulate apart
     // (c = 0 / 128): tensor-core accumulation truncates, so fewer steps per accumulator = less bias, and the small lo
     // products live apart from the large ones; the four 64-column groups are summed once, in fp32 RN, in the epilogue.
-    g.prog_steps = lo_plane ? 8 : 4; g.nb_tiles = 4; g.n_groups = 4; g.b_rows = 128;
+    // TQ_STEM_SPLIT=0: all four filter rows into ONE accumulator pair (2 column groups, half the TMEM reads of the
+    // epilogue, three accumulator stages) at the price of 16 instead of 8 truncating accumulation steps
+    static const int split_rows = getenv("TQ_STEM_SPLIT") ? atoi(getenv("TQ_STEM_SPLIT")) : 1;
+    g.prog_steps = lo_plane ? 8 : 4; g.nb_tiles = 4; g.n_groups = split_rows ? 4 : 2; g.b_rows = 128;
     for (uint32_t R = 0; R < 4; ++R) {
-        g.prog_mma[R] = 1u | (R << 4) | ((R < 2 ? 0u : 2u) << 8);
+        g.prog_mma[R] = 1u | (R << 4) | (((R < 2 || !split_rows) ? 0u : 2u) << 8);
         g.prog_mma[4 + R] = g.prog_mma[R];                  // x_lo against the same tiles (x_lo * w_lo is 2^-22: harmless)
     }
 
