@@ -11,10 +11,13 @@ unquantised fp32 arithmetic but also runs on the tensor cores (hi/lo fp16 operan
 accumulate: conv_codes.stem_conv7x7s2; `stem="cudnn"` keeps cuDNN's fp32 conv); its BatchNorm + ReLU +
 max-pool + first encode are one pass.  Global average pool and the classifier stay on PyTorch.
 
-Numerics: integer accumulators are exact; the BatchNorm affine is evaluated as
-fma(t, a, b) with a = weight * rsqrt(var + eps), b = fma(-mean, a, bias), which is within 1-2 ulp
-of cuDNN's inference BatchNorm but not bit-identical (tools/bn_probe*.py), so a value sitting on
-a quantisation boundary can round differently than in the unfused path.
+Numerics: every conv's accumulator is the exact int32 accumulator of the integer contraction -- by a static proof
+from the weight codes (kind::f16 MMAs with K-chunk accumulators) or on the kind::i8 plane engine
+(conv_codes.plan_weight; include/tq_b200.h "EXACTNESS CONTRACT") -- and every step of the epilogue is one IEEE fp32
+operation (fl32(acc) * scale, fmaf(t, a, b) with a = weight * rsqrt(var + eps), b = fmaf(-mean, a, bias), + residual,
+ReLU, the reference's quantise / HESE / truncate), so the whole chain is reproduced bit for bit by
+oracle/fused_emul.py on a CPU (tests/test_layers_gpu.py).  Against the reference's own float path (cuDNN fp32 conv and
+BatchNorm, 1-2 ulp from fmaf) a value sitting on a quantisation boundary can round differently.
 """
 import torch
 import torch.nn as nn

@@ -23,7 +23,7 @@ ncu -i $O/r2_prof_conv.ncu-rep --page source --csv --print-source sass -s 0 -c 1
 rm -f $O/r2_prof_conv.ncu-rep
 fi
 if [ "$WHAT" = all ] || [ "$WHAT" = i8 ]; then
-I="env TQ_PROBE_TIMEOUT=900 python tools/hang_probe.py 256 i8"
+I="env TQ_PROBE_TIMEOUT=900 python tools/forward_probe.py 256 i8"
 $I > $O/r2_i8_plain.log 2>&1 &&
 ncu --set full --clock-control none -k regex:conv_igemm -s 21 -c 19 -o $O/r2_prof_i8 -f $I > $O/r2_ncu_i8.log 2>&1
 ncu -i $O/r2_prof_i8.ncu-rep --page raw --csv > $O/r2_i8_raw.csv 2>/dev/null
