@@ -777,85 +777,86 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if constexpr (MODE == 2) {
                     if (g.pool) {
                         // ---- fused BatchNorm + ReLU + 3x3 / stride 2 / pad 1 max-pool + next-layer encode (stem) ----
-                        // Tile = 8 rows x 16 columns of conv pixels (accumulator row m = 16 y + x: warp w holds conv rows
-                        // 2w and 2w+1, one per half-warp), stepping by 6 x 14: it yields 3 x 7 pooled pixels, pooled
-                        // (p, q) covering conv rows 2p..2p+2 and columns 2q..2q+2.  The window maximum of the RAW conv sums
-                        // is taken in registers: columns with two warp shuffles (x+1, x+2 stay inside the half-warp for
-                        // the x <= 13 that are used), rows 2w / 2w+1 with one shuffle by 16, and only the third row comes
-                        // from the next warp through shared memory (7 x 32 values per warp instead of staging all 128 x 32
-                        // and re-reading each nine times -- ncu, round 2: that version spent 49 instructions per conv
-                        // value, 0.37 ms per forward).  Conv pixels outside the image take no part (-inf).  The affine,
-                        // ReLU and encode then run ONCE per pooled value, redistributed over all 128 threads.  max
-                        // commutes with the affine because bn_a >= 0 here: the host folds sign(bn_a) into the weights of
-                        // the channel (exact), so max_i fma(x_i, a, b) = fma(max_i(sign(a) x_i), |a|, b).
-                        uint8_t *xch = st_f32;                                       // [4 warps][7][32] fp32 boundary rows
-                        uint8_t *st_pool = st_codes, *st_pcodes = st_codes + 4096;   // [21][32] fp32 (SW128) / fp16 (SW64) tiles
-                        const int x = lane & 15, y = 2 * ew + (lane >> 4);
-                        const int oh = th * g.step_h + g.off_h + y, ow = tw * g.step_w + g.off_w + x;
-                        const bool inside = (unsigned)oh < (unsigned)g.Ho && (unsigned)ow < (unsigned)g.Wo;
+                        // The tile is the (2P+1) x (2Q+1) box of conv pixels under P x Q pooled pixels.  The RAW conv
+                        // sums are staged; the pooling threads take the window maximum out of shared memory (window
+                        // positions outside the conv output are replaced by the centre, which always exists) and only
+                        // then apply fma(., bn_a, bn_b), ReLU and the encode -- once per pooled value instead of once
+                        // per conv value.  max commutes with the affine because bn_a >= 0 here: the host folds
+                        // sign(bn_a) into the weights of the channel (exact: products and truncated sums negate
+                        // exactly), so max_i fma(x_i, a, b) = fma(max_i(sign(a) x_i), |a|, b).
+                        // (the conv staging tile is never read by TMA; the previous tile's pooling reads of it
+                        // finished before that tile's last group barrier)
+                        {
+                            uint8_t *frow = st_f32 + mrow * 128;
+                            const uint32_t sw = (uint32_t)(mrow & 7);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float v = inside ? t[j] : -INFINITY;
-                            v = fmaxf(v, fmaxf(__shfl_down_sync(0xFFFFFFFFu, v, 1), __shfl_down_sync(0xFFFFFFFFu, v, 2)));
-                            t[j] = v;                                                // max over columns x .. x+2 (x <= 13)
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4 *>(frow + (((uint32_t)(j >> 2) ^ sw) << 4)) =
+                                    make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
                         }
-                        const bool qlane = (x & 1) == 0 && x <= 12;                  // lanes holding a pooled column q = x / 2
-                        const int q = x >> 1;
-                        // the first conv row of warps 1..3 is the third window row of the warp above
-                        if (ew > 0 && lane < 16 && qlane) {
-                            float4 *dst = reinterpret_cast<float4 *>(xch + ((ew * 7 + q) << 7));
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) dst[j >> 2] = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) t[j] = fmaxf(t[j], __shfl_down_sync(0xFFFFFFFFu, t[j], 16));   // rows 2w, 2w+1
-                        // the pooled staging tiles are free once this group's previous TMA store has read them
-                        if (store_thread) bulk_wait_read0();
                         epi_bar_sync(1 + grp);
-                        if (ew < 3 && lane < 16 && qlane) {
-                            const float4 *src = reinterpret_cast<const float4 *>(xch + (((ew + 1) * 7 + q) << 7));
-                            const int pp = ew * 7 + q;                               // pooled pixel of the tile, row-major 3 x 7
-                            const uint32_t psw = (uint32_t)(pp & 7);
+                        uint8_t *st_pool = st_codes, *st_pcodes = st_codes + 4096;   // [P*Q][32] fp32 / fp16 tiles
+                        const int pp = mrow >> 2, cb = mrow & 3;                     // pooled pixel, 8-channel block
+                        float pv[8];
+                        const bool pool_thread = pp < g.pool_p * g.pool_q;
+                        if (pool_thread) {
+                            const int pl = pp / g.pool_q, ql = pp % g.pool_q;
+                            // conv pixel of window position (dy, dx): (2 (p0 + pl) - 1 + dy, 2 (q0 + ql) - 1 + dx)
+                            const int oh0 = 2 * (th * g.pool_p + pl) - 1, ow0 = 2 * (tw * g.pool_q + ql) - 1;
+                            int rowoff[3], coloff[3];
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 r = src[j >> 2];
-                                *reinterpret_cast<float4 *>(st_pool + pp * 128 + (((uint32_t)(j >> 2) ^ psw) << 4)) =
-                                    make_float4(fmaxf(t[j], r.x), fmaxf(t[j + 1], r.y), fmaxf(t[j + 2], r.z), fmaxf(t[j + 3], r.w));
+                            for (int d = 0; d < 3; ++d) {
+                                rowoff[d] = (2 * pl + (((unsigned)(oh0 + d) < (unsigned)g.Ho) ? d : 1)) * g.hw;
+                                coloff[d] = 2 * ql + (((unsigned)(ow0 + d) < (unsigned)g.Wo) ? d : 1);
                             }
-                        }
-                        epi_bar_sync(1 + grp);
-                        // affine + ReLU + encode, four channels per work item, 21 x 8 items over the 128 threads of the group
-                        for (int item = ew * 32 + lane; item < 21 * 8; item += 128) {
-                            const int pp = item >> 3, c4 = item & 7;
-                            float4 *slot = reinterpret_cast<float4 *>(st_pool + pp * 128 + (((uint32_t)c4 ^ (uint32_t)(pp & 7)) << 4));
-                            const float4 raw = *slot;
-                            float pv[4] = {raw.x, raw.y, raw.z, raw.w};
-                            const int cc4 = c0 + 4 * c4;
-                            uint32_t hc[4] = {0u, 0u, 0u, 0u};
-                            if (cc4 < g.Cout) {                                      // Cout % 8 == 0
-                                const float4 a = __ldg(reinterpret_cast<const float4 *>(g.bn_a + cc4));
-                                const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bn_b + cc4));
-                                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+                            float4 m0 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), m1 = m0;
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) {
+                            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                                for (int dx = 0; dx < 3; ++dx) {
+                                    const int mm = rowoff[dy] + coloff[dx];
+                                    const uint32_t sw = (uint32_t)(mm & 7);
+                                    const float4 a = *reinterpret_cast<const float4 *>(st_f32 + mm * 128 + (((uint32_t)(2 * cb) ^ sw) << 4));
+                                    const float4 b = *reinterpret_cast<const float4 *>(st_f32 + mm * 128 + (((uint32_t)(2 * cb + 1) ^ sw) << 4));
+                                    m0.x = fmaxf(m0.x, a.x); m0.y = fmaxf(m0.y, a.y); m0.z = fmaxf(m0.z, a.z); m0.w = fmaxf(m0.w, a.w);
+                                    m1.x = fmaxf(m1.x, b.x); m1.y = fmaxf(m1.y, b.y); m1.z = fmaxf(m1.z, b.z); m1.w = fmaxf(m1.w, b.w);
+                                }
+                            pv[0] = m0.x; pv[1] = m0.y; pv[2] = m0.z; pv[3] = m0.w; pv[4] = m1.x; pv[5] = m1.y; pv[6] = m1.z; pv[7] = m1.w;
+                            const int c8 = c0 + 8 * cb;
+                            if (c8 < g.Cout) {                                        // Cout % 8 == 0
+                                const float4 a0 = __ldg(reinterpret_cast<const float4 *>(g.bn_a + c8));
+                                const float4 a1 = __ldg(reinterpret_cast<const float4 *>(g.bn_a + c8 + 4));
+                                const float4 b0 = __ldg(reinterpret_cast<const float4 *>(g.bn_b + c8));
+                                const float4 b1 = __ldg(reinterpret_cast<const float4 *>(g.bn_b + c8 + 4));
+                                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
                                     pv[e] = __fmaf_rn(pv[e], av[e], bv[e]);
                                     if (RELU) pv[e] = fmaxf(pv[e], 0.0f);
                                 }
-                                if (g.write_codes) {
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        uint32_t idx;
-                                        if (RELU) idx = g.next_fastdiv ? quantize_f32_nonneg<true>(pv[e], nq) : quantize_f32_nonneg<false>(pv[e], nq);
-                                        else idx = (g.next_fastdiv ? quantize_f32<true>(pv[e], nq) : quantize_f32<false>(pv[e], nq)) |
-                                                   ((__float_as_uint(pv[e]) >> 31) << g.next_bits);
-                                        hc[e] = __half_as_ushort(lut[idx]);
-                                    }
-                                }
                             }
-                            *slot = make_float4(pv[0], pv[1], pv[2], pv[3]);
-                            if (g.write_codes)
-                                *reinterpret_cast<uint2 *>(st_pcodes + pp * 64 + (((uint32_t)(c4 >> 1) ^ (uint32_t)((pp >> 1) & 3)) << 4) + (c4 & 1) * 8) =
-                                    make_uint2(hc[0] | (hc[1] << 16), hc[2] | (hc[3] << 16));
+                        }
+                        // the pooled staging tiles are free once this group's previous TMA store has read them
+                        if (store_thread) bulk_wait_read0();
+                        epi_bar_sync(1 + grp);
+                        if (pool_thread) {
+                            const uint32_t psw = (uint32_t)(pp & 7);
+                            *reinterpret_cast<float4 *>(st_pool + pp * 128 + (((uint32_t)(2 * cb) ^ psw) << 4)) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+                            *reinterpret_cast<float4 *>(st_pool + pp * 128 + (((uint32_t)(2 * cb + 1) ^ psw) << 4)) = make_float4(pv[4], pv[5], pv[6], pv[7]);
+                            if (g.write_codes) {
+                                uint32_t hc[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    uint32_t idx;
+                                    if (RELU) idx = g.next_fastdiv ? quantize_f32_nonneg<true>(pv[e], nq) : quantize_f32_nonneg<false>(pv[e], nq);
+                                    else idx = (g.next_fastdiv ? quantize_f32<true>(pv[e], nq) : quantize_f32<false>(pv[e], nq)) |
+                                               ((__float_as_uint(pv[e]) >> 31) << g.next_bits);
+                                    hc[e] = __half_as_ushort(lut[idx]);
+                                }
+                                *reinterpret_cast<uint4 *>(st_pcodes + pp * 64 + (((uint32_t)cb ^ (uint32_t)((pp >> 1) & 3)) << 4)) =
+                                    make_uint4(hc[0] | (hc[1] << 16), hc[2] | (hc[3] << 16), hc[4] | (hc[5] << 16), hc[6] | (hc[7] << 16));
+                            }
                         }
                         fence_proxy_async();
                         epi_bar_sync(1 + grp);
@@ -1528,17 +1529,21 @@ static int stem_impl(const void *x, int x_dtype, void *x2_scratch, const void *w
         if (!pick_box_halo(g)) return fail(TQ_ERR_UNSUPPORTED, "stem conv: no tile shape");
         g.step_w = g.wbox; g.step_h = g.hbox;
     } else {
-        // pooled tile: 3 x 7 pooled pixels out of 8 x 16 conv pixels (row 7 and column 15 are computed but unused): the
-        // power-of-two row pitch keeps every pooling window's columns inside a half-warp and its first two rows inside a
-        // warp, so the epilogue takes the window maximum with shuffles (see the kernel)
+        // pooled tile P x Q over the (2P+1) x (2Q+1) conv pixels it needs (<= 128 accumulator rows): fewest tiles
         Hp = (Ho + 2 - 3) / 2 + 1; Wp = (Wo + 2 - 3) / 2 + 1;
+        long best = -1;
+        for (int P = 1; P <= Hp && 2 * P + 1 <= 128; ++P)
+            for (int Q = 1; Q <= Wp && (2 * P + 1) * (2 * Q + 1) <= 128; ++Q) {
+                const long tiles = (long)((Hp + P - 1) / P) * ((Wp + Q - 1) / Q);
+                if (best < 0 || tiles < best || (tiles == best && Q > g.pool_q)) { best = tiles; g.pool_p = P; g.pool_q = Q; }
+            }
         g.pool = 1;
-        g.pool_p = 3; g.pool_q = 7;
-        g.wbox = 16; g.hbox = 8; g.nbox = 1;
+        g.wbox = 2 * g.pool_q + 1; g.hbox = 2 * g.pool_p + 1; g.nbox = 1;
         g.step_w = 2 * g.pool_q; g.step_h = 2 * g.pool_p; g.off_w = -1; g.off_h = -1;
         g.tiles_w = (Wp + g.pool_q - 1) / g.pool_q; g.tiles_h = (Hp + g.pool_p - 1) / g.pool_p; g.tiles_n = N;
         g.m_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
         g.a_tx_bytes = g.wbox * g.hbox * GM_BLOCK_K * 2;
+        if (g.pool_p * g.pool_q > 32) return fail(TQ_ERR_UNSUPPORTED, "pooled tile too large");
         g.bn_a = bn_a; g.bn_b = bn_b; g.relu = relu ? 1 : 0;
         g.write_codes = out_codes ? 1 : 0;
         if (out_codes) {
