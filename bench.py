@@ -381,6 +381,39 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
     assert bool(torch.isfinite(host_logits).all())
+    # ---- e2e with uint8 images: 1 byte per value over PCIe, ToTensor + Normalize on the device --------------------
+    e2e_u8 = None
+    if args.conv_backend == "fused" and not args.no_e2e_uint8:
+        front = inference.U8Frontend(model)
+        runner8 = inference.ShardedInference(front, dev, cuda_graphs=use_graphs, gather=args.gather)
+        host8 = [torch.randint(0, 256, (BATCH, 224, 224, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        a0 = runner8.stage(host8[0])
+        a1 = runner8.stage(host8[1])
+        for i in range(max(args.warmup, 3)):
+            nxt = runner8.stage(host8[i % 2])
+            runner8.run(a0)
+            a0, a1 = a1, nxt
+        runner8.finish()
+        barrier()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record()
+        for i in range(args.steps):
+            nxt = runner8.stage(host8[i % 2])
+            host_logits8 = runner8.run(a0)
+            a0, a1 = a1, nxt
+        runner8.finish()
+        u1.record()
+        barrier()
+        t = torch.tensor([u0.elapsed_time(u1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert bool(torch.isfinite(host_logits8).all())
+        e2e_u8 = {"value": BATCH * world * args.steps / (float(t.item()) * 1e-3), "unit": "images/s",
+                  "ms_per_step": float(t.item()) / args.steps,
+                  "h2d_bytes_per_step": BATCH * 224 * 224 * 3 * world, "d2h_bytes_per_step": int(host_logits8.numel()) * 4 * world,
+                  "note": "same engine fed uint8 NHWC images; ((u8 / 255) - mean) / std as the reference loader computes it "
+                          "(util.py:12-27), on the device (tq_u8_normalize_bf16), rounded to the bf16 the engine consumes"}
+        del runner8, front
     # what the box allows: the same host -> device copies alone, all ranks at once (max over ranks)
     import bench_extra
     barrier()
@@ -460,6 +493,7 @@ def run_b200(args):
                     "h2d_ceiling_images_per_s": BATCH * world / (h2d_only_ms * 1e-3),
                     "h2d_ceiling_note": "the same pinned-host -> device copies with no compute, all ranks at once, max over ranks: "
                                         "the e2e number cannot exceed this on this box"},
+            **({"e2e_uint8": e2e_u8} if e2e_u8 else {}),
             "gpu_launches": int(launches),
             "clocks": clocks,
             **({"per_rank": per_rank} if per_rank else {}),
@@ -577,6 +611,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=16, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip tr_grid / kernel_to_beat / other_configs")
+    ap.add_argument("--no-e2e-uint8", action="store_true", help="skip the additional end-to-end measurement with uint8 images")
     ap.add_argument("--conv-engine", default="auto", choices=["auto", "f16", "i8"],
                     help="how the exact accumulator is obtained per layer (conv_codes.plan_weight): auto = kind::f16 where "
                          "proven from the weights, kind::i8 planes otherwise")

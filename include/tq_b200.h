@@ -280,6 +280,14 @@ int tq_bn_act_encode(const float *x, const float *bn_a, const float *bn_b, float
                      int64_t npix, int C, int relu, float next_sf, int next_bits, int next_terms, void *stream);
 
 /*
+ * uint8 NHWC images [npix][3] -> normalised bf16 [npix][3]: ((u8 / 255) - mean[c]) / std[c], each step one fp32 IEEE
+ * operation as torchvision's ToTensor + Normalize compute it on the host (util.py:12-27), then rounded to bf16 -- the
+ * image dtype of the fused engine.  mean3 / std3 are HOST arrays of 3 floats.  npix % 4 == 0.
+ */
+int tq_u8_normalize_bf16(const void *x_u8, void *y_bf16, int64_t npix, const float *mean3, const float *std3,
+                         void *stream);
+
+/*
  * Device self-test: quantises n pseudo-random (a, sf) pairs (sf in [2^-30, 2^30], a over all
  * non-negative floats and the quantiser's rounding boundaries) with the hoisted-reciprocal
  * divide and with div.rn.f32 and adds the number of disagreements to *mismatch (device).

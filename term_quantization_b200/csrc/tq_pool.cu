@@ -107,3 +107,54 @@ extern "C" int tq_bn_relu_maxpool_encode(const float *x, const float *bn_a, cons
     count_launch();
     return check_launch("bn_relu_maxpool3x3s2_kernel");
 }
+
+
+// =============================================================================================
+// uint8 images -> normalised bf16: what torchvision's ToTensor + Normalize compute on the host in fp32
+// (util.py:12-27: x = u8 / 255, then (x - mean[c]) / std[c]), rounded to the bf16 the fused engine consumes.
+// Lets a batch cross PCIe as 1 byte per value instead of 2 (bf16) or 4 (the reference's fp32 loader, util.py:54).
+// =============================================================================================
+namespace tq {
+
+__global__ void __launch_bounds__(256)
+u8_normalize_bf16_kernel(const uint8_t *__restrict__ x, __nv_bfloat16 *__restrict__ y, int64_t npix4,
+                         float m0, float m1, float m2, float s0, float s1, float s2)
+{
+    // 4 pixels (12 bytes in, 24 bytes out) per thread: channel of byte k is k % 3
+    const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < npix4; t += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(x) + t * 3;
+        const uint32_t w[3] = {__ldg(src), __ldg(src + 1), __ldg(src + 2)};
+        __align__(8) __nv_bfloat16 out[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const float v = __fdiv_rn((float)((w[k >> 2] >> (8 * (k & 3))) & 0xFFu), 255.0f);
+            out[k] = __float2bfloat16_rn(__fdiv_rn(__fsub_rn(v, mean[k % 3]), sd[k % 3]));
+        }
+        uint2 *dst = reinterpret_cast<uint2 *>(y + t * 12);
+        dst[0] = reinterpret_cast<const uint2 *>(out)[0];
+        dst[1] = reinterpret_cast<const uint2 *>(out)[1];
+        dst[2] = reinterpret_cast<const uint2 *>(out)[2];
+    }
+}
+
+}  // namespace tq
+
+extern "C" int tq_u8_normalize_bf16(const void *x_u8, void *y_bf16, int64_t npix, const float *mean3, const float *std3,
+                                    void *stream)
+{
+    if (!x_u8 || !y_bf16 || !mean3 || !std3) return fail(TQ_ERR_INVALID, "NULL pointer");
+    if (npix < 0 || npix % 4 != 0) return fail(TQ_ERR_INVALID, "pixel count must be a multiple of 4");
+    if ((((uintptr_t)x_u8 & 3u) | ((uintptr_t)y_bf16 & 7u)) != 0) return fail(TQ_ERR_INVALID, "pointers must be 4 / 8-byte aligned");
+    for (int c = 0; c < 3; ++c)
+        if (!(std3[c] > 0.0f)) return fail(TQ_ERR_INVALID, "std must be positive");
+    if (npix == 0) return TQ_OK;
+    const int64_t n4 = npix / 4;
+    int64_t blocks = (n4 + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    u8_normalize_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const uint8_t *)x_u8, (__nv_bfloat16 *)y_bf16, n4,
+                                                                          mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
+    count_launch();
+    return check_launch("u8_normalize_bf16_kernel");
+}

@@ -43,6 +43,40 @@ def bind_to_gpu_numa_node(device_index):
         return None
 
 
+IMAGENET_MEAN = (0.485, 0.456, 0.406)            # util.py:12-13
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def normalize_u8(x_u8_nhwc, mean=IMAGENET_MEAN, std=IMAGENET_STD, out=None):
+    """uint8 [N, H, W, 3] CUDA images -> bf16 [N, 3, H, W] view in channels_last memory holding
+    ((u8 / 255) - mean) / std (the reference loader's ToTensor + Normalize, util.py:12-27, on the device)."""
+    import ctypes
+    from . import _lib
+    if x_u8_nhwc.dtype != torch.uint8 or not x_u8_nhwc.is_cuda or not x_u8_nhwc.is_contiguous() or x_u8_nhwc.shape[-1] != 3:
+        raise RuntimeError("normalize_u8 expects a contiguous uint8 CUDA [N, H, W, 3] tensor")
+    if out is None:
+        out = torch.empty(x_u8_nhwc.shape, dtype=torch.bfloat16, device=x_u8_nhwc.device)
+    m = (ctypes.c_float * 3)(*mean)
+    s = (ctypes.c_float * 3)(*std)
+    with torch.cuda.device(x_u8_nhwc.device):
+        rc = _lib.lib().tq_u8_normalize_bf16(x_u8_nhwc.data_ptr(), out.data_ptr(), x_u8_nhwc.numel() // 3,
+                                             ctypes.cast(m, ctypes.c_void_p), ctypes.cast(s, ctypes.c_void_p),
+                                             torch.cuda.current_stream(x_u8_nhwc.device).cuda_stream)
+    _lib.check(rc)
+    return out.permute(0, 3, 1, 2)
+
+
+class U8Frontend(torch.nn.Module):
+    """model(normalize_u8(images)): lets batches cross PCIe as uint8 (1 byte per value)."""
+
+    def __init__(self, model, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+        super().__init__()
+        self.model, self.mean, self.std = model, tuple(mean), tuple(std)
+
+    def forward(self, x_u8_nhwc):
+        return self.model(normalize_u8(x_u8_nhwc, self.mean, self.std))
+
+
 def shard_bounds(n_items, world_size, rank):
     """Contiguous [lo, hi) slice of rank `rank`; the first n % world ranks hold one extra."""
     base, extra = divmod(n_items, world_size)

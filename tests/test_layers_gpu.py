@@ -549,3 +549,17 @@ def test_linear_and_lstm_input_projection_on_tensor_cores():
     for a, b in ((y, y_ref), (h, h_ref), (c, c_ref)):
         assert a.shape == b.shape
         assert float((a - b).abs().max()) <= 1e-5 * max(float(b.abs().max()), 1.0), float((a - b).abs().max())
+
+
+def test_u8_normalize_matches_torchvision_arithmetic():
+    """tq_u8_normalize_bf16 = ToTensor + Normalize (util.py:12-27) in fp32, rounded to bf16; U8Frontend feeds a model."""
+    from term_quantization_b200 import inference
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randint(0, 256, (3, 20, 12, 3), device="cuda", dtype=torch.uint8, generator=g)
+    got = inference.normalize_u8(x)
+    mean = torch.tensor(inference.IMAGENET_MEAN, device="cuda")
+    std = torch.tensor(inference.IMAGENET_STD, device="cuda")
+    want = ((x.float() / 255.0 - mean) / std).bfloat16().permute(0, 3, 1, 2)
+    assert got.shape == want.shape and torch.equal(got, want)
+    net = torch.nn.Conv2d(3, 4, 3).cuda().bfloat16()
+    assert torch.equal(inference.U8Frontend(net)(x), net(want))
