@@ -42,19 +42,25 @@ def select_engine(qmodel, engine):
     """How the calibrated model runs the validation pass.
     'float'   -- the reference's path: TR kernels + cuDNN fp32 conv on dequantised tensors (tr_layer.py:124-126);
     'tcgen05' -- every supported wrapped conv on integer term codes with the tcgen05 kernel, module tree unchanged;
-    'fused'   -- fused.FusedResNet (BasicBlock ResNets): BN / residual / ReLU / next encode in the conv epilogue;
-    'auto'    -- 'fused' where the topology allows it, else 'tcgen05'."""
+    'fused'   -- the fused executor of the architecture (fused.FusedResNet for BasicBlock ResNets, fused.FusedVGG,
+                 fused.FusedMobileNet): BN / residual / ReLU(6) / next encode in the conv epilogue, depthwise convs code
+                 to code;
+    'auto'    -- 'fused' where the topology allows it, else 'tcgen05'.
+    On the tensor-core engines every conv's accumulator is exact by contract (conv_codes.plan_weight)."""
     if engine == "float":
         return qmodel
     from . import fused
     qmodel = qmodel.to(memory_format=torch.channels_last)
-    switched, skipped = tr_layer.use_tensor_cores(qmodel)
     if engine in ("fused", "auto"):
-        try:
-            return fused.FusedResNet(qmodel)
-        except (NotImplementedError, AttributeError):
-            if engine == "fused":
-                raise
+        errors = []
+        for cls in (fused.FusedResNet, fused.FusedVGG, fused.FusedMobileNet):
+            try:
+                return cls(qmodel)
+            except (NotImplementedError, AttributeError, IndexError, TypeError) as e:
+                errors.append(f"{cls.__name__}: {e}")
+        if engine == "fused":
+            raise NotImplementedError("no fused executor for this architecture: " + "; ".join(errors))
+    tr_layer.use_tensor_cores(qmodel)
     return qmodel
 
 
