@@ -34,7 +34,8 @@
 // TMA store).
 //
 // Measurement / experiment switches (environment, read once; none is needed in normal use):
-//   TQ_CONV_SKIP_EPI / _SKIP_MMA / _SKIP_TMA   run without the epilogue / the MMAs / the TMA loads (results are garbage):
+//   TQ_CONV_SKIP_EPI / _SKIP_MMA / _SKIP_TMA   run without the epilogue / the MMAs / the TMA loads (results are garbage;
+//                                              SKIP_TMA=2 / 4 in the streamed-weight halo mode: no weight / no halo loads):
 //                                              isolates which pipeline paces a layer (tools/conv_microbench.py)
 //   TQ_CONV_STAGES=n, TQ_CONV_ASTAGES=n        cap the stage ring / set the halo-buffer ring depth (MODE 4)
 //   TQ_CONV_WBOX / TQ_CONV_HBOX                force the pixel box of MODE 0 tiles
@@ -443,13 +444,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const int nb0 = n_tile * BLOCK_N;
                     for (int kc = 0; kc < kcb; ++kc) {
                         mbar_wait(&aempty_bar[as], aph ^ 1u);
+                        if (g.dbg_skip_tma == 4) {                      // TQ_CONV_SKIP_TMA=4: no halo loads (isolation run)
+                            mbar_arrive(&afull_bar[as]);
+                        } else {
                         mbar_expect_tx(&afull_bar[as], (uint32_t)g.a_tx_bytes);
                         tma_load_4d(&tmA, &afull_bar[as], bstat + as * g.a_stage_bytes, kc * GM_BLOCK_K, w_in0, h_in0, tn);
+                        }
                         if (++as == a_stages) { as = 0; aph ^= 1u; }
                         for (int tap = 0; tap < taps; ++tap) {
                             mbar_wait(&empty_bar[bs], bph ^ 1u);
+                            if (g.dbg_skip_tma == 2) {                  // TQ_CONV_SKIP_TMA=2: no weight loads (isolation run)
+                                mbar_arrive(&full_bar[bs]);
+                            } else {
                             mbar_expect_tx(&full_bar[bs], (uint32_t)B_BYTES);
                             tma_load_3d(&tmB, &full_bar[bs], ring + bs * B_BYTES, kc * GM_BLOCK_K, nb0, tap);
+                            }
                             if (++bs == STAGES) { bs = 0; bph ^= 1u; }
                         }
                     }
@@ -1015,9 +1024,10 @@ static int launch_conv_mode(const CUtensorMap &tmA, const CUtensorMap &tmB, cons
 {
     static const bool skip_epi = getenv("TQ_CONV_SKIP_EPI") != nullptr;
     g.dbg_skip_epilogue = skip_epi ? 1 : 0;
-    static const bool skip_mma = getenv("TQ_CONV_SKIP_MMA") != nullptr, skip_tma = getenv("TQ_CONV_SKIP_TMA") != nullptr;
+    static const bool skip_mma = getenv("TQ_CONV_SKIP_MMA") != nullptr;
+    static const int skip_tma = getenv("TQ_CONV_SKIP_TMA") ? atoi(getenv("TQ_CONV_SKIP_TMA")) : 0;
     g.dbg_skip_mma = skip_mma ? 1 : 0;
-    g.dbg_skip_tma = skip_tma ? 1 : 0;
+    g.dbg_skip_tma = skip_tma;
     auto kern = g.relu ? conv_igemm_kernel<BLOCK_N, MODE, true, KIND> : conv_igemm_kernel<BLOCK_N, MODE, false, KIND>;
     static bool attr_set[2][64] = {{false}};
     int dev = 0;

@@ -107,8 +107,12 @@ def use_tensor_cores(model, enable=True, engine="auto"):
         if isinstance(layer, TRConv2dLayer):
             why = layer.tensor_core_blocker() if enable else None
             if why is None:
-                layer.use_tensor_cores(enable, engine)
-                switched.append(name)
+                try:
+                    layer.use_tensor_cores(enable, engine)
+                    switched.append(name)
+                except NotImplementedError as e:      # no engine can run this layer exactly (e.g. unprovable and C % 16 != 0)
+                    layer.use_tensor_cores(False)
+                    skipped.append((name, str(e)))
             else:
                 skipped.append((name, why))
         elif isinstance(layer, (TRLinearLayer, TRLSTMLayer)):
