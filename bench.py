@@ -602,7 +602,7 @@ def main():
                          "unchanged torchvision graph; cudnn_fp32: the reference's float path")
     ap.add_argument("--input-dtype", default="bf16", choices=["bf16", "fp32"],
                     help="dtype of the image batches in HBM and over PCIe (fused engine; bf16 per BASELINE configs[1])")
-    ap.add_argument("--stem", default="tcgen05_pool", choices=["tcgen05", "tcgen05_pool", "cudnn"],
+    ap.add_argument("--stem", default="tcgen05", choices=["tcgen05", "tcgen05_pool", "cudnn"],
                     help="fused engine: two-launch tensor-core stem, one-kernel stem (pooling in the conv epilogue), cuDNN")
     ap.add_argument("--gather", default="step", choices=["step", "async", "end"],
                     help="when the other ranks' logits are collected (inference.ShardedInference)")

@@ -247,8 +247,8 @@ def test_fused_resnet_matches_unfused_tensor_core_path():
         f = fused.FusedResNet(q)                                # stem conv on the tensor cores too
         assert f.stem_w is not None
         got_tc_stem = f(x)
-        # the two-launch stem is bit-identical to the default one-kernel stem (pooling in the conv epilogue)
-        assert torch.equal(fused.FusedResNet(q, stem="tcgen05")(x), got_tc_stem)
+        # the one-kernel stem (pooling in the conv epilogue) is bit-identical to the default two-launch stem
+        assert torch.equal(fused.FusedResNet(q, stem="tcgen05_pool")(x), got_tc_stem)
         # 16-bit images are used as they are: same logits as their fp32 upcast
         xb = x.bfloat16()
         assert torch.equal(f(xb), f(xb.float()))
@@ -458,7 +458,7 @@ def test_fused_resnet34_odd_resolution():
         assert len(switched) == 35 and not skipped
         unfused = q(x.contiguous(memory_format=torch.channels_last))
         a = fused.FusedResNet(q)(x)
-        b = fused.FusedResNet(q, stem="tcgen05")(x)
+        b = fused.FusedResNet(q, stem="tcgen05_pool")(x)
         c = fused.FusedResNet(q, stem="cudnn")(x)
     scale = float(unfused.abs().max())
     assert torch.equal(a, b)
