@@ -125,6 +125,35 @@ def _time_model(fn, iters, warmup=3):
     return e0.elapsed_time(e1) / iters
 
 
+def _time_graphed(fn, iters, warmup=3):
+    """ms per call of fn() replayed as ONE CUDA graph (like the headline engine); falls back to eager launches when the
+    capture fails.  Returns (ms, 'cuda graph' | 'eager')."""
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            fn()
+        for _ in range(2):
+            graph.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters, "cuda graph"
+    except Exception:
+        torch.cuda.synchronize()
+        return _time_model(fn, iters, warmup), "eager"
+
+
 def other_configs(dev):
     """BASELINE.json configs[0], [2], [3], [4] on one GPU: units/s with inputs resident in HBM (synthetic, random init)."""
     import torchvision
@@ -176,19 +205,22 @@ def other_configs(dev):
     with torch.no_grad():
         mlp(xm)
         tr_layer.set_tr_tracking(mlp, False)
-        n0 = _lib.launch_count()
-        ms = _time_model(lambda: mlp(xm), 20)
+        ms, how = _time_graphed(lambda: mlp(xm), 20)
+        ms_eager = _time_model(lambda: mlp(xm), 20)
         tr_layer.use_tensor_cores(mlp)                      # linear(q(x)) on term codes, tcgen05 (non-strict semantics)
+        mlp(xm)
         n1 = _lib.launch_count()
-        ms_tc = _time_model(lambda: mlp(xm), 20)
-        l_tc = (_lib.launch_count() - n1) // 23
+        mlp(xm)
+        l_tc = _lib.launch_count() - n1
+        ms_tc, how_tc = _time_graphed(lambda: mlp(xm), 20)
+        ms_tc_eager = _time_model(lambda: mlp(xm), 20)
     out["mlp_b256"] = {"workload": "MNIST MLP 784-512-512-10 TQ (wb 4, g=8, alpha=12, db 6), batch 256",
-                       "engine": "tcgen05 on term codes: linear(q(x)), exact int32 accumulators", "ms_per_step": ms_tc,
-                       "value": 256 / ms_tc * 1e3, "unit": "images/s", "gpu_launches_per_step": l_tc,
+                       "engine": "tcgen05 on term codes: linear(q(x)), exact int32 accumulators; " + how_tc, "ms_per_step": ms_tc,
+                       "value": 256 / ms_tc * 1e3, "unit": "images/s", "gpu_launches_per_step": l_tc, "ms_per_step_eager": ms_tc_eager,
                        "strict_reference_path": {"what": "tr_layer.py:152-154 as shipped: the quantised input is discarded, cuBLAS fp32 "
-                                                         "linear on the raw input with term-revealed weights",
-                                                 "ms_per_step": ms, "value": 256 / ms * 1e3},
-                       "note": "launch-latency bound (0.17 MMAC per image)"}
+                                                         "linear on the raw input with term-revealed weights; " + how,
+                                                 "ms_per_step": ms, "value": 256 / ms * 1e3, "ms_per_step_eager": ms_eager},
+                       "note": "launch-latency bound (0.17 MMAC per image): eager launches cost more than the arithmetic"}
 
     # configs[4]: LSTM 650/650 tied, vocab 33,278, seq 35 x batch 80, wb 8 / g 8 / alpha 12 / db 8 (evaluate_lstm.sh:4)
     torch.manual_seed(0)
@@ -200,20 +232,24 @@ def other_configs(dev):
         lstm(tokens, hidden)
         tr_layer.set_tr_tracking(lstm, False)
         n0 = _lib.launch_count()
-        ms = _time_model(lambda: lstm(tokens, hidden), 10)
+        lstm(tokens, hidden)
+        l_strict = _lib.launch_count() - n0
+        ms, how = _time_graphed(lambda: lstm(tokens, hidden), 10)
         tr_layer.use_tensor_cores(lstm)
+        lstm(tokens, hidden)
         n1 = _lib.launch_count()
-        ms_tc = _time_model(lambda: lstm(tokens, hidden), 10)
-        l_tc = (_lib.launch_count() - n1) // 13
+        lstm(tokens, hidden)
+        l_tc = _lib.launch_count() - n1
+        ms_tc, how_tc = _time_graphed(lambda: lstm(tokens, hidden), 10)
     out["lstm_35x80"] = {"workload": "Wikitext-2-shaped LSTM 650/650 tied, TQ on layer-0 gates and decoder (wb 8, g=8, alpha=12, db 8), "
                                      "seq 35 x batch 80",
                          "engine": "tcgen05 on term codes: layer-0 input projection W_ih.q(emb) and the 650 -> 33,278 decoder "
-                                   "linear(q(x)) (60.6 GMAC per step), exact int32 accumulators; recurrence step-wise, layer 1 cuDNN",
+                                   "linear(q(x)) (60.6 GMAC per step), exact int32 accumulators; recurrence step-wise, layer 1 cuDNN; " + how_tc,
                          "ms_per_step": ms_tc, "value": 35 * 80 / ms_tc * 1e3, "unit": "tokens/s", "gpu_launches_per_step": l_tc,
                          "strict_reference_path": {"what": "the reference forward as shipped: cuDNN LSTM on quantised emb / h0 / c0, "
                                                            "decoder = cuBLAS fp32 linear on the RAW input (tr_layer.py:152-154)",
-                                                   "ms_per_step": ms, "value": 35 * 80 / ms * 1e3,
-                                                   "gpu_launches_per_step": (n1 - n0) // 13}}
+                                                   "ms_per_step": ms, "value": 35 * 80 / ms * 1e3, "timed_as": how,
+                                                   "gpu_launches_per_step": l_strict}}
     return out
 
 
