@@ -1,5 +1,5 @@
-"""One small launch of every kernel added in round 2, for `compute-sanitizer --tool memcheck python tools/sanitize_smoke.py`
-(one tool per gpurun call; tiny shapes: memcheck slows kernels 10-50x)."""
+"""One small launch of every kernel added in round 2 on ragged shapes (written for `compute-sanitizer --tool memcheck`,
+which is closed on this GPU pool; as a plain run it still exercises every new launch path with synchronous error checks)."""
 import os
 import sys
 
