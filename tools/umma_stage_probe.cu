@@ -15,7 +15,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 
-template <int MMAS, int STAGES, bool SPIN>
+template <int MMAS, int STAGES, bool SPIN, int AROW>
 __global__ void __launch_bounds__(640, 1) probe(int stages_total, long long *out)
 {
     extern __shared__ uint8_t raw[];
@@ -59,13 +59,14 @@ __global__ void __launch_bounds__(640, 1) probe(int stages_total, long long *out
         for (int i = 0; i < stages_total; ++i) {
             mbar_wait(&full[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t da = DESC_HI | a_lo, db = DESC_HI | (a_lo + (16384u >> 4));
+            // AROW: the A operand starts AROW 128-byte rows into the swizzled buffer (the halo modes' row-offset views)
+            const uint64_t da = DESC_HI | (a_lo + (uint32_t)(AROW * 8)), db = DESC_HI | (a_lo + (20480u >> 4));
 #pragma unroll
             for (int k = 0; k < MMAS; ++k)
                 asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                              ::"r"(tmem), "l"(da + (uint64_t)(2 * (k & 3))), "l"(db + (uint64_t)(2 * (k & 3))), "r"(IDESC), "r"((uint32_t)(i | k)) : "memory");
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
-            a_lo += 32768u >> 4;
+            a_lo += 40960u >> 4;
             if (++s == STAGES) { s = 0; ph ^= 1u; a_lo = a_lo0; }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&done)) : "memory");
@@ -81,24 +82,24 @@ __global__ void __launch_bounds__(640, 1) probe(int stages_total, long long *out
     if (threadIdx.x >= 64 && threadIdx.x < 96) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
-template <int MMAS, int STAGES, bool SPIN>
+template <int MMAS, int STAGES, bool SPIN, int AROW = 0>
 static void run()
 {
     long long *d, h[2] = {0, 0};
     cudaMalloc(&d, 16);
-    cudaFuncSetAttribute(probe<MMAS, STAGES, SPIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024);
+    cudaFuncSetAttribute(probe<MMAS, STAGES, SPIN, AROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024);
     const int stages_total = 4096 / MMAS * 4;
-    for (int rep = 0; rep < 2; ++rep) probe<MMAS, STAGES, SPIN><<<1, 640, 168 * 1024>>>(stages_total, d);
+    for (int rep = 0; rep < 2; ++rep) probe<MMAS, STAGES, SPIN, AROW><<<1, 640, 168 * 1024>>>(stages_total, d);
     cudaError_t e = cudaDeviceSynchronize();
     cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-    printf("N=128: %2d MMAs per stage, %d ring stages, idle warps %s: %.1f cycles per MMA, %.0f per stage  %s\n", MMAS, STAGES,
-           SPIN ? "spinning" : "parked ", (double)h[0] / (stages_total * MMAS), (double)h[0] / stages_total, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    printf("N=128: %2d MMAs per stage, %d ring stages, A row offset %2d, idle warps %s: %.1f cycles per MMA, %.0f per stage  %s\n", MMAS, STAGES,
+           AROW, SPIN ? "spinning" : "parked ", (double)h[0] / (stages_total * MMAS), (double)h[0] / stages_total, e == cudaSuccess ? "" : cudaGetErrorString(e));
     cudaFree(d);
 }
 
 int main()
 {
-    run<4, 4, false>(); run<4, 4, true>(); run<8, 4, false>(); run<8, 4, true>(); run<16, 4, true>(); run<4, 2, true>(); run<4, 8, true>();
-    run<2, 4, true>(); run<1, 4, true>();
+    run<4, 4, false>(); run<4, 4, true>(); run<8, 4, false>(); run<8, 4, true>(); run<16, 4, true>(); run<4, 2, true>();
+    run<4, 4, true, 1>(); run<4, 4, true, 3>(); run<4, 4, true, 31>(); run<8, 4, true, 1>(); run<8, 4, true, 31>(); run<16, 4, true, 31>();
     return 0;
 }
