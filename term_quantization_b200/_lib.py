@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtq_b200.so")
+# TQ_B200_LIB: another build of the same C ABI (the instrumented debug build of tools/conv_trace.sh)
+LIB_PATH = os.environ.get("TQ_B200_LIB") or os.path.join(_HERE, "libtq_b200.so")
 
 TQ_OK, TQ_ERR_INVALID, TQ_ERR_UNSUPPORTED, TQ_ERR_CUDA = 0, 1, 2, 3
 TQ_F32, TQ_F64, TQ_BF16, TQ_F16 = 0, 1, 2, 3

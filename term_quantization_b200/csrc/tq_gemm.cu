@@ -43,6 +43,9 @@
 //   TQ_CONV_N256=1                             BLOCK_N = 256 tiles where Cout % 256 == 0 (slower on ResNet shapes)
 //   TQ_CONV_HALO_BASEOFF=1                     set the UMMA descriptor base-offset field in halo mode (WRONG results:
 //                                              kept as the record of how the swizzle was found to be address-based)
+#ifdef TQ_CONV_TRACE
+#include <cstdio>
+#endif
 #include <cuda.h>
 
 #include <cstdlib>
@@ -68,6 +71,7 @@ struct ConvGeom {
     int step_w, step_h, off_w, off_h;           // tile origin in output pixels: (tw * step_w + off_w, th * step_h + off_h)
     int pool, pool_p, pool_q;                   // fused 3x3/s2/p1 max-pool (stem): pooled pixels per tile
     int halo, halo_baseoff;                     // halo mode (MODE 3); whether to set the descriptor's base-offset field
+    int pair;                                   // MODE 4 on CTA pairs (cta_group::2): two M tiles per MMA, half a weight tile per CTA
     int tiles_w, tiles_h, tiles_n;              // M tiles along w, h, image
     int m_tiles, n_tiles, kc_blocks;
     int a_tx_bytes;                             // bytes one A box deposits
@@ -173,10 +177,76 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t 
     if constexpr (KIND == 1) umma_i8(tmem_d, desc_a, desc_b, idesc, accumulate);
     else umma_f16(tmem_d, desc_a, desc_b, idesc, accumulate);
 }
+// ---- CTA pair (cta_group::2): two CTAs of a cluster on one TPC run ONE tcgen05.mma of M = 256 -- each supplies the A rows
+// of its own M tile and HALF of the B tile (N / 2 rows), so per CTA the weight traffic from L2 and the B reads from shared
+// memory are halved.  The leader (cluster rank 0) issues every MMA and commit; loads of both CTAs complete on the leader's
+// barriers, commits arrive on the same barrier of both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// loads into this CTA's shared memory whose bytes complete on a barrier of either CTA of the pair
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap *map, uint32_t bar_cluster, void *dst, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap *map, uint32_t bar_cluster, void *dst, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives (once the MMAs issued so far have retired) on the same barrier of BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// -DTQ_CONV_TRACE (debug builds only, tools/conv_trace.sh): per-role cycle accounting with clock64, printed by two CTAs
+#ifdef TQ_CONV_TRACE
+#define TR_DECL(n) long long trc[n] = {}
+#define TR(slot, ...) do { const long long _t = clock64(); __VA_ARGS__; trc[slot] += clock64() - _t; } while (0)
+#define TR_T0(name) const long long name = clock64()
+#define TR_SINCE(slot, name) trc[slot] += clock64() - name
+#else
+#define TR_DECL(n)
+#define TR(slot, ...) do { __VA_ARGS__; } while (0)
+#define TR_T0(name)
+#define TR_SINCE(slot, name)
+#endif
+
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32])
 {
     asm volatile(
@@ -346,13 +416,15 @@ __device__ __forceinline__ void epi_stage(float (&t)[32], const ConvGeom &g, uin
 // RELU: the epilogue's ReLU flag as a compile-time constant (the encode after a ReLU needs no sign handling; a
 // run-time branch would duplicate the staging code inside one kernel and cost instruction-cache misses).
 // KIND: 0 = fp16 codes, kind::f16, fp32 accumulators; 1 = s8 planes, kind::i8, s32 accumulators (MODE 0 only).
-template <int BLOCK_N, int MODE, bool RELU, int KIND>
+// CG: 1 = one CTA per tile; 2 = CTA pair (MODE 4 only): the pair takes two M tiles of the same N tile, see the helpers above.
+template <int BLOCK_N, int MODE, bool RELU, int KIND, int CG = 1>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD,
                       const __grid_constant__ CUtensorMap tmR, const __grid_constant__ ConvGeom g)
 {
     static_assert(KIND == 0 || MODE == 0, "the s8-plane engine streams both operands (MODE 0)");
+    static_assert(CG == 1 || (MODE == 4 && KIND == 0), "the CTA pair runs the streamed-weight halo mode");
     // MODE 2 (hi/lo stem conv): a resident weight tile stacks the hi plane (rows 0..63) on the lo plane (rows 64..127) and
     // ONE N = 128 MMA computes x * w_hi into accumulator columns [c, c + 64) and x * w_lo into [c + 64, c + 128): 64 cycles
     // instead of two N = 64 MMAs at 57 each.  The epilogue's view stays BLOCK_N = 64 output channels, four column groups.
@@ -376,7 +448,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int acc_cols = g.n_groups * BLOCK_N;          // TMEM columns of one accumulator stage
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = g.m_tiles * g.n_tiles;
+    // Tile walk.  CG 1: CTA b takes tiles b, b + grid, ...; tile = m_tile * n_tiles + n_tile.  CG 2: pair p = b / 2 takes
+    // "super tiles" p, p + grid / 2, ...; super tile = (m_tile / 2) * n_tiles + n_tile and CTA rank r of the pair owns
+    // m_tile = 2 * (super / n_tiles) + r.  With an odd number of M tiles the last one has no partner: the partner CTA runs
+    // a tile whose image index is out of range -- its TMA loads are zero-filled and its TMA stores dropped.
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+    const int tile_first = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int total_tiles = CG == 2 ? ((g.m_tiles + 1) / 2) * g.n_tiles : g.m_tiles * g.n_tiles;
+    auto m_tile_of = [&](int tile) { return CG == 2 ? 2 * (tile / g.n_tiles) + (int)cta_rank : tile / g.n_tiles; };
     const int kblocks = g.R * g.S * g.kc_blocks * (KIND == 1 ? g.planes_a * g.planes_w : 1);
     // accumulator stages in TMEM: three when they fit the 512 columns (the MMA issuer may then run two tiles ahead of
     // an epilogue that holds its accumulator until the last chunk is in registers), else two; a tile with four K chunks
@@ -406,17 +486,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_init(bfull_bar, 1);
         // an accumulator stage is drained by two epilogue groups (256 threads); with a single stage all four groups
         // drain every tile (a quarter of the columns each)
-        for (int i = 0; i < 3; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], ACC_STAGES == 1 ? 512 : 256); }
+        // (CTA pair: the leader's barrier also collects the partner's epilogue threads)
+        for (int i = 0; i < 3; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], (ACC_STAGES == 1 ? 512 : 256) * CG); }
         for (int i = 0; i < GM_EPI_GROUPS; ++i) mbar_init(&res_bar[i], 1);
         for (int i = 0; i < 4; ++i) { mbar_init(&afull_bar[i], 1); mbar_init(&aempty_bar[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (CG == 2) {                            // the same warp of both CTAs, same destination offset
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();              // the partner's barriers are initialised before anything arrives on them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -433,17 +520,67 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 mbar_expect_tx(bfull_bar, (uint32_t)(g.nb_tiles * B_BYTES));
                 for (int t = 0; t < g.nb_tiles; ++t) tma_load_3d(&tmB, bfull_bar, bstat + t * B_BYTES, 0, 0, t);
             }
-            if constexpr (MODE == 4) {
+            if constexpr (MODE == 4 && CG == 2) {
+                // CTA pair: this CTA's halo box and its half (rows cta_rank * 64 ..) of every weight tile, TWO filter taps
+                // per ring stage (eight MMAs per hand-shake).  All bytes complete on the LEADER's full barriers, which the
+                // leader arms with the byte count of both CTAs; a slot is free when the leader's multicast commit has
+                // arrived on this CTA's own empty barrier.
+                constexpr uint32_t B_HALF = (uint32_t)B_BYTES / 2;
+                const int kcb = g.kc_blocks, taps = g.R * g.S, a_stages = g.a_stages;
+                const uint32_t full0 = mapa_u32(smem_u32(full_bar), 0), afull0 = mapa_u32(smem_u32(afull_bar), 0);
+                int as = 0, bs = 0;
+                uint32_t aph = 0, bph = 0;
+                TR_DECL(4);
+                TR_T0(tp0);
+                // The halo box of step (tile, kc) + 1 is requested BEFORE the weight tiles of step (tile, kc): its buffer (a ring
+                // of three) was last read two steps ago, so the request never waits, and the box has a whole step to land.
+                auto load_halo = [&](int tile, int kc) {
+                    const int m_tile = m_tile_of(tile);
+                    const int tw = m_tile % g.tiles_w, th = (m_tile / g.tiles_w) % g.tiles_h, tn = m_tile / (g.tiles_w * g.tiles_h);
+                    TR(0, mbar_wait(&aempty_bar[as], aph ^ 1u));
+                    if (cta_rank == 0) mbar_expect_tx(&afull_bar[as], 2u * (uint32_t)g.a_tx_bytes);
+                    tma_load_4d_pair(&tmA, afull0 + 8u * (uint32_t)as, bstat + as * g.a_stage_bytes, kc * GM_BLOCK_K,
+                                     tw * g.step_w - g.pad, th * g.step_h - g.pad, tn);     // stride 1
+                    if (++as == a_stages) { as = 0; aph ^= 1u; }
+                };
+                const bool ahead = a_stages >= 3;
+                if (ahead && tile_first < total_tiles) load_halo(tile_first, 0);
+                for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+                    const int n_tile = tile % g.n_tiles;
+                    const int nb0 = n_tile * BLOCK_N + (int)cta_rank * (BLOCK_N / 2);
+                    for (int kc = 0; kc < kcb; ++kc) {
+                        if (!ahead) load_halo(tile, kc);
+                        else if (kc + 1 < kcb) load_halo(tile, kc + 1);
+                        else if (tile + tile_step < total_tiles) load_halo(tile + tile_step, 0);
+                        for (int tap = 0; tap < taps; tap += 2) {
+                            const int nt = taps - tap >= 2 ? 2 : 1;
+                            TR(1, mbar_wait(&empty_bar[bs], bph ^ 1u));
+                            if (cta_rank == 0) mbar_expect_tx(&full_bar[bs], 2u * (uint32_t)nt * B_HALF);
+                            for (int j = 0; j < nt; ++j)
+                                tma_load_3d_pair(&tmB, full0 + 8u * (uint32_t)bs, ring + bs * g.stage_bytes + j * (int)B_HALF,
+                                                 kc * GM_BLOCK_K, nb0, tap + j);
+                            if (++bs == STAGES) { bs = 0; bph ^= 1u; }
+                        }
+                    }
+                }
+#ifdef TQ_CONV_TRACE
+                TR_SINCE(2, tp0);
+                if (blockIdx.x == 0 || blockIdx.x == 101)
+                    printf("cta %3d producer (pair): total %lld, wait halo-empty %lld, wait weight-empty %lld\n", blockIdx.x, trc[2], trc[0], trc[1]);
+#endif
+            } else if constexpr (MODE == 4) {
                 const int kcb = g.kc_blocks, taps = g.R * g.S, a_stages = g.a_stages;
                 int as = 0, bs = 0;
                 uint32_t aph = 0, bph = 0;
-                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                    const int n_tile = tile % g.n_tiles, m_tile = tile / g.n_tiles;
+                TR_DECL(4);
+                TR_T0(tp0);
+                for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+                    const int n_tile = tile % g.n_tiles, m_tile = m_tile_of(tile);
                     const int tw = m_tile % g.tiles_w, th = (m_tile / g.tiles_w) % g.tiles_h, tn = m_tile / (g.tiles_w * g.tiles_h);
                     const int w_in0 = tw * g.step_w - g.pad, h_in0 = th * g.step_h - g.pad;     // stride 1
                     const int nb0 = n_tile * BLOCK_N;
                     for (int kc = 0; kc < kcb; ++kc) {
-                        mbar_wait(&aempty_bar[as], aph ^ 1u);
+                        TR(0, mbar_wait(&aempty_bar[as], aph ^ 1u));
                         if (g.dbg_skip_tma == 4) {                      // TQ_CONV_SKIP_TMA=4: no halo loads (isolation run)
                             mbar_arrive(&afull_bar[as]);
                         } else {
@@ -452,7 +589,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         }
                         if (++as == a_stages) { as = 0; aph ^= 1u; }
                         for (int tap = 0; tap < taps; ++tap) {
-                            mbar_wait(&empty_bar[bs], bph ^ 1u);
+                            TR(1, mbar_wait(&empty_bar[bs], bph ^ 1u));
                             if (g.dbg_skip_tma == 2) {                  // TQ_CONV_SKIP_TMA=2: no weight loads (isolation run)
                                 mbar_arrive(&full_bar[bs]);
                             } else {
@@ -463,13 +600,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         }
                     }
                 }
+#ifdef TQ_CONV_TRACE
+                TR_SINCE(2, tp0);
+                if (blockIdx.x == 0 || blockIdx.x == 100)
+                    printf("cta %3d producer: total %lld, wait halo-empty %lld, wait weight-empty %lld\n", blockIdx.x, trc[2], trc[0], trc[1]);
+#endif
             } else {
             const int steps = MODE == 3 ? g.kc_blocks : (MODE == 2 ? g.prog_steps / g.R : (prog ? g.prog_steps : kblocks));
             const int S = MODE == 3 ? 1 : g.S, kc_blocks = g.kc_blocks, stage_bytes = g.stage_bytes;
             const uint32_t tx_bytes = (uint32_t)g.a_tx_bytes + (prog ? 0u : (uint32_t)B_BYTES);
             const bool skip_tma = g.dbg_skip_tma != 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int n_tile = tile % g.n_tiles, m_tile = tile / g.n_tiles;
+            for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+                const int n_tile = tile % g.n_tiles, m_tile = m_tile_of(tile);
                 const int tw = m_tile % g.tiles_w, th = (m_tile / g.tiles_w) % g.tiles_h, tn = m_tile / (g.tiles_w * g.tiles_h);
                 const int w_in0 = (tw * g.step_w + g.off_w) * g.stride - g.pad, h_in0 = (th * g.step_h + g.off_h) * g.stride - g.pad, n0 = tn * g.nbox;
                 const int nb0 = n_tile * BLOCK_N;
@@ -515,7 +657,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         constexpr uint32_t IDESC = (KIND == 1 ? ((2u << 4) | (1u << 7) | (1u << 10)) : (1u << 4)) |
                                    ((uint32_t)(MMA_N >> 3) << 17) | ((uint32_t)(GM_BLOCK_M >> 4) << 24);
         constexpr uint64_t DESC_HI = ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-        if (elect_one()) {
+        if (elect_one() && cta_rank == 0) {
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -533,22 +675,57 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 mbar_wait(bfull_bar, 0);
                 tc_fence_after();
             }
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+            TR_DECL(6);
+            TR_T0(ti0);
+            for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+                TR(0, mbar_wait(&tempty_bar[acc], acc_phase ^ 1u));
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
-                if constexpr (MODE == 4) {
+                if constexpr (MODE == 4 && CG == 2) {
+                    // leader of the CTA pair: M = 256 (both CTAs' tiles), two taps per stage, multicast commits
+                    constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)(MMA_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+                    constexpr uint32_t B_HALF16 = (uint32_t)(B_BYTES / 2) >> 4;
+                    const int taps = g.R * g.S, S = g.S, kcb = g.kc_blocks;
+                    const uint32_t row_step = (uint32_t)g.hw * 8u;
+                    int kin = 0;
+                    uint32_t td = tmem_d;
+                    for (int kc = 0; kc < kcb; ++kc) {
+                        TR(1, mbar_wait(&afull_bar[as4], aph4));
+                        tc_fence_after();
+                        uint32_t a_row = b_lo0 + (uint32_t)as4 * ((uint32_t)g.a_stage_bytes >> 4);
+                        int sx = 0;
+                        for (int tap = 0; tap < taps; tap += 2) {
+                            const int nt = taps - tap >= 2 ? 2 : 1;
+                            TR(2, mbar_wait(&full_bar[stage], phase));
+                            tc_fence_after();
+                            for (int j = 0; j < nt; ++j) {
+                                const uint64_t da = DESC_HI | (a_row + (uint32_t)sx * 8u);
+                                const uint64_t db = DESC_HI | (a_lo + (uint32_t)j * B_HALF16);
+#pragma unroll
+                                for (int k = 0; k < GM_ROW_BYTES / 32; ++k)
+                                    umma_f16_pair(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC2, (kin | (tap + j) | k) != 0 ? 1u : 0u);
+                                if (++sx == S) { sx = 0; a_row += row_step; }
+                            }
+                            umma_commit_pair(&empty_bar[stage]);        // both CTAs' halves of the stage are free
+                            a_lo += a_step;
+                            if (++stage == STAGES) { stage = 0; phase ^= 1u; a_lo = a_lo0; }
+                        }
+                        umma_commit_pair(&aempty_bar[as4]);
+                        if (++as4 == g.a_stages) { as4 = 0; aph4 ^= 1u; }
+                        if (++kin == g.kcpg) { kin = 0; td += BLOCK_N; }
+                    }
+                } else if constexpr (MODE == 4) {
                     const int taps = g.R * g.S, S = g.S, kcb = g.kc_blocks;
                     const uint32_t row_step = (uint32_t)g.hw * 8u;      // one halo row of pixels, in 16-byte units
                     int kin = 0;                                        // channel block within the K chunk
                     uint32_t td = tmem_d;                               // accumulator of the current K chunk
                     for (int kc = 0; kc < kcb; ++kc) {
-                        mbar_wait(&afull_bar[as4], aph4);
+                        TR(1, mbar_wait(&afull_bar[as4], aph4));
                         tc_fence_after();
                         uint32_t a_row = b_lo0 + (uint32_t)as4 * ((uint32_t)g.a_stage_bytes >> 4);   // halo ring lives at bstat
                         int sx = 0;
                         for (int tap = 0; tap < taps; ++tap) {
-                            mbar_wait(&full_bar[stage], phase);
+                            TR(2, mbar_wait(&full_bar[stage], phase));
                             tc_fence_after();
                             const uint64_t da = DESC_HI | (a_row + (uint32_t)sx * 8u);
                             const uint64_t db = DESC_HI | a_lo;         // weight-tile ring (stage_bytes = B_BYTES)
@@ -570,7 +747,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const int taps = g.R * g.S, S = g.S, kcb = g.kc_blocks;
                     const uint32_t row_step = (uint32_t)g.hw * 8u;      // one halo row of pixels, in 16-byte units
                     for (int kc = 0; kc < kcb; ++kc) {
-                        mbar_wait(&full_bar[stage], phase);
+                        TR(2, mbar_wait(&full_bar[stage], phase));
                         tc_fence_after();
                         uint32_t a_row = a_lo, b_lo = b_lo0 + (uint32_t)kc * (uint32_t)(B_BYTES >> 4);
                         int s = 0;
@@ -600,7 +777,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     int kc = 0, kin = 0, tap0 = 1, pa = 0, pw = 0;
                     uint32_t grp = 0;
                     for (int st = 0; st < steps; ++st) {
-                        mbar_wait(&full_bar[stage], phase);
+                        TR(2, mbar_wait(&full_bar[stage], phase));
                         tc_fence_after();
                         const uint64_t da = DESC_HI | a_lo;
                         const uint64_t db = DESC_HI | (MODE == 1 ? b_lo : a_lo + (uint32_t)(GM_A_BYTES >> 4));
@@ -638,7 +815,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const uint32_t row_step = (uint32_t)g.hw * 8u;      // one row of the pixel box, in 16-byte units
                     int st = 0;
                     for (int pl = 0; pl < planes; ++pl) {
-                        mbar_wait(&full_bar[stage], phase);
+                        TR(2, mbar_wait(&full_bar[stage], phase));
                         tc_fence_after();
                         uint32_t a_row = a_lo;
                         for (int r = 0; r < R; ++r, ++st, a_row += row_step) {
@@ -673,9 +850,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; a_lo = a_lo0; }
                     }
                 }
-                umma_commit(&tfull_bar[acc]);                           // accumulator complete
+                if constexpr (CG == 2) umma_commit_pair(&tfull_bar[acc]);
+                else umma_commit(&tfull_bar[acc]);                      // accumulator complete
                 if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
             }
+#ifdef TQ_CONV_TRACE
+            TR_SINCE(3, ti0);
+            if (blockIdx.x == 0 || blockIdx.x == 100)
+                printf("cta %3d issuer: total %lld, wait acc-empty %lld, wait halo-full %lld, wait stage-full %lld\n", blockIdx.x, trc[3], trc[0], trc[1], trc[2]);
+#endif
         }
         __syncwarp();
     } else if (warp >= 4) {
@@ -708,11 +891,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t res_bytes = (uint32_t)(g.wbox * g.hbox * g.nbox) * 128u;
         uint32_t res_phase = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        // "this thread's share of accumulator stage a is in registers": on the MMA issuer's barrier (the pair leader's)
+        const uint32_t tempty0 = CG == 2 ? mapa_u32(smem_u32(tempty_bar), 0) : 0u;
+        auto release_acc = [&](int a) {
+            if (CG == 2 && cta_rank != 0) mbar_arrive_cluster(tempty0 + 8u * (uint32_t)a);
+            else mbar_arrive(&tempty_bar[a]);
+        };
+        TR_DECL(8);
+        TR_T0(te0);
+        for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
             if (!single && (it & 1) != pair) continue;
             const int acc = it % ACC_STAGES;                          // accumulator stage of this tile and its use parity
             const uint32_t acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
-            const int n_tile = tile % g.n_tiles, m_tile = tile / g.n_tiles;
+            const int n_tile = tile % g.n_tiles, m_tile = m_tile_of(tile);
             const int tw = m_tile % g.tiles_w, th = (m_tile / g.tiles_w) % g.tiles_h, tn = m_tile / (g.tiles_w * g.tiles_h);
             const int w0 = tw * g.wbox, h0 = th * g.hbox, n0 = tn * g.nbox;
 
@@ -720,7 +911,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
                 tc_fence_before();
-                mbar_arrive(&tempty_bar[acc]);
+                release_acc(acc);
                 continue;
             }
 #pragma unroll 1
@@ -735,17 +926,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     tma_load_4d(&tmR, &res_bar[grp], st_f32, c0, w0, h0, n0);
                 }
                 if (cc == 0) {
-                    mbar_wait(&tfull_bar[acc], acc_phase);
+                    TR(0, mbar_wait(&tfull_bar[acc], acc_phase));
                     tc_fence_after();
                 }
                 if (!chunk_live) {                               // channels beyond Cout (uniform over the group)
                     if (cc == CHUNKS - 1) {
                         tc_fence_before();
-                        mbar_arrive(&tempty_bar[acc]);
+                        release_acc(acc);
                     }
                     continue;
                 }
                 float t[32];
+                TR_T0(tl0);
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     uint32_t v[16];
@@ -781,8 +973,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
                 if (cc == CHUNKS - 1) {                          // this group's share of the accumulator is in registers
                     tc_fence_before();
-                    mbar_arrive(&tempty_bar[acc]);
+                    release_acc(acc);
                 }
+                TR_SINCE(1, tl0);
+                TR_T0(tq0);
                 if constexpr (MODE == 2) {
                     if (g.pool) {
                         // ---- fused BatchNorm + ReLU + 3x3 / stride 2 / pad 1 max-pool + next-layer encode (stem) ----
@@ -874,21 +1068,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             if (g.write_codes) tma_store_4d(&tmD, st_pcodes, c0, tw * g.pool_q, th * g.pool_p, n0);
                             bulk_commit();
                         }
+                        TR_SINCE(6, tq0);
                         continue;
                     }
                 }
-                if (c0 + 32 <= g.Cout) epi_affine<true>(t, g, c0); else epi_affine<false>(t, g, c0);
+                TR(2, if (c0 + 32 <= g.Cout) epi_affine<true>(t, g, c0); else epi_affine<false>(t, g, c0));
                 // (b) staging: with a residual it already holds this chunk's residual tile; otherwise the previous
                 //     store of this group must have finished reading it before it is overwritten
+                TR_T0(tw0);
                 if (has_res) {
                     mbar_wait(&res_bar[grp], res_phase);
                 } else {
                     if (store_thread) bulk_wait_read0();
                     epi_bar_sync(1 + grp);
                 }
-                if (row_live) epi_stage<RELU>(t, g, st_f32, st_codes, row, has_res, lut, nq);
+                TR_SINCE(3, tw0);
+                TR(4, if (row_live) epi_stage<RELU>(t, g, st_f32, st_codes, row, has_res, lut, nq));
                 if (has_res) res_phase ^= 1u;
                 // (c) staging complete: hand it to the async proxy and store
+                TR_T0(ts0);
                 fence_proxy_async();
                 epi_bar_sync(1 + grp);
                 if (store_thread) {
@@ -896,15 +1094,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     if (g.write_codes) tma_store_4d(&tmD, st_codes, c0, w0, h0, n0);
                     bulk_commit();
                 }
+                TR_SINCE(5, ts0);
             }
         }
+#ifdef TQ_CONV_TRACE
+        TR_SINCE(7, te0);
+        if ((blockIdx.x == 0 || blockIdx.x == 100) && store_thread && grp < 2)
+            printf("cta %3d epilogue group %d: total %lld, wait acc-full %lld, tmem+combine %lld, affine %lld, wait staging %lld, stage %lld, "
+                   "sync+store %lld, pooled tail %lld\n", blockIdx.x, grp, trc[7], trc[0], trc[1], trc[2], trc[3], trc[4], trc[5], trc[6]);
+#endif
         if (store_thread) bulk_wait0();
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();              // neither CTA leaves while the pair's MMAs may touch its memories
+    else __syncthreads();
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if constexpr (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -995,7 +1202,9 @@ static int plan_smem(ConvGeom &g, int block_n)
     if (g.halo && !prog) {                          // MODE 4: [halo ring][weight-tile ring]
         g.a_stage_bytes = (g.a_tx_bytes + 1023) & ~1023;
         static const int a_stages_env = getenv("TQ_CONV_ASTAGES") ? atoi(getenv("TQ_CONV_ASTAGES")) : 0;
-        g.a_stages = a_stages_env >= 2 && a_stages_env <= 4 ? a_stages_env : 2;   // measured: 2 halo buffers + a deeper weight ring win
+        // single CTAs, measured: 2 halo buffers + a deeper weight ring win.  CTA pairs: 3, so that the next box is requested a
+        // whole step ahead (see the producer)
+        g.a_stages = a_stages_env >= 2 && a_stages_env <= 4 ? a_stages_env : (g.pair ? 3 : 2);
         g.stage_bytes = b_bytes;
         g.ring_off = g.a_stages * g.a_stage_bytes;
     }
@@ -1018,7 +1227,7 @@ static int plan_smem(ConvGeom &g, int block_n)
     return TQ_OK;
 }
 
-template <int BLOCK_N, int MODE, int KIND = 0>
+template <int BLOCK_N, int MODE, int KIND = 0, int CG = 1>
 static int launch_conv_mode(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
                             const CUtensorMap &tmD, const CUtensorMap &tmR, ConvGeom &g, cudaStream_t s)
 {
@@ -1028,7 +1237,7 @@ static int launch_conv_mode(const CUtensorMap &tmA, const CUtensorMap &tmB, cons
     static const int skip_tma = getenv("TQ_CONV_SKIP_TMA") ? atoi(getenv("TQ_CONV_SKIP_TMA")) : 0;
     g.dbg_skip_mma = skip_mma ? 1 : 0;
     g.dbg_skip_tma = skip_tma;
-    auto kern = g.relu ? conv_igemm_kernel<BLOCK_N, MODE, true, KIND> : conv_igemm_kernel<BLOCK_N, MODE, false, KIND>;
+    auto kern = g.relu ? conv_igemm_kernel<BLOCK_N, MODE, true, KIND, CG> : conv_igemm_kernel<BLOCK_N, MODE, false, KIND, CG>;
     static bool attr_set[2][64] = {{false}};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1037,15 +1246,40 @@ static int launch_conv_mode(const CUtensorMap &tmA, const CUtensorMap &tmB, cons
             return check_launch("cudaFuncSetAttribute(conv_igemm_kernel)");
         attr_set[g.relu ? 1 : 0][dev] = true;
     }
-    const int total = g.m_tiles * g.n_tiles;
-    const int grid = total < num_sms() ? total : num_sms();
-    kern<<<grid, GM_THREADS, g.smem_total, s>>>(tmA, tmB, tmC, tmD, tmR, g);
-    count_launch();
-    return check_launch("conv_igemm_kernel");
+    if constexpr (CG == 2) {
+        // one cluster of two CTAs per TPC; as many pairs as fit the device at once (at most one per two SMs)
+        const int supers = ((g.m_tiles + 1) / 2) * g.n_tiles;
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.blockDim = dim3(GM_THREADS); cfg.dynamicSmemBytes = (size_t)g.smem_total; cfg.stream = s;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        static int max_pairs[2][64] = {{0}};
+        int &mp = max_pairs[g.relu ? 1 : 0][dev >= 0 && dev < 64 ? dev : 0];
+        if (mp == 0) {
+            cfg.gridDim = dim3((unsigned)(num_sms() & ~1));
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = num_sms() / 2; }
+            mp = n < num_sms() / 2 ? n : num_sms() / 2;
+        }
+        const int pairs = supers < mp ? supers : mp;
+        cfg.gridDim = dim3((unsigned)(2 * pairs));
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmD, tmR, g);
+        count_launch();
+        if (e != cudaSuccess) return fail(TQ_ERR_CUDA, "conv_igemm_kernel (CTA pairs): %s", cudaGetErrorString(e));
+        return check_launch("conv_igemm_kernel");
+    } else {
+        const int total = g.m_tiles * g.n_tiles;
+        const int grid = total < num_sms() ? total : num_sms();
+        kern<<<grid, GM_THREADS, g.smem_total, s>>>(tmA, tmB, tmC, tmD, tmR, g);
+        count_launch();
+        return check_launch("conv_igemm_kernel");
+    }
 }
 
 // which kernel instance runs a planned conv
-enum ConvVariant { CV_NONE = 0, CV_64_M0, CV_64_M1, CV_64_M2, CV_64_M3, CV_128_M0, CV_128_M4, CV_256_M0, CV_I8_64, CV_I8_128 };
+enum ConvVariant { CV_NONE = 0, CV_64_M0, CV_64_M1, CV_64_M2, CV_64_M3, CV_128_M0, CV_128_M4, CV_128_M4_PAIR, CV_256_M0, CV_I8_64, CV_I8_128 };
 
 // general_prog: the step table (prog_mma) is in use; otherwise resident weights are tile = tap
 static int pick_variant(ConvGeom &g, int block_n, int kind, bool general_prog, ConvVariant &v)
@@ -1062,7 +1296,7 @@ static int pick_variant(ConvGeom &g, int block_n, int kind, bool general_prog, C
     }
     if (g.prog_steps == 0 && g.halo) {
         if (block_n != 128) return fail(TQ_ERR_UNSUPPORTED, "streamed-weight halo mode is built for BLOCK_N = 128 only");
-        v = CV_128_M4;
+        v = g.pair ? CV_128_M4_PAIR : CV_128_M4;
         return TQ_OK;
     }
     if (g.prog_steps == 0) { v = block_n == 64 ? CV_64_M0 : (block_n == 128 ? CV_128_M0 : CV_256_M0); return TQ_OK; }
@@ -1081,6 +1315,7 @@ static int launch_variant(ConvVariant v, const CUtensorMap &tmA, const CUtensorM
     case CV_64_M3: return launch_conv_mode<64, 3>(tmA, tmB, tmC, tmD, tmR, g, s);
     case CV_128_M0: return launch_conv_mode<128, 0>(tmA, tmB, tmC, tmD, tmR, g, s);
     case CV_128_M4: return launch_conv_mode<128, 4>(tmA, tmB, tmC, tmD, tmR, g, s);
+    case CV_128_M4_PAIR: return launch_conv_mode<128, 4, 0, 2>(tmA, tmB, tmC, tmD, tmR, g, s);
     case CV_256_M0: return launch_conv_mode<256, 0>(tmA, tmB, tmC, tmD, tmR, g, s);
     case CV_I8_64: return launch_conv_mode<64, 0, 1>(tmA, tmB, tmC, tmD, tmR, g, s);
     case CV_I8_128: return launch_conv_mode<128, 0, 1>(tmA, tmB, tmC, tmD, tmR, g, s);
@@ -1216,6 +1451,10 @@ static int plan_conv(const ConvArgs &a, ConvPlan &pl)
             h.step_w = h.wbox; h.step_h = h.hbox;
             g = h;
             g.halo = 1;
+            // CTA pairs (cta_group::2) when there are enough tiles to keep every pair busy: per CTA half the weight
+            // traffic from L2 and 6 KB instead of 8 KB of operand reads per MMA.  TQ_CONV_PAIR=0 keeps single CTAs.
+            static const int pair_env = getenv("TQ_CONV_PAIR") ? atoi(getenv("TQ_CONV_PAIR")) : 1;
+            if (pair_env && ((g.m_tiles + 1) / 2) * g.n_tiles >= num_sms() / 2) g.pair = 1;
         }
     }
     const CUtensorMapDataType op_dt = kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -1231,7 +1470,7 @@ static int plan_conv(const ConvArgs &a, ConvPlan &pl)
     {   // weights: (C, Cout, planes * R*S), one K block of one tap per tile
         if (g.prog_steps > 0 && g.kc_blocks != 1) { g.halo = 0; g.prog_steps = 0; g.nb_tiles = 0; }   // (program mode: one block per tap)
         cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Cout, (cuuint64_t)(g.planes_w * R * S)};
-        cuuint32_t box[3] = {(cuuint32_t)g.kblk, (cuuint32_t)block_n, 1};
+        cuuint32_t box[3] = {(cuuint32_t)g.kblk, (cuuint32_t)(g.pair ? block_n / 2 : block_n), 1};   // (a pair CTA loads half a tile)
         cuuint32_t estr[3] = {1, 1, 1};
         if ((rc = encode_map(enc, &pl.tmB, op_dt, op_es, a.wgt, 3, dims, box, estr, "weights")) != TQ_OK) return rc;
     }
