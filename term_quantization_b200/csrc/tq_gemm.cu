@@ -998,6 +998,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                     make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
                         }
                         epi_bar_sync(1 + grp);
+                        TR_SINCE(2, tq0);
+                        TR_T0(tq1);
                         uint8_t *st_pool = st_codes, *st_pcodes = st_codes + 4096;   // [P*Q][32] fp32 / fp16 tiles
                         const int pp = mrow >> 2, cb = mrow & 3;                     // pooled pixel, 8-channel block
                         float pv[8];
@@ -1041,8 +1043,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             }
                         }
                         // the pooled staging tiles are free once this group's previous TMA store has read them
+                        TR_SINCE(3, tq1);
+                        TR_T0(tq2);
                         if (store_thread) bulk_wait_read0();
                         epi_bar_sync(1 + grp);
+                        TR_SINCE(4, tq2);
+                        TR_T0(tq3);
                         if (pool_thread) {
                             const uint32_t psw = (uint32_t)(pp & 7);
                             *reinterpret_cast<float4 *>(st_pool + pp * 128 + (((uint32_t)(2 * cb) ^ psw) << 4)) = make_float4(pv[0], pv[1], pv[2], pv[3]);
@@ -1061,6 +1067,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                     make_uint4(hc[0] | (hc[1] << 16), hc[2] | (hc[3] << 16), hc[4] | (hc[5] << 16), hc[6] | (hc[7] << 16));
                             }
                         }
+                        TR_SINCE(5, tq3);
                         fence_proxy_async();
                         epi_bar_sync(1 + grp);
                         if (store_thread) {
@@ -1101,7 +1108,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         TR_SINCE(7, te0);
         if ((blockIdx.x == 0 || blockIdx.x == 100) && store_thread && grp < 2)
             printf("cta %3d epilogue group %d: total %lld, wait acc-full %lld, tmem+combine %lld, affine %lld, wait staging %lld, stage %lld, "
-                   "sync+store %lld, pooled tail %lld\n", blockIdx.x, grp, trc[7], trc[0], trc[1], trc[2], trc[3], trc[4], trc[5], trc[6]);
+                   "sync+store %lld, pooled tail %lld  (pooled stem: the four middle slots are raw staging + sync, window max + affine, store wait + sync, "
+                   "pooled tile + encode)\n", blockIdx.x, grp, trc[7], trc[0], trc[1], trc[2], trc[3], trc[4], trc[5], trc[6]);
 #endif
         if (store_thread) bulk_wait0();
     }
