@@ -71,6 +71,7 @@ struct ConvGeom {
     int step_w, step_h, off_w, off_h;           // tile origin in output pixels: (tw * step_w + off_w, th * step_h + off_h)
     int pool, pool_p, pool_q;                   // fused 3x3/s2/p1 max-pool (stem): pooled pixels per tile
     int halo, halo_baseoff;                     // halo mode (MODE 3); whether to set the descriptor's base-offset field
+    int img_h1;                                 // packed halo (small maps, several images per tile): H + 1 box rows per image, else 0
     int pair;                                   // MODE 4 on CTA pairs (cta_group::2): two M tiles per MMA, half a weight tile per CTA
     int tiles_w, tiles_h, tiles_n;              // M tiles along w, h, image
     int m_tiles, n_tiles, kc_blocks;
@@ -481,6 +482,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             lut[i] = __int2half_rn((i >> g.next_bits) ? -code : code);
         }
     }
+    if (MODE == 4 && g.img_h1) {
+        // packed halo: the rows after each box (read by the taps of the last image's last pixels: its bottom padding)
+        // are never written by TMA -- zero them once, for the tensor cores' (async-proxy) reads
+        const int tail = g.a_stage_bytes - g.a_tx_bytes;
+        for (int i = threadIdx.x * 16; i < g.a_stages * tail; i += GM_THREADS * 16)
+            *reinterpret_cast<uint4 *>(bstat + (i / tail) * g.a_stage_bytes + g.a_tx_bytes + (i % tail)) = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async();
+    }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         mbar_init(bfull_bar, 1);
@@ -540,7 +549,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     TR(0, mbar_wait(&aempty_bar[as], aph ^ 1u));
                     if (cta_rank == 0) mbar_expect_tx(&afull_bar[as], 2u * (uint32_t)g.a_tx_bytes);
                     tma_load_4d_pair(&tmA, afull0 + 8u * (uint32_t)as, bstat + as * g.a_stage_bytes, kc * GM_BLOCK_K,
-                                     tw * g.step_w - g.pad, th * g.step_h - g.pad, tn);     // stride 1
+                                     tw * g.step_w - g.pad, th * g.step_h - g.pad, tn * g.nbox);     // stride 1
                     if (++as == a_stages) { as = 0; aph ^= 1u; }
                 };
                 const bool ahead = a_stages >= 3;
@@ -585,7 +594,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             mbar_arrive(&afull_bar[as]);
                         } else {
                         mbar_expect_tx(&afull_bar[as], (uint32_t)g.a_tx_bytes);
-                        tma_load_4d(&tmA, &afull_bar[as], bstat + as * g.a_stage_bytes, kc * GM_BLOCK_K, w_in0, h_in0, tn);
+                        tma_load_4d(&tmA, &afull_bar[as], bstat + as * g.a_stage_bytes, kc * GM_BLOCK_K, w_in0, h_in0, tn * g.nbox);
                         }
                         if (++as == a_stages) { as = 0; aph ^= 1u; }
                         for (int tap = 0; tap < taps; ++tap) {
@@ -875,8 +884,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int mrow = ew * 32 + lane;                        // accumulator row = TMEM lane
         // staging row of this accumulator row: dense (hbox x wbox) pixel order; in halo mode the columns
         // mrow % hw >= wbox are junk and write nothing
-        const int row = (mrow / g.hw) * g.wbox + (mrow % g.hw);
-        const bool row_live = (mrow % g.hw) < g.wbox && row < 128;
+        // (packed halo: box row y = image y / (H + 1), pixel row y % (H + 1) < H; the staging tile is [image][h][w])
+        const int my = mrow / g.hw, mx = mrow % g.hw;
+        const int row = g.img_h1 ? (my / g.img_h1) * (g.wbox * g.hbox) + (my % g.img_h1) * g.wbox + mx : my * g.wbox + mx;
+        const bool row_live = g.img_h1 ? (mx < g.wbox && (my % g.img_h1) < g.hbox && (my / g.img_h1) < g.nbox) : (mx < g.wbox && row < 128);
         const bool store_thread = (ew == 0 && lane == 0);
         uint8_t *st_f32 = smem + g.epi_off + grp * g.epi_group_bytes;   // [128][32] fp32, 128B swizzle
         uint8_t *st_codes = st_f32 + g.epi_codes_off;                   // [128][32] fp16,  64B swizzle
@@ -1209,6 +1220,7 @@ static int plan_smem(ConvGeom &g, int block_n)
     g.ring_off = prog ? g.nb_tiles * b_bytes : 0;
     if (g.halo && !prog) {                          // MODE 4: [halo ring][weight-tile ring]
         g.a_stage_bytes = (g.a_tx_bytes + 1023) & ~1023;
+        if (g.img_h1) g.a_stage_bytes = (g.a_tx_bytes + ((g.R - 1) * g.hw + g.S) * GM_ROW_BYTES + 1023) & ~1023;   // + the zero tail
         static const int a_stages_env = getenv("TQ_CONV_ASTAGES") ? atoi(getenv("TQ_CONV_ASTAGES")) : 0;
         // single CTAs, measured: 2 halo buffers + a deeper weight ring win.  CTA pairs: 3, so that the next box is requested a
         // whole step ahead (see the producer)
@@ -1453,6 +1465,24 @@ static int plan_conv(const ConvArgs &a, ConvPlan &pl)
     g.step_w = g.wbox; g.step_h = g.hbox; g.off_w = 0; g.off_h = 0;
     // streamed-weight halo mode (MODE 4): stride-1 filters wider than 1x1 on maps that fill the tile
     static const bool no_halo4 = getenv("TQ_CONV_NO_HALO4") != nullptr;
+    // Packed halo for small maps (7x7): images are laid out W + 1 pixels per row and H + 1 rows apart -- the zero column
+    // left of a row is also the right padding of the row above, the zero row above an image also the bottom padding of
+    // the image before it -- so one TMA box of (W + 1) x (H + 1) x nbox pixels (origin (-1, -1)) is the halo of nbox whole
+    // images, and filter tap (r, s) is that buffer read from row r * (W + 1) + s on.  MMA row m = image m / ((W+1)(H+1)),
+    // pixel ((m / (W+1)) % (H+1), m % (W+1)); the rows with pixel row H or column W are junk.
+    static const bool no_packed = getenv("TQ_CONV_NO_PACKED") != nullptr;
+    if (kind == 0 && !no_halo4 && !no_packed && g.prog_steps == 0 && !g.halo && block_n == 128 && stride == 1 && R == 3 && S == 3 &&
+        pad == 1 && N >= 2 && 2 * (W + 1) * (H + 1) <= 128) {
+        const int per = (W + 1) * (H + 1);
+        g.wbox = W; g.hbox = H; g.nbox = 128 / per < N ? 128 / per : N;
+        g.hw = W + 1; g.img_h1 = H + 1;
+        g.tiles_w = g.tiles_h = 1; g.tiles_n = (N + g.nbox - 1) / g.nbox; g.m_tiles = g.tiles_n;
+        g.a_tx_bytes = g.nbox * per * GM_ROW_BYTES;
+        g.step_w = g.wbox; g.step_h = g.hbox;
+        g.halo = 1;
+        static const int pair_env = getenv("TQ_CONV_PAIR") ? atoi(getenv("TQ_CONV_PAIR")) : 1;
+        if (pair_env && ((g.m_tiles + 1) / 2) * g.n_tiles >= num_sms() / 2) g.pair = 1;
+    }
     if (kind == 0 && !no_halo4 && g.prog_steps == 0 && !g.halo && block_n == 128 && stride == 1 && R * S > 1) {
         ConvGeom h = g;
         if (pick_box_halo(h) && h.m_tiles <= g.m_tiles + g.m_tiles / 8) {
@@ -1472,6 +1502,7 @@ static int plan_conv(const ConvArgs &a, ConvPlan &pl)
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(g.planes_a * N)};
         cuuint32_t box[4] = {(cuuint32_t)g.kblk, (cuuint32_t)(g.wbox * stride), (cuuint32_t)(g.hbox * stride), (cuuint32_t)g.nbox};
         if (g.halo) { box[1] = (cuuint32_t)g.hw; box[2] = (cuuint32_t)(g.hbox + R - 1); }
+        if (g.img_h1) { box[2] = (cuuint32_t)g.img_h1; box[3] = (cuuint32_t)g.nbox; }
         cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
         if ((rc = encode_map(enc, &pl.tmA, op_dt, op_es, a.act, 4, dims, box, estr, "activations")) != TQ_OK) return rc;
     }
