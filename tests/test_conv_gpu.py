@@ -32,6 +32,15 @@ CASES = [
     (1, 33, 21, 72, 136, 3, 1, 1),
     (2, 14, 14, 256, 256, 3, 1, 1),
     (1, 40, 40, 64, 128, 5, 1, 2),
+    # CTA pairs (cta_group::2, at least one pair of M tiles per TPC): odd tile counts leave a tile without a partner
+    (41, 28, 28, 128, 128, 3, 1, 1),
+    (41, 14, 14, 256, 256, 3, 1, 1),
+    (38, 20, 24, 64, 192, 3, 1, 1),
+    # packed halo (small maps, several images per tile): single CTAs, then pairs, odd batches
+    (75, 7, 7, 128, 128, 3, 1, 1),
+    (151, 7, 7, 256, 512, 3, 1, 1),
+    (37, 4, 4, 128, 256, 3, 1, 1),
+    (301, 5, 6, 64, 128, 3, 1, 1),
 ]
 
 
@@ -161,7 +170,8 @@ def test_i8_plane_engine_plane_counts():
 
 FUSED = [(2, 56, 56, 64, 64, 3, 1, 1), (3, 28, 28, 128, 128, 3, 1, 1), (2, 56, 56, 64, 128, 1, 2, 0),
          (5, 7, 7, 512, 512, 3, 1, 1), (1, 9, 13, 72, 72, 3, 1, 1), (3, 14, 14, 256, 256, 3, 1, 1),
-         (2, 20, 33, 32, 40, 3, 1, 1), (1, 57, 29, 64, 64, 3, 1, 1), (2, 30, 27, 128, 192, 3, 1, 1)]
+         (2, 20, 33, 32, 40, 3, 1, 1), (1, 57, 29, 64, 64, 3, 1, 1), (2, 30, 27, 128, 192, 3, 1, 1),
+         (41, 28, 28, 128, 128, 3, 1, 1), (151, 7, 7, 128, 256, 3, 1, 1), (9, 7, 7, 512, 512, 3, 1, 1)]   # CTA pairs / packed halo
 
 
 def _random_fused_cases(n, seed=31):
