@@ -332,6 +332,41 @@ tr_group_kernel(const float *__restrict__ in, Tout *__restrict__ out,
             __syncthreads();
         }
     }
+    if constexpr (LAYOUT == 1 && G >= 4 && (sizeof(Tout) * G) % 16 == 0) {
+        // contiguous groups, 128-bit accesses: the NEXT group of this thread is requested before the current one is
+        // encoded (registers as a second buffer), which doubles the bytes in flight per SM at the same occupancy --
+        // with one group per thread in flight the kernel sat at ~32 KB per SM, short of what HBM latency x bandwidth asks
+        constexpr int NV = (G * 4) / 16, NVO = (int)(sizeof(Tout) * G) / 16;
+        const int64_t step = (int64_t)gridDim.x * GROUP_THREADS;
+        int64_t t = (int64_t)blockIdx.x * GROUP_THREADS + threadIdx.x;
+        int4 cur[NV], nxt[NV];
+        if (t < total) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) cur[v] = __ldcs(reinterpret_cast<const int4 *>(in + t * G) + v);
+        }
+        while (t < total) {
+            const int64_t tn = t + step;
+            if (tn < total) {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) nxt[v] = __ldcs(reinterpret_cast<const int4 *>(in + tn * G) + v);
+            }
+            float x[G];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) memcpy(&x[v * 4], &cur[v], 16);
+            Tout y[G];
+            select(x, y);
+            int4 *dst = reinterpret_cast<int4 *>(out + t * G);
+#pragma unroll
+            for (int v = 0; v < NVO; ++v) {
+                int4 raw;
+                memcpy(&raw, reinterpret_cast<const char *>(y) + 16 * v, 16);
+                __stcs(dst + v, raw);
+            }
+#pragma unroll
+            for (int v = 0; v < NV; ++v) cur[v] = nxt[v];
+            t = tn;
+        }
+    } else
     if constexpr (LAYOUT != 2)
     for (int64_t t = (int64_t)blockIdx.x * GROUP_THREADS + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * GROUP_THREADS) {
