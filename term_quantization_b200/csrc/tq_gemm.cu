@@ -425,7 +425,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                       const __grid_constant__ CUtensorMap tmR, const __grid_constant__ ConvGeom g)
 {
     static_assert(KIND == 0 || MODE == 0, "the s8-plane engine streams both operands (MODE 0)");
-    static_assert(CG == 1 || (MODE == 4 && KIND == 0), "the CTA pair runs the streamed-weight halo mode");
+    static_assert(CG == 1 || ((MODE == 4 || MODE == 3) && KIND == 0), "the CTA pair runs the halo modes");
     // MODE 2 (hi/lo stem conv): a resident weight tile stacks the hi plane (rows 0..63) on the lo plane (rows 64..127) and
     // ONE N = 128 MMA computes x * w_hi into accumulator columns [c, c + 64) and x * w_lo into [c + 64, c + 128): 64 cycles
     // instead of two N = 64 MMAs at 57 each.  The epilogue's view stays BLOCK_N = 64 output channels, four column groups.
@@ -525,7 +525,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             uint8_t *sdst = ring;
-            if constexpr (prog) {                           // all weights once: they stay resident
+            if constexpr (prog && CG == 2) {                // this CTA's half of every resident tile, counted on the leader's barrier
+                const uint32_t bfull0 = mapa_u32(smem_u32(bfull_bar), 0);
+                if (cta_rank == 0) mbar_expect_tx(bfull_bar, (uint32_t)(g.nb_tiles * B_BYTES));
+                for (int t = 0; t < g.nb_tiles; ++t)
+                    tma_load_3d_pair(&tmB, bfull0, bstat + t * (B_BYTES / 2), 0, (int)cta_rank * (BLOCK_N / 2), t);
+            } else if constexpr (prog) {                    // all weights once: they stay resident
                 mbar_expect_tx(bfull_bar, (uint32_t)(g.nb_tiles * B_BYTES));
                 for (int t = 0; t < g.nb_tiles; ++t) tma_load_3d(&tmB, bfull_bar, bstat + t * B_BYTES, 0, 0, t);
             }
@@ -614,6 +619,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (blockIdx.x == 0 || blockIdx.x == 100)
                     printf("cta %3d producer: total %lld, wait halo-empty %lld, wait weight-empty %lld\n", blockIdx.x, trc[2], trc[0], trc[1]);
 #endif
+            } else if constexpr (MODE == 3 && CG == 2) {
+                // CTA pair, resident weights: one halo box per tile and CTA, completing on the leader's full barrier
+                const uint32_t full0 = mapa_u32(smem_u32(full_bar), 0);
+                for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+                    const int m_tile = m_tile_of(tile);
+                    const int tw = m_tile % g.tiles_w, th = (m_tile / g.tiles_w) % g.tiles_h, tn = m_tile / (g.tiles_w * g.tiles_h);
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (uint32_t)g.a_tx_bytes);
+                    tma_load_4d_pair(&tmA, full0 + 8u * (uint32_t)stage, sdst, 0, tw * g.step_w - g.pad, th * g.step_h - g.pad, tn * g.nbox);
+                    sdst += g.stage_bytes;
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; sdst = ring; }
+                }
             } else {
             const int steps = MODE == 3 ? g.kc_blocks : (MODE == 2 ? g.prog_steps / g.R : (prog ? g.prog_steps : kblocks));
             const int S = MODE == 3 ? 1 : g.S, kc_blocks = g.kc_blocks, stage_bytes = g.stage_bytes;
@@ -752,6 +769,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         if (++as4 == g.a_stages) { as4 = 0; aph4 ^= 1u; }
                         if (++kin == g.kcpg) { kin = 0; td += BLOCK_N; }   // next K chunk: next accumulator group
                     }
+                } else if constexpr (MODE == 3 && CG == 2) {
+                    // leader of the CTA pair: M = 256 (both CTAs' tiles), every tap against the pair's resident half tiles
+                    constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)(MMA_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+                    const int taps = g.R * g.S, S = g.S;
+                    const uint32_t row_step = (uint32_t)g.hw * 8u;
+                    TR(2, mbar_wait(&full_bar[stage], phase));
+                    tc_fence_after();
+                    uint32_t a_row = a_lo, b_lo = b_lo0;
+                    int s = 0;
+                    for (int tap = 0; tap < taps; ++tap) {
+                        const uint64_t da = DESC_HI | (a_row + (uint32_t)s * 8u);
+                        const uint64_t db = DESC_HI | b_lo;
+#pragma unroll
+                        for (int k = 0; k < GM_ROW_BYTES / 32; ++k)
+                            umma_f16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC2, (tap | k) != 0 ? 1u : 0u);
+                        b_lo += (uint32_t)(B_BYTES / 2) >> 4;
+                        if (++s == S) { s = 0; a_row += row_step; }
+                    }
+                    umma_commit_pair(&empty_bar[stage]);
+                    a_lo += a_step;
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; a_lo = a_lo0; }
                 } else if constexpr (MODE == 3) {
                     const int taps = g.R * g.S, S = g.S, kcb = g.kc_blocks;
                     const uint32_t row_step = (uint32_t)g.hw * 8u;      // one halo row of pixels, in 16-byte units
@@ -1217,7 +1255,7 @@ static int plan_smem(ConvGeom &g, int block_n)
     g.stage_bytes = GM_A_BYTES + (prog ? 0 : b_bytes);
     if (g.halo) g.stage_bytes = (g.a_tx_bytes + 1023) & ~1023;
     g.bstat_off = 0;
-    g.ring_off = prog ? g.nb_tiles * b_bytes : 0;
+    g.ring_off = prog ? g.nb_tiles * (g.pair ? b_bytes / 2 : b_bytes) : 0;     // (a pair CTA keeps half of every resident tile)
     if (g.halo && !prog) {                          // MODE 4: [halo ring][weight-tile ring]
         g.a_stage_bytes = (g.a_tx_bytes + 1023) & ~1023;
         if (g.img_h1) g.a_stage_bytes = (g.a_tx_bytes + ((g.R - 1) * g.hw + g.S) * GM_ROW_BYTES + 1023) & ~1023;   // + the zero tail
@@ -1299,7 +1337,7 @@ static int launch_conv_mode(const CUtensorMap &tmA, const CUtensorMap &tmB, cons
 }
 
 // which kernel instance runs a planned conv
-enum ConvVariant { CV_NONE = 0, CV_64_M0, CV_64_M1, CV_64_M2, CV_64_M3, CV_128_M0, CV_128_M4, CV_128_M4_PAIR, CV_256_M0, CV_I8_64, CV_I8_128 };
+enum ConvVariant { CV_NONE = 0, CV_64_M0, CV_64_M1, CV_64_M2, CV_64_M3, CV_64_M3_PAIR, CV_128_M0, CV_128_M4, CV_128_M4_PAIR, CV_256_M0, CV_I8_64, CV_I8_128 };
 
 // general_prog: the step table (prog_mma) is in use; otherwise resident weights are tile = tap
 static int pick_variant(ConvGeom &g, int block_n, int kind, bool general_prog, ConvVariant &v)
@@ -1321,7 +1359,7 @@ static int pick_variant(ConvGeom &g, int block_n, int kind, bool general_prog, C
     }
     if (g.prog_steps == 0) { v = block_n == 64 ? CV_64_M0 : (block_n == 128 ? CV_128_M0 : CV_256_M0); return TQ_OK; }
     if (block_n != 64) return fail(TQ_ERR_UNSUPPORTED, "resident-weight mode is built for BLOCK_N = 64 only");
-    v = general_prog ? CV_64_M2 : (g.halo ? CV_64_M3 : CV_64_M1);
+    v = general_prog ? CV_64_M2 : (g.halo ? (g.pair ? CV_64_M3_PAIR : CV_64_M3) : CV_64_M1);
     return TQ_OK;
 }
 
@@ -1333,6 +1371,7 @@ static int launch_variant(ConvVariant v, const CUtensorMap &tmA, const CUtensorM
     case CV_64_M1: return launch_conv_mode<64, 1>(tmA, tmB, tmC, tmD, tmR, g, s);
     case CV_64_M2: return launch_conv_mode<64, 2>(tmA, tmB, tmC, tmD, tmR, g, s);
     case CV_64_M3: return launch_conv_mode<64, 3>(tmA, tmB, tmC, tmD, tmR, g, s);
+    case CV_64_M3_PAIR: return launch_conv_mode<64, 3, 0, 2>(tmA, tmB, tmC, tmD, tmR, g, s);
     case CV_128_M0: return launch_conv_mode<128, 0>(tmA, tmB, tmC, tmD, tmR, g, s);
     case CV_128_M4: return launch_conv_mode<128, 4>(tmA, tmB, tmC, tmD, tmR, g, s);
     case CV_128_M4_PAIR: return launch_conv_mode<128, 4, 0, 2>(tmA, tmB, tmC, tmD, tmR, g, s);
@@ -1458,6 +1497,14 @@ static int plan_conv(const ConvArgs &a, ConvPlan &pl)
                 g = h;
                 g.halo = 1;
                 g.halo_baseoff = halo_baseoff ? 1 : 0;
+                // CTA pairs (opt-in, TQ_CONV_PAIR3=1): N = 64 MMAs are bound by shared-memory operand reads (A 4 KB + B 2 KB per
+                // 32-cycle MMA); with half of every weight tile per CTA it is 4 + 1 KB.  Measured: the 56x56 64 -> 64 layer with
+                // an fp32-only epilogue 0.0756 -> 0.0569 ms (1040 TFLOP/s), but NO change inside ResNet-18 / VGG-16, where
+                // these layers also encode their output and the epilogue's instruction issue (30 per value) is what bounds
+                // them -- so single CTAs stay the default.
+                static const int pair3_env = getenv("TQ_CONV_PAIR3") ? atoi(getenv("TQ_CONV_PAIR3")) : 0;
+                static const int pair_env3 = getenv("TQ_CONV_PAIR") ? atoi(getenv("TQ_CONV_PAIR")) : 1;
+                if (pair3_env && pair_env3 && !g.halo_baseoff && Cout % 16 == 0 && ((g.m_tiles + 1) / 2) * g.n_tiles >= num_sms() / 2) g.pair = 1;
             }
         }
     }
@@ -1507,7 +1554,7 @@ static int plan_conv(const ConvArgs &a, ConvPlan &pl)
         if ((rc = encode_map(enc, &pl.tmA, op_dt, op_es, a.act, 4, dims, box, estr, "activations")) != TQ_OK) return rc;
     }
     {   // weights: (C, Cout, planes * R*S), one K block of one tap per tile
-        if (g.prog_steps > 0 && g.kc_blocks != 1) { g.halo = 0; g.prog_steps = 0; g.nb_tiles = 0; }   // (program mode: one block per tap)
+        if (g.prog_steps > 0 && g.kc_blocks != 1) { g.halo = 0; g.pair = 0; g.prog_steps = 0; g.nb_tiles = 0; }   // (program mode: one block per tap)
         cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Cout, (cuuint64_t)(g.planes_w * R * S)};
         cuuint32_t box[3] = {(cuuint32_t)g.kblk, (cuuint32_t)(g.pair ? block_n / 2 : block_n), 1};   // (a pair CTA loads half a tile)
         cuuint32_t estr[3] = {1, 1, 1};

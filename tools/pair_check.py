@@ -12,7 +12,8 @@ torch.manual_seed(0)
 bad = 0
 for (N, H, C, Cout, amp) in ((32, 28, 128, 128, 40), (33, 28, 128, 128, 40), (64, 14, 256, 256, 40), (25, 28, 64, 192, 60), (256, 28, 128, 128, 40),
                             (256, 7, 512, 512, 20), (5, 7, 128, 128, 40), (2, 7, 64, 128, 40), (301, 7, 256, 256, 30), (37, 4, 128, 256, 40),
-                            (64, 5, 128, 128, 40)):
+                            (64, 5, 128, 128, 40),
+                            (16, 56, 64, 64, 60), (5, 56, 64, 64, 60), (256, 56, 64, 64, 60), (9, 40, 32, 48, 60), (7, 60, 64, 16, 60)):
     act = (torch.randint(0, 513, (N, H, H, C), device="cuda") * (torch.rand(N, H, H, C, device="cuda") < 0.5)).half()
     wgt = (torch.randn(9, Cout, C, device="cuda") * amp).round().clamp(-256, 256).half().contiguous()
     plan = conv_codes.plan_weight(wgt, 512)
