@@ -948,12 +948,39 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         };
         TR_DECL(8);
         TR_T0(te0);
-        for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
+        // Tile coordinates and the accumulator stage advance by carries, not by the seven run-time integer divisions per
+        // tile the plain decode costs every epilogue thread (~150 of the ~950 instructions per 32-column chunk).
+        const int n_tiles = g.n_tiles, tiles_w = g.tiles_w, tiles_h = g.tiles_h;
+        int n_tile = tile_first % n_tiles;
+        int tw, th, tn;
+        {
+            const int m0 = m_tile_of(tile_first);
+            tw = m0 % tiles_w; th = (m0 / tiles_w) % tiles_h; tn = m0 / (tiles_w * tiles_h);
+        }
+        const int step_n = tile_step % n_tiles, step_m = (tile_step / n_tiles) * CG;       // M tiles per loop step (before the carry)
+        const int s_w = step_m % tiles_w, s_h = (step_m / tiles_w) % tiles_h, s_n = step_m / (tiles_w * tiles_h);
+        const int u_w = CG % tiles_w, u_h = (CG / tiles_w) % tiles_h, u_n = CG / (tiles_w * tiles_h);   // the carry out of n_tile
+        auto add_m = [&](int dw, int dh, int dn) {
+            tw += dw;
+            int c = tw >= tiles_w ? 1 : 0;
+            tw -= c ? tiles_w : 0;
+            th += dh + c;
+            c = th >= tiles_h ? 1 : 0;
+            th -= c ? tiles_h : 0;
+            tn += dn + c;
+        };
+        int acc = 0;                                                  // accumulator stage of this tile and its use parity
+        uint32_t acc_phase = 0;
+        auto next_tile = [&]() {
+            n_tile += step_n;
+            const bool carry = n_tile >= n_tiles;
+            n_tile -= carry ? n_tiles : 0;
+            add_m(s_w, s_h, s_n);
+            if (carry) add_m(u_w, u_h, u_n);
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+        };
+        for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it, next_tile()) {
             if (!single && (it & 1) != pair) continue;
-            const int acc = it % ACC_STAGES;                          // accumulator stage of this tile and its use parity
-            const uint32_t acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
-            const int n_tile = tile % g.n_tiles, m_tile = m_tile_of(tile);
-            const int tw = m_tile % g.tiles_w, th = (m_tile / g.tiles_w) % g.tiles_h, tn = m_tile / (g.tiles_w * g.tiles_h);
             const int w0 = tw * g.wbox, h0 = th * g.hbox, n0 = tn * g.nbox;
 
             if (g.dbg_skip_epilogue) {
