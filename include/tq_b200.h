@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define TQ_VERSION 200
+#define TQ_VERSION 201
 
 /* status codes */
 #define TQ_OK               0
@@ -273,11 +273,21 @@ int tq_depthwise3x3_codes(const void *act_codes, const int32_t *wgt_codes, float
 
 /*
  * Tail of an unwrapped conv (the first conv of every CNN, cnn_models/__init__.py:34-36) fused with the first wrapped
- * layer's LinearQuantize (tr_layer.py:96-99): x fp32 [npix][C] -> fma(x, bn_a, bn_b) -> activation (relu as above) ->
- * out_f32 and / or fp16 term codes.  C % 4 == 0.
+ * layer's LinearQuantize (tr_layer.py:96-99): x fp32 [npix][C] -> + bias (the conv's own bias, one fp32 add, when the
+ * conv ran without it; may be NULL) -> fma(x, bn_a, bn_b) -> activation (relu as above) -> out_f32 and / or fp16 term
+ * codes.  C % 4 == 0.
  */
-int tq_bn_act_encode(const float *x, const float *bn_a, const float *bn_b, float *out_f32, void *out_codes,
-                     int64_t npix, int C, int relu, float next_sf, int next_bits, int next_terms, void *stream);
+int tq_bn_act_encode(const float *x, const float *bias, const float *bn_a, const float *bn_b, float *out_f32,
+                     void *out_codes, int64_t npix, int C, int relu, float next_sf, int next_bits, int next_terms,
+                     void *stream);
+
+/*
+ * nn.MaxPool2d(k, stride, pad) (floor mode, no dilation) on an fp16 NHWC tensor: the term codes between the convs of
+ * the VGG-style stacks (cnn_models/__init__.py wraps the convs, the pools stay: for g = 1 the truncated code is monotone
+ * in the non-negative value, so pooling codes == encoding pooled values).  C % 8 == 0.
+ */
+int tq_maxpool2d_f16(const void *x_f16, void *y_f16, int N, int H, int W, int C, int k, int stride, int pad,
+                     void *stream);
 
 /*
  * uint8 NHWC images [npix][3] -> normalised bf16 [npix][3]: ((u8 / 255) - mean[c]) / std[c], each step one fp32 IEEE

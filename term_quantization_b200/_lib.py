@@ -33,7 +33,8 @@ SYMBOLS = {
     "tq_codes_to_planes": (_i, [_p, _p, _i64, _i, _p, _p]),
     "tq_conv_weight_l1": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "tq_depthwise3x3_codes": (_i, [_p] * 7 + [_i] * 5 + [_f, _i, _i, _f, _i, _i, _p]),
-    "tq_bn_act_encode": (_i, [_p] * 5 + [_i64, _i, _i, _f, _i, _i, _p]),
+    "tq_bn_act_encode": (_i, [_p] * 6 + [_i64, _i, _i, _f, _i, _i, _p]),
+    "tq_maxpool2d_f16": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "tq_u8_normalize_bf16": (_i, [_p, _p, _i64, _p, _p, _p]),
     "tq_bn_relu_maxpool_encode": (_i, [_p] * 5 + [_i] * 5 + [_f, _i, _i, _p]),
     "tq_stem_conv7x7s2": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),

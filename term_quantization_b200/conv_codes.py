@@ -283,8 +283,25 @@ def depthwise3x3_codes(act, wgt, stride, scale, *, bias=None, bn=None, relu=Fals
     return out, codes
 
 
-def bn_act_encode(x_nhwc, bn=None, relu=False, want_f32=False, next_quant=None):
-    """fp32 [..., C] -> fma(x, a, b) -> activation -> fp32 and / or fp16 term codes (tq_bn_act_encode)."""
+def maxpool_codes(codes_nhwc, kernel_size, stride=None, padding=0):
+    """nn.MaxPool2d(kernel_size, stride, padding) (floor mode) on fp16 NHWC term codes (tq_maxpool2d_f16)."""
+    k = kernel_size if isinstance(kernel_size, int) else kernel_size[0]
+    st = k if stride is None else (stride if isinstance(stride, int) else stride[0])
+    pd = padding if isinstance(padding, int) else padding[0]
+    if codes_nhwc.dtype != torch.float16 or not codes_nhwc.is_contiguous() or not codes_nhwc.is_cuda:
+        raise RuntimeError("maxpool_codes expects a contiguous fp16 CUDA [N, H, W, C] tensor")
+    N, H, W, C = codes_nhwc.shape
+    Ho, Wo = (H + 2 * pd - k) // st + 1, (W + 2 * pd - k) // st + 1
+    out = torch.empty((N, Ho, Wo, C), dtype=torch.float16, device=codes_nhwc.device)
+    with torch.cuda.device(codes_nhwc.device):
+        rc = _lib.lib().tq_maxpool2d_f16(codes_nhwc.data_ptr(), out.data_ptr(), N, H, W, C, k, st, pd,
+                                         torch.cuda.current_stream(codes_nhwc.device).cuda_stream)
+    _lib.check(rc)
+    return out
+
+
+def bn_act_encode(x_nhwc, bn=None, relu=False, want_f32=False, next_quant=None, bias=None):
+    """fp32 [..., C] -> (+ bias) -> fma(x, a, b) -> activation -> fp32 and / or fp16 term codes (tq_bn_act_encode)."""
     if x_nhwc.dtype != torch.float32 or not x_nhwc.is_contiguous() or not x_nhwc.is_cuda:
         raise RuntimeError("bn_act_encode expects a contiguous fp32 CUDA tensor with channels last")
     C = x_nhwc.shape[-1]
@@ -293,8 +310,10 @@ def bn_act_encode(x_nhwc, bn=None, relu=False, want_f32=False, next_quant=None):
     sf, bits, terms = next_quant if next_quant else (1.0, 1, 0)
     ptr = lambda t: t.data_ptr() if t is not None else None   # noqa: E731
     with torch.cuda.device(x_nhwc.device):
+        if bias is not None and (bias.dtype != torch.float32 or bias.numel() != C or not bias.is_contiguous() or bias.device != x_nhwc.device):
+            raise RuntimeError("bn_act_encode: bias must be a contiguous fp32 [C] tensor on the input's device")
         rc = _lib.lib().tq_bn_act_encode(
-            x_nhwc.data_ptr(), ptr(bn[0]) if bn else None, ptr(bn[1]) if bn else None, ptr(out), ptr(codes),
+            x_nhwc.data_ptr(), ptr(bias), ptr(bn[0]) if bn else None, ptr(bn[1]) if bn else None, ptr(out), ptr(codes),
             x_nhwc.numel() // C, C, _relu_code(relu), float(sf), int(bits), int(terms),
             torch.cuda.current_stream(x_nhwc.device).cuda_stream)
     _lib.check(rc)

@@ -230,7 +230,7 @@ depthwise3x3_codes_kernel(const __grid_constant__ CUtensorMap tmIn, const int32_
     }
 }
 
-// fp32 NHWC -> fma(x, a[c], b[c]) -> activation -> fp32 and / or fp16 term codes: the tail of an unwrapped first conv
+// fp32 NHWC -> (+ bias[c]) -> fma(x, a[c], b[c]) -> activation -> fp32 and / or fp16 term codes: the tail of an unwrapped first conv
 // (cnn_models/__init__.py:34-36) fused with the first wrapped layer's LinearQuantize (tr_layer.py:96-99).
 __global__ void __launch_bounds__(256)
 bn_act_encode_kernel(const float *__restrict__ x, float *__restrict__ out_f32, __half *__restrict__ out_codes, int64_t n4, int C,
@@ -251,6 +251,11 @@ bn_act_encode_kernel(const float *__restrict__ x, float *__restrict__ out_f32, _
         const int c4 = (int)(t % c4n);
         const float4 v = __ldg(reinterpret_cast<const float4 *>(x) + t);
         float tv[4] = {v.x, v.y, v.z, v.w};
+        if (p.bias) {                                   // the conv's own bias: one fp32 add, as cuDNN / torch apply it
+            const float4 bi = __ldg(reinterpret_cast<const float4 *>(p.bias) + c4);
+            tv[0] = __fadd_rn(tv[0], bi.x); tv[1] = __fadd_rn(tv[1], bi.y);
+            tv[2] = __fadd_rn(tv[2], bi.z); tv[3] = __fadd_rn(tv[3], bi.w);
+        }
         if (p.bn_a) {
             const float4 a = __ldg(reinterpret_cast<const float4 *>(p.bn_a) + c4);
             const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bn_b) + c4);
@@ -270,6 +275,40 @@ bn_act_encode_kernel(const float *__restrict__ x, float *__restrict__ out_f32, _
             }
             reinterpret_cast<uint2 *>(out_codes)[t] = make_uint2(hc[0] | (hc[1] << 16), hc[2] | (hc[3] << 16));
         }
+    }
+}
+
+// Max-pool on fp16 NHWC tensors (term codes between the convs of the VGG-style stacks: for g = 1 the truncated code is
+// monotone in the value, so pooling the codes equals encoding the pooled values).  One thread = 8 channels (16 bytes) of
+// one output pixel; window positions outside the map are skipped (torch's -inf padding).  Memory-bound.
+__global__ void __launch_bounds__(256)
+maxpool2d_f16_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, int N, int H, int W, int C8, int Ho, int Wo,
+                     int k, int stride, int pad)
+{
+    const int64_t total = (int64_t)N * Ho * Wo * C8;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c8 = (int)(t % C8);
+        const int64_t pix = t / C8;
+        const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho), n = (int)(pix / ((int64_t)Wo * Ho));
+        const __half2 ninf = __half2half2(__ushort_as_half((unsigned short)0xFC00u));
+        __half2 m0 = ninf, m1 = ninf, m2 = ninf, m3 = ninf;
+        for (int dy = 0; dy < k; ++dy) {
+            const int h = ho * stride - pad + dy;
+            if (h < 0 || h >= H) continue;
+            for (int dx = 0; dx < k; ++dx) {
+                const int w = wo * stride - pad + dx;
+                if (w < 0 || w >= W) continue;
+                const uint4 v = __ldcs(x + (((int64_t)n * H + h) * W + w) * C8 + c8);
+                m0 = __hmax2(m0, *reinterpret_cast<const __half2 *>(&v.x));
+                m1 = __hmax2(m1, *reinterpret_cast<const __half2 *>(&v.y));
+                m2 = __hmax2(m2, *reinterpret_cast<const __half2 *>(&v.z));
+                m3 = __hmax2(m3, *reinterpret_cast<const __half2 *>(&v.w));
+            }
+        }
+        uint4 o;
+        o.x = *reinterpret_cast<const uint32_t *>(&m0); o.y = *reinterpret_cast<const uint32_t *>(&m1);
+        o.z = *reinterpret_cast<const uint32_t *>(&m2); o.w = *reinterpret_cast<const uint32_t *>(&m3);
+        y[t] = o;
     }
 }
 
@@ -377,18 +416,19 @@ extern "C" int tq_depthwise3x3_codes(const void *act_codes, const int32_t *wgt_c
     return check_launch("depthwise3x3_codes_kernel");
 }
 
-extern "C" int tq_bn_act_encode(const float *x, const float *bn_a, const float *bn_b, float *out_f32, void *out_codes,
-                                int64_t npix, int C, int relu, float next_sf, int next_bits, int next_terms, void *stream)
+extern "C" int tq_bn_act_encode(const float *x, const float *bias, const float *bn_a, const float *bn_b, float *out_f32,
+                                void *out_codes, int64_t npix, int C, int relu, float next_sf, int next_bits, int next_terms,
+                                void *stream)
 {
     if (!x || (!out_f32 && !out_codes)) return fail(TQ_ERR_INVALID, "NULL pointer");
     if (npix < 0 || C < 4 || C % 4) return fail(TQ_ERR_INVALID, "bad shape (C must be a multiple of 4)");
     if ((bn_a == nullptr) != (bn_b == nullptr)) return fail(TQ_ERR_INVALID, "bn_a and bn_b go together");
     if (relu < 0 || relu > 2) return fail(TQ_ERR_INVALID, "relu: 0 none, 1 ReLU, 2 ReLU6");
-    if ((((uintptr_t)x | (uintptr_t)bn_a | (uintptr_t)bn_b | (uintptr_t)out_f32 | (uintptr_t)out_codes) & 15u) != 0)
+    if ((((uintptr_t)x | (uintptr_t)bias | (uintptr_t)bn_a | (uintptr_t)bn_b | (uintptr_t)out_f32 | (uintptr_t)out_codes) & 15u) != 0)
         return fail(TQ_ERR_INVALID, "pointers must be 16-byte aligned");
     if (npix == 0) return TQ_OK;
     DwParams p{};
-    p.C = C; p.bn_a = bn_a; p.bn_b = bn_b; p.relu = relu; p.write_f32 = out_f32 ? 1 : 0;
+    p.C = C; p.bias = bias; p.bn_a = bn_a; p.bn_b = bn_b; p.relu = relu; p.write_f32 = out_f32 ? 1 : 0;
     int rc = fill_quant(p, out_codes, next_sf, next_bits, next_terms);
     if (rc != TQ_OK) return rc;
     const int64_t n4 = npix * (C / 4);
@@ -399,4 +439,23 @@ extern "C" int tq_bn_act_encode(const float *x, const float *bn_a, const float *
     bn_act_encode_kernel<<<(int)blocks, 256, smem, (cudaStream_t)stream>>>(x, out_f32, (__half *)out_codes, n4, C, p);
     count_launch();
     return check_launch("bn_act_encode_kernel");
+}
+
+extern "C" int tq_maxpool2d_f16(const void *x_f16, void *y_f16, int N, int H, int W, int C, int k, int stride, int pad,
+                                void *stream)
+{
+    if (!x_f16 || !y_f16) return fail(TQ_ERR_INVALID, "NULL pointer");
+    if (N < 1 || H < 1 || W < 1 || C < 8 || C % 8) return fail(TQ_ERR_INVALID, "bad shape (C must be a multiple of 8)");
+    if (k < 1 || k > 7 || stride < 1 || pad < 0 || 2 * pad > k) return fail(TQ_ERR_INVALID, "bad pooling window");
+    if ((((uintptr_t)x_f16 | (uintptr_t)y_f16) & 15u) != 0) return fail(TQ_ERR_INVALID, "pointers must be 16-byte aligned");
+    const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;      // floor mode
+    if (Ho < 1 || Wo < 1) return fail(TQ_ERR_INVALID, "empty output");
+    const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 32;
+    if (blocks > cap) blocks = cap;
+    maxpool2d_f16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4 *)x_f16, (uint4 *)y_f16, N, H, W, C / 8, Ho, Wo,
+                                                                        k, stride, pad);
+    count_launch();
+    return check_launch("maxpool2d_f16_kernel");
 }

@@ -21,6 +21,7 @@ BatchNorm, 1-2 ulp from fmaf) a value sitting on a quantisation boundary can rou
 """
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import conv_codes, tr_cuda, tr_layer
 
@@ -189,6 +190,14 @@ class FusedResNet(nn.Module):
         return m.fc(torch.flatten(m.avgpool(y), 1))
 
 
+def _square(pool):
+    """nn.MaxPool2d with one window size / stride / padding for both axes (what tq_maxpool2d_f16 takes)."""
+    def one(v):
+        return v if isinstance(v, int) else (v[0] if v[0] == v[1] else None)
+    k, s, p = one(pool.kernel_size), one(pool.stride if pool.stride is not None else pool.kernel_size), one(pool.padding)
+    return k is not None and s is not None and p is not None and k <= 7 and 2 * p <= k
+
+
 class FusedVGG(nn.Module):
     """Fused execution of a TQ-converted torchvision VGG (`features` = conv [-> BatchNorm] -> ReLU [-> MaxPool 2x2]
     chains; BASELINE.json configs[2]).  Every wrapped conv is one launch of the tcgen05 kernel with bias,
@@ -258,10 +267,14 @@ class FusedVGG(nn.Module):
                 and isinstance(stem[2], nn.ReLU) and stem[0].out_channels % 4 == 0):
             # unwrapped first conv on cuDNN fp32; its BatchNorm + ReLU + the first wrapped conv's encode in ONE pass
             # (tq_bn_act_encode) instead of three passes over the largest activation of the network
-            y = stem[0](x).permute(0, 2, 3, 1).contiguous()
+            # (the conv's bias rides along as one fp32 add in that pass: torch would add it in a pass of its own over
+            # the 1.6 GB map)
+            c0 = stem[0]
+            y = F.conv2d(x, c0.weight, None, c0.stride, c0.padding, c0.dilation, c0.groups).permute(0, 2, 3, 1).contiguous()
             if getattr(self, "_stem_bn", None) is None:
                 self._stem_bn = _bn_affine(stem[1])
-            _, codes = conv_codes.bn_act_encode(y, self._stem_bn, relu=True, next_quant=q0)
+            _, codes = conv_codes.bn_act_encode(y, self._stem_bn, relu=True, next_quant=q0,
+                                                bias=None if c0.bias is None else c0.bias.detach().float().contiguous())
         else:
             for mod in stem:                                      # any other stem: module by module on torch
                 x = mod(x)
@@ -279,6 +292,9 @@ class FusedVGG(nn.Module):
                     out, _ = conv(codes, relu=relu, want_f32=True)
                     codes = None
             else:                                                   # max-pool: on the codes (exact), or on the last fp32 map
+                if codes is not None and codes.shape[-1] % 8 == 0 and _square(payload):
+                    codes = conv_codes.maxpool_codes(codes, payload.kernel_size, payload.stride, payload.padding)
+                    continue
                 t = codes if codes is not None else out
                 t = payload(t.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
                 if codes is not None:

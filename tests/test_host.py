@@ -19,7 +19,7 @@ def test_capi_exports_every_declared_symbol():
     declared = set(re.findall(r"\b(tq_[a-z0-9_]+)\s*\(", header))
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     L = _lib.lib()                       # loads, binds every symbol (AttributeError otherwise)
-    assert L.tq_version() == 200
+    assert L.tq_version() == 201
     assert isinstance(_lib.launch_count(), int)
 
 

@@ -357,6 +357,27 @@ def test_depthwise_and_bn_act_kernels_against_cpu_emulation():
         o2, c2 = conv_codes.bn_act_encode(x, (a, b), relu=relu, want_f32=True, next_quant=nq)
         assert np.array_equal(o2.cpu().numpy(), want)
         assert np.array_equal(c2.cpu().numpy().astype(np.int32), fused_emul.encode(want, nq))
+        # ... with the producing conv's bias as one fp32 add before the affine (what torch's conv2d(bias=...) computes)
+        bias = torch.randn(C, device="cuda", generator=g)
+        want_b = fused_emul._act(O.fma_channels((x + bias).cpu().numpy(), a.cpu().numpy(), b.cpu().numpy()), relu)
+        o3, c3 = conv_codes.bn_act_encode(x, (a, b), relu=relu, want_f32=True, next_quant=nq, bias=bias)
+        assert np.array_equal(o3.cpu().numpy(), want_b)
+        assert np.array_equal(c3.cpu().numpy().astype(np.int32), fused_emul.encode(want_b, nq))
+
+
+def test_maxpool_on_codes_equals_torch():
+    """tq_maxpool2d_f16 (the pools between the wrapped convs of the VGG-style stacks, run on fp16 term codes) against
+    nn.MaxPool2d on the same tensor: VGG's 2x2/s2, AlexNet's 3x3/s2, ResNet's 3x3/s2/p1, odd maps, signed values."""
+    from term_quantization_b200 import conv_codes
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for (N, H, W, C, k, s, p) in ((2, 224, 224, 64, 2, 2, 0), (3, 13, 13, 256, 3, 2, 0), (2, 57, 31, 128, 3, 2, 1),
+                                  (1, 7, 9, 8, 2, 2, 0), (5, 14, 14, 512, 2, 2, 0), (2, 6, 6, 24, 3, 1, 1)):
+        codes = (torch.randint(-512, 513, (N, H, W, C), device="cuda", generator=g)).half()
+        got = conv_codes.maxpool_codes(codes, k, s, p)
+        want = torch.nn.functional.max_pool2d(codes.permute(0, 3, 1, 2), k, s, p).permute(0, 2, 3, 1)
+        assert got.shape == want.shape and torch.equal(got, want.contiguous()), (N, H, W, C, k, s, p)
+    with pytest.raises(Exception):
+        conv_codes.maxpool_codes(torch.zeros(1, 4, 4, 12, device="cuda").half(), 2)          # C % 8 != 0
 
 
 def test_fused_mobilenet_v2_bit_exact_against_cpu_emulation():

@@ -15,12 +15,23 @@ torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 iters = 5
-model = bench.build_tq_resnet18(dev)
+arch = sys.argv[2] if len(sys.argv) > 2 else "resnet18"          # or vgg16_bn (BASELINE.json configs[2], batch 128)
 x = torch.randn(batch, 3, 224, 224, device=dev).contiguous(memory_format=torch.channels_last)
-inference.calibrate(model, [x[:64]])
+if arch == "resnet18":
+    model = bench.build_tq_resnet18(dev)
+else:
+    import torchvision
+    from term_quantization_b200 import cnn_models
+    torch.manual_seed(0)
+    base = getattr(torchvision.models, arch)(weights=None).to(dev).eval()
+    model = cnn_models.convert_model(base, cnn_models.static_conv_layer_settings(base, 9, 8, 12), 9, 3)
+inference.calibrate(model, [x[:16]])
 model = model.to(memory_format=torch.channels_last)
-tr_layer.use_tensor_cores(model)
-f = fused.FusedResNet(model)
+if arch == "resnet18":
+    tr_layer.use_tensor_cores(model)
+    f = fused.FusedResNet(model)
+else:
+    f = fused.FusedVGG(model)
 
 records = []
 recording = False
