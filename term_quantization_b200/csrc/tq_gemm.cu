@@ -1520,7 +1520,11 @@ static int plan_conv(const ConvArgs &a, ConvPlan &pl)
         static const bool halo_baseoff = getenv("TQ_CONV_HALO_BASEOFF") ? atoi(getenv("TQ_CONV_HALO_BASEOFF")) != 0 : false;
         if (!no_halo && g.kc_blocks == 1 && stride == 1 && R * S > 1) {
             ConvGeom h = g;
-            if (pick_box_halo(h) && h.m_tiles <= g.m_tiles + g.m_tiles / 8) {
+            // (halo tiles are a little less dense -- up to TQ_CONV_HALO_SLACK percent more tiles are accepted: one box per
+            // tile instead of R*S is worth more than that.  Measured on VGG-16's 224x224 64 -> 64 layer, 14 % more tiles:
+            // 0.740 -> 0.621 ms)
+            static const int slack = getenv("TQ_CONV_HALO_SLACK") ? atoi(getenv("TQ_CONV_HALO_SLACK")) : 16;
+            if (pick_box_halo(h) && (long)h.m_tiles * 100 <= (long)g.m_tiles * (100 + slack)) {
                 g = h;
                 g.halo = 1;
                 g.halo_baseoff = halo_baseoff ? 1 : 0;
@@ -1559,7 +1563,8 @@ static int plan_conv(const ConvArgs &a, ConvPlan &pl)
     }
     if (kind == 0 && !no_halo4 && g.prog_steps == 0 && !g.halo && block_n == 128 && stride == 1 && R * S > 1) {
         ConvGeom h = g;
-        if (pick_box_halo(h) && h.m_tiles <= g.m_tiles + g.m_tiles / 8) {
+        static const int slack4 = getenv("TQ_CONV_HALO_SLACK") ? atoi(getenv("TQ_CONV_HALO_SLACK")) : 16;
+        if (pick_box_halo(h) && (long)h.m_tiles * 100 <= (long)g.m_tiles * (100 + slack4)) {
             h.step_w = h.wbox; h.step_h = h.hbox;
             g = h;
             g.halo = 1;
