@@ -282,6 +282,18 @@ int tq_bn_act_encode(const float *x, const float *bias, const float *bn_a, const
                      void *stream);
 
 /*
+ * The unwrapped first conv of the VGG-style / depthwise CNNs (cnn_models/__init__.py:34-36: nn.Conv2d(3, Cout, 3, stride,
+ * padding=1), Cout 32 or 64, stride 1 or 2) in fp32 on the CUDA cores, fused with what follows it: + bias, BatchNorm
+ * affine, ReLU / ReLU6 and the first wrapped layer's LinearQuantize (tr_layer.py:96-99).  x fp32 NHWC [N][H][W][3],
+ * wgt fp32 [3][3][3][Cout] (filter row, filter column, input channel, output channel); sums run in that order, one
+ * fmaf per term, bias added after the sum.  out_f32 and / or fp16 term codes, NHWC.  An fp32 conv: it equals cuDNN's
+ * up to the summation order, not bit for bit.
+ */
+int tq_first_conv3x3_fused(const float *x, const float *wgt, const float *bias, const float *bn_a, const float *bn_b,
+                           float *out_f32, void *out_codes, int N, int H, int W, int Cout, int stride, int relu,
+                           float next_sf, int next_bits, int next_terms, void *stream);
+
+/*
  * nn.MaxPool2d(k, stride, pad) (floor mode, no dilation) on an fp16 NHWC tensor: the term codes between the convs of
  * the VGG-style stacks (cnn_models/__init__.py wraps the convs, the pools stay: for g = 1 the truncated code is monotone
  * in the non-negative value, so pooling codes == encoding pooled values).  C % 8 == 0.

@@ -35,6 +35,7 @@ SYMBOLS = {
     "tq_depthwise3x3_codes": (_i, [_p] * 7 + [_i] * 5 + [_f, _i, _i, _f, _i, _i, _p]),
     "tq_bn_act_encode": (_i, [_p] * 6 + [_i64, _i, _i, _f, _i, _i, _p]),
     "tq_maxpool2d_f16": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "tq_first_conv3x3_fused": (_i, [_p] * 7 + [_i, _i, _i, _i, _i, _i, _f, _i, _i, _p]),
     "tq_u8_normalize_bf16": (_i, [_p, _p, _i64, _p, _p, _p]),
     "tq_bn_relu_maxpool_encode": (_i, [_p] * 5 + [_i] * 5 + [_f, _i, _i, _p]),
     "tq_stem_conv7x7s2": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),

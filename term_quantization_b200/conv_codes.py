@@ -283,6 +283,40 @@ def depthwise3x3_codes(act, wgt, stride, scale, *, bias=None, bn=None, relu=Fals
     return out, codes
 
 
+def pack_first_conv_weight(w_oihw):
+    """(Cout, 3, 3, 3) conv weight -> fp32 [3][3][3][Cout] (filter row, filter column, input channel, output channel)."""
+    if w_oihw.dim() != 4 or w_oihw.shape[1:] != (3, 3, 3):
+        raise RuntimeError("pack_first_conv_weight expects a (Cout, 3, 3, 3) weight")
+    return w_oihw.detach().float().permute(2, 3, 1, 0).contiguous()
+
+
+def first_conv3x3_fused(x_nhwc, w_packed, stride=1, bias=None, bn=None, relu=False, want_f32=False, next_quant=None):
+    """nn.Conv2d(3, Cout, 3, stride, padding=1) in fp32 on an fp32 NHWC [N, H, W, 3] tensor, fused with + bias,
+    BatchNorm affine, ReLU / ReLU6 and the next quantiser (tq_first_conv3x3_fused).  Returns (out fp32 or None,
+    fp16 term codes or None), both [N, Ho, Wo, Cout]."""
+    if x_nhwc.dtype != torch.float32 or not x_nhwc.is_contiguous() or not x_nhwc.is_cuda or x_nhwc.shape[-1] != 3:
+        raise RuntimeError("first_conv3x3_fused expects a contiguous fp32 CUDA [N, H, W, 3] tensor")
+    N, H, W, _ = x_nhwc.shape
+    Cout = w_packed.shape[-1]
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    out = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=x_nhwc.device) if want_f32 else None
+    codes = torch.empty((N, Ho, Wo, Cout), dtype=torch.float16, device=x_nhwc.device) if next_quant else None
+    if out is None and codes is None:
+        raise RuntimeError("first_conv3x3_fused: nothing to compute (want_f32 or next_quant)")
+    sf, bits, terms = next_quant if next_quant else (1.0, 1, 0)
+    ptr = lambda t: t.data_ptr() if t is not None else None   # noqa: E731
+    for t in (bias, bn[0] if bn else None, bn[1] if bn else None):
+        if t is not None and (t.dtype != torch.float32 or t.numel() != Cout or not t.is_contiguous() or t.device != x_nhwc.device):
+            raise RuntimeError("first_conv3x3_fused: bias / bn must be contiguous fp32 [Cout] tensors on the input's device")
+    with torch.cuda.device(x_nhwc.device):
+        rc = _lib.lib().tq_first_conv3x3_fused(
+            x_nhwc.data_ptr(), w_packed.data_ptr(), ptr(bias), ptr(bn[0]) if bn else None, ptr(bn[1]) if bn else None,
+            ptr(out), ptr(codes), N, H, W, Cout, int(stride), _relu_code(relu), float(sf), int(bits), int(terms),
+            torch.cuda.current_stream(x_nhwc.device).cuda_stream)
+    _lib.check(rc)
+    return out, codes
+
+
 def maxpool_codes(codes_nhwc, kernel_size, stride=None, padding=0):
     """nn.MaxPool2d(kernel_size, stride, padding) (floor mode) on fp16 NHWC term codes (tq_maxpool2d_f16)."""
     k = kernel_size if isinstance(kernel_size, int) else kernel_size[0]

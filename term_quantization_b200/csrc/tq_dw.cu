@@ -312,6 +312,128 @@ maxpool2d_f16_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, int N, 
     }
 }
 
+// =============================================================================================
+// First conv of the VGG-style / depthwise CNNs (3x3, 3 input channels, never wrapped: cnn_models/__init__.py:34-36) on the
+// CUDA cores in fp32, with its bias, BatchNorm, ReLU / ReLU6 and the first wrapped layer's LinearQuantize in the same
+// kernel: the fp32 map (1.6 GB for VGG-16 at batch 128) is never written unless asked for.  27 FMAs per output in a fixed
+// order (filter row, filter column, channel), bias added after the sum as cuDNN does.
+// One thread = 8 output channels x 8 pixels (64 accumulators); a warp = COUT/8 channel groups x PGW = 256/COUT pixel
+// groups; pixel j of group pg is column j * PGW + pg of the tile, so the lanes of a warp read ADJACENT input pixels
+// (bank-conflict free for both strides: 3 or 6 floats apart) and a 16-byte store instruction writes PGW adjacent pixels
+// x COUT channels = 512 contiguous bytes.  Operands come from shared memory as broadcasts (the lanes of a pixel group
+// share the input value, the lanes of a channel group the weights).
+// =============================================================================================
+struct FirstConvParams {
+    int N, H, W, Ho, Wo, stride;
+    const float *bias, *bn_a, *bn_b;
+    int relu, write_f32, write_codes;
+    float next_sf;
+    int next_bits, next_terms, next_fastdiv;
+};
+
+template <int COUT, int STRIDE, bool FAST>
+__global__ void __launch_bounds__(256, 2)
+first_conv3x3_kernel(const float *__restrict__ x, const float *__restrict__ wgt, float *__restrict__ out_f32,
+                     __half *__restrict__ out_codes, FirstConvParams p)
+{
+    constexpr int CG = COUT / 8;                 // channel groups per warp
+    constexpr int PGW = 32 / CG;                 // pixel groups (of 8 pixels) per warp
+    constexpr int TW = PGW * 8, TH = 8;          // output tile of a CTA: one row per warp
+    constexpr int IW = (TW - 1) * STRIDE + 3, IH = (TH - 1) * STRIDE + 3;
+    extern __shared__ __align__(128) uint8_t dw_smem[];
+    float *sw = reinterpret_cast<float *>(dw_smem);                 // [27][COUT]
+    float *sin = sw + 27 * COUT;                                    // [IH][IW][3]
+    __half *lut = reinterpret_cast<__half *>(sin + ((IH * IW * 3 + 3) & ~3));
+    for (int i = threadIdx.x; i < 27 * COUT; i += 256) sw[i] = wgt[i];
+    if (p.write_codes) {
+        for (uint32_t i = threadIdx.x; i < (2u << p.next_bits); i += 256) {
+            const int code = elem_code(i & ((1u << p.next_bits) - 1u), TQ_ENC_HESE, p.next_terms);
+            lut[i] = __int2half_rn((i >> p.next_bits) ? -code : code);
+        }
+    }
+    const Quant nq = make_quant(p.write_codes ? p.next_sf : 1.0f, (float)((1u << p.next_bits) - 1u));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cg = lane % CG, pg = lane / CG;
+    const int tiles_w = (p.Wo + TW - 1) / TW, tiles_h = (p.Ho + TH - 1) / TH;
+    const int64_t total = (int64_t)p.N * tiles_h * tiles_w;
+    for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int tw = (int)(tile % tiles_w), th = (int)((tile / tiles_w) % tiles_h), n = (int)(tile / ((int64_t)tiles_w * tiles_h));
+        const int h_in0 = th * TH * STRIDE - 1, w_in0 = tw * TW * STRIDE - 1;
+        __syncthreads();                                            // the previous tile's reads of `sin` are done
+        for (int hi = warp; hi < IH; hi += 8) {                     // a tile row is IW * 3 contiguous floats of the image row
+            const int h = h_in0 + hi;
+            const bool row_in = h >= 0 && h < p.H;
+            const float *src = x + (((int64_t)n * p.H + (row_in ? h : 0)) * p.W + w_in0) * 3;
+            const int k_lo = w_in0 < 0 ? -w_in0 * 3 : 0, k_hi = (p.W - w_in0) * 3;      // floats of the row that exist
+            for (int k = lane; k < IW * 3; k += 32)
+                sin[hi * IW * 3 + k] = (row_in && k >= k_lo && k < k_hi) ? __ldg(src + k) : 0.0f;
+        }
+        __syncthreads();
+        float acc[8][8];                                            // [pixel][channel]
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[j][c] = 0.0f;
+        const float *in0 = sin + ((warp * STRIDE) * IW + pg * STRIDE) * 3;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int sx = 0; sx < 3; ++sx) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float4 w0 = *reinterpret_cast<const float4 *>(sw + ((r * 3 + sx) * 3 + c) * COUT + cg * 8);
+                    const float4 w1 = *reinterpret_cast<const float4 *>(sw + ((r * 3 + sx) * 3 + c) * COUT + cg * 8 + 4);
+                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float v = in0[(r * IW + j * PGW * STRIDE + sx) * 3 + c];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) acc[j][k] = __fmaf_rn(v, wv[k], acc[j][k]);
+                    }
+                }
+            }
+        }
+        const int ho = th * TH + warp;
+        if (ho >= p.Ho) continue;
+        float ba[8], bb[8], bs[8];                                  // (loaded per tile: 24 registers less across the FMA loop)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            ba[c] = p.bn_a ? __ldg(p.bn_a + cg * 8 + c) : 1.0f;
+            bb[c] = p.bn_b ? __ldg(p.bn_b + cg * 8 + c) : 0.0f;
+            bs[c] = p.bias ? __ldg(p.bias + cg * 8 + c) : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int wo = tw * TW + j * PGW + pg;
+            if (wo >= p.Wo) break;
+            const int64_t o = (((int64_t)n * p.Ho + ho) * p.Wo + wo) * COUT + cg * 8;
+            float tv[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float t = acc[j][c];
+                if (p.bias) t = __fadd_rn(t, bs[c]);
+                if (p.bn_a) t = __fmaf_rn(t, ba[c], bb[c]);
+                tv[c] = apply_act(t, p.relu);
+            }
+            if (p.write_f32) {
+                reinterpret_cast<float4 *>(out_f32 + o)[0] = make_float4(tv[0], tv[1], tv[2], tv[3]);
+                reinterpret_cast<float4 *>(out_f32 + o)[1] = make_float4(tv[4], tv[5], tv[6], tv[7]);
+            }
+            if (p.write_codes) {
+                uint32_t hc[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t neg = __float_as_uint(tv[c]) >> 31;
+                    const uint32_t qi = quantize_f32<FAST>(tv[c], nq);
+                    hc[c] = __half_as_ushort(lut[qi | (neg << p.next_bits)]);
+                }
+                *reinterpret_cast<uint4 *>(out_codes + o) =
+                    make_uint4(hc[0] | (hc[1] << 16), hc[2] | (hc[3] << 16), hc[4] | (hc[5] << 16), hc[6] | (hc[7] << 16));
+            }
+        }
+    }
+}
+
 static int fill_quant(DwParams &p, void *out_codes, float next_sf, int next_bits, int next_terms)
 {
     p.write_codes = out_codes ? 1 : 0;
@@ -458,4 +580,47 @@ extern "C" int tq_maxpool2d_f16(const void *x_f16, void *y_f16, int N, int H, in
                                                                         k, stride, pad);
     count_launch();
     return check_launch("maxpool2d_f16_kernel");
+}
+
+template <int COUT, int STRIDE>
+static int launch_first_conv(const float *x, const float *wgt, float *out_f32, void *out_codes, const FirstConvParams &p,
+                             cudaStream_t s)
+{
+    constexpr int CGN = COUT / 8, TW = (32 / CGN) * 8, TH = 8;
+    constexpr int IW = (TW - 1) * STRIDE + 3, IH = (TH - 1) * STRIDE + 3;
+    const size_t smem = (size_t)27 * COUT * 4 + (size_t)((IH * IW * 3 + 3) & ~3) * 4 + (p.write_codes ? (size_t)(2u << p.next_bits) * 2 : 0);
+    const int64_t tiles = (int64_t)p.N * ((p.Ho + TH - 1) / TH) * ((p.Wo + TW - 1) / TW);
+    const int64_t cap = (int64_t)num_sms() * 2;
+    const int grid = (int)(tiles < cap ? tiles : cap);
+    auto kern = p.next_fastdiv ? first_conv3x3_kernel<COUT, STRIDE, true> : first_conv3x3_kernel<COUT, STRIDE, false>;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return check_launch("cudaFuncSetAttribute(first_conv3x3_kernel)");
+    kern<<<grid, 256, smem, s>>>(x, wgt, out_f32, (__half *)out_codes, p);
+    count_launch();
+    return check_launch("first_conv3x3_kernel");
+}
+
+extern "C" int tq_first_conv3x3_fused(const float *x, const float *wgt, const float *bias, const float *bn_a, const float *bn_b,
+                                      float *out_f32, void *out_codes, int N, int H, int W, int Cout, int stride, int relu,
+                                      float next_sf, int next_bits, int next_terms, void *stream)
+{
+    if (!x || !wgt || (!out_f32 && !out_codes)) return fail(TQ_ERR_INVALID, "NULL pointer");
+    if (N < 1 || H < 1 || W < 1) return fail(TQ_ERR_INVALID, "bad shape");
+    if (Cout != 32 && Cout != 64) return fail(TQ_ERR_UNSUPPORTED, "first conv: Cout must be 32 or 64, got %d", Cout);
+    if (stride != 1 && stride != 2) return fail(TQ_ERR_UNSUPPORTED, "first conv: stride 1 or 2");
+    if ((bn_a == nullptr) != (bn_b == nullptr)) return fail(TQ_ERR_INVALID, "bn_a and bn_b go together");
+    if (relu < 0 || relu > 2) return fail(TQ_ERR_INVALID, "relu: 0 none, 1 ReLU, 2 ReLU6");
+    if ((((uintptr_t)out_f32 | (uintptr_t)out_codes) & 15u) != 0 || (((uintptr_t)x | (uintptr_t)wgt) & 3u) != 0)
+        return fail(TQ_ERR_INVALID, "outputs must be 16-byte aligned");
+    FirstConvParams p{};
+    p.N = N; p.H = H; p.W = W; p.stride = stride;
+    p.Ho = (H + 2 - 3) / stride + 1; p.Wo = (W + 2 - 3) / stride + 1;                // pad 1
+    p.bias = bias; p.bn_a = bn_a; p.bn_b = bn_b; p.relu = relu; p.write_f32 = out_f32 ? 1 : 0;
+    DwParams q{};
+    int rc = fill_quant(q, out_codes, next_sf, next_bits, next_terms);
+    if (rc != TQ_OK) return rc;
+    p.write_codes = q.write_codes; p.next_sf = q.next_sf; p.next_bits = q.next_bits; p.next_terms = q.next_terms; p.next_fastdiv = q.next_fastdiv;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (Cout == 64) return stride == 1 ? launch_first_conv<64, 1>(x, wgt, out_f32, out_codes, p, s) : launch_first_conv<64, 2>(x, wgt, out_f32, out_codes, p, s);
+    return stride == 1 ? launch_first_conv<32, 1>(x, wgt, out_f32, out_codes, p, s) : launch_first_conv<32, 2>(x, wgt, out_f32, out_codes, p, s);
 }

@@ -190,6 +190,12 @@ class FusedResNet(nn.Module):
         return m.fc(torch.flatten(m.avgpool(y), 1))
 
 
+def _first_conv_ok(c):
+    """Is this unwrapped first conv one tq_first_conv3x3_fused runs (3 -> 32 / 64 channels, 3x3, pad 1, stride 1 / 2)?"""
+    return (c.in_channels == 3 and c.out_channels in (32, 64) and c.kernel_size == (3, 3) and c.padding == (1, 1)
+            and c.stride in ((1, 1), (2, 2)) and c.dilation == (1, 1) and c.groups == 1 and c.weight.dtype == torch.float32)
+
+
 def _square(pool):
     """nn.MaxPool2d with one window size / stride / padding for both axes (what tq_maxpool2d_f16 takes)."""
     def one(v):
@@ -270,11 +276,19 @@ class FusedVGG(nn.Module):
             # (the conv's bias rides along as one fp32 add in that pass: torch would add it in a pass of its own over
             # the 1.6 GB map)
             c0 = stem[0]
-            y = F.conv2d(x, c0.weight, None, c0.stride, c0.padding, c0.dilation, c0.groups).permute(0, 2, 3, 1).contiguous()
             if getattr(self, "_stem_bn", None) is None:
                 self._stem_bn = _bn_affine(stem[1])
-            _, codes = conv_codes.bn_act_encode(y, self._stem_bn, relu=True, next_quant=q0,
-                                                bias=None if c0.bias is None else c0.bias.detach().float().contiguous())
+            bias0 = None if c0.bias is None else c0.bias.detach().float().contiguous()
+            if _first_conv_ok(c0):
+                # 3 -> 32 / 64 channels, 3x3, pad 1: conv + bias + BN + ReLU + encode in ONE kernel of the library (fp32 on
+                # the CUDA cores); the fp32 map -- 1.6 GB at batch 128 -- is never written
+                if getattr(self, "_stem_w", None) is None:
+                    self._stem_w = conv_codes.pack_first_conv_weight(c0.weight)
+                _, codes = conv_codes.first_conv3x3_fused(x.permute(0, 2, 3, 1), self._stem_w, c0.stride[0], bias0, self._stem_bn,
+                                                          relu=True, next_quant=q0)
+            else:
+                y = F.conv2d(x, c0.weight, None, c0.stride, c0.padding, c0.dilation, c0.groups).permute(0, 2, 3, 1).contiguous()
+                _, codes = conv_codes.bn_act_encode(y, self._stem_bn, relu=True, next_quant=q0, bias=bias0)
         else:
             for mod in stem:                                      # any other stem: module by module on torch
                 x = mod(x)
@@ -399,9 +413,18 @@ class FusedMobileNet(nn.Module):
                     raise RuntimeError("the wrapped model was re-calibrated after fusing: build the fused executor again")
             self.last.check_fresh()
         x = x.contiguous(memory_format=torch.channels_last)
-        y = self.stem_conv(x.float()).permute(0, 2, 3, 1)                       # fp32 NHWC (channels_last memory)
         first = self.blocks[0][0] or self.blocks[0][1]
-        _, codes = conv_codes.bn_act_encode(y.contiguous(), self.stem_bn, relu="relu6", next_quant=first.quant)
+        c0 = self.stem_conv
+        if _first_conv_ok(c0):
+            # conv 3 -> 32 (3x3 / stride 2) + BN + ReLU6 + the first wrapped layer's encode in one kernel of the library
+            if getattr(self, "_stem_w", None) is None:
+                self._stem_w = conv_codes.pack_first_conv_weight(c0.weight)
+            bias0 = None if c0.bias is None else c0.bias.detach().float().contiguous()
+            _, codes = conv_codes.first_conv3x3_fused(x.float().permute(0, 2, 3, 1), self._stem_w, c0.stride[0], bias0,
+                                                      self.stem_bn, relu="relu6", next_quant=first.quant)
+        else:
+            y = c0(x.float()).permute(0, 2, 3, 1)                               # fp32 NHWC (channels_last memory)
+            _, codes = conv_codes.bn_act_encode(y.contiguous(), self.stem_bn, relu="relu6", next_quant=first.quant)
         if capture is not None:
             capture["stem_codes"] = codes
         cur = None                                                              # fp32 block output, when a residual needs it

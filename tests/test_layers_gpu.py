@@ -365,6 +365,42 @@ def test_depthwise_and_bn_act_kernels_against_cpu_emulation():
         assert np.array_equal(c3.cpu().numpy().astype(np.int32), fused_emul.encode(want_b, nq))
 
 
+def test_first_conv3x3_fused_against_torch():
+    """tq_first_conv3x3_fused (the unwrapped first conv of VGG / MobileNet-V2 + bias + BN + ReLU(6) + first encode in one
+    kernel): the fp32 result against torch's fp32 conv (different summation order: tolerance 2e-6 of the output range,
+    the reference's own TF32 default is ~1e-3), the codes EXACTLY against the oracle encode of the kernel's own fp32
+    result; ragged maps, both strides, both channel counts."""
+    from oracle import fused_emul
+    from term_quantization_b200 import conv_codes
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(21)
+    for (N, H, W, Cout, stride, relu, with_bias) in ((2, 224, 224, 64, 1, True, True), (3, 96, 128, 32, 2, "relu6", False),
+                                                    (1, 37, 53, 64, 2, True, True), (2, 9, 7, 32, 1, False, True),
+                                                    (1, 8, 300, 64, 1, "relu6", False)):
+        x = torch.randn(N, H, W, 3, device="cuda", generator=g)
+        w = torch.randn(Cout, 3, 3, 3, device="cuda", generator=g) * 0.2
+        bias = torch.randn(Cout, device="cuda", generator=g) if with_bias else None
+        a = torch.rand(Cout, device="cuda", generator=g) + 0.5
+        b = torch.randn(Cout, device="cuda", generator=g)
+        ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), None if bias is None else bias.double(),
+                                         stride, 1).permute(0, 2, 3, 1)
+        ref = ref * a.double() + b.double()
+        if relu:
+            ref = ref.clamp(min=0)
+        if relu == "relu6":
+            ref = ref.clamp(max=6)
+        nq = (max(float(ref.abs().max()), 1e-3) / 512, 9, 3)
+        out, codes = conv_codes.first_conv3x3_fused(x, conv_codes.pack_first_conv_weight(w), stride, bias, (a, b), relu=relu,
+                                                    want_f32=True, next_quant=nq)
+        assert out.shape == ref.shape
+        err = float((out.double() - ref).abs().max()) / max(float(ref.abs().max()), 1e-6)
+        assert err < 2e-6, (N, H, W, Cout, stride, err)
+        assert np.array_equal(codes.cpu().numpy().astype(np.int32), fused_emul.encode(out.cpu().numpy(), nq)), (N, H, W, Cout, stride)
+        none, codes2 = conv_codes.first_conv3x3_fused(x, conv_codes.pack_first_conv_weight(w), stride, bias, (a, b), relu=relu,
+                                                      next_quant=nq)
+        assert none is None and torch.equal(codes2, codes)
+
+
 def test_maxpool_on_codes_equals_torch():
     """tq_maxpool2d_f16 (the pools between the wrapped convs of the VGG-style stacks, run on fp16 term codes) against
     nn.MaxPool2d on the same tensor: VGG's 2x2/s2, AlexNet's 3x3/s2, ResNet's 3x3/s2/p1, odd maps, signed values."""
