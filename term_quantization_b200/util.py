@@ -39,7 +39,11 @@ def get_imagenet_validation(args):
     root = os.path.join(val_dir, 'imagenet', 'val') if val_dir else None
     image_size, bicubic = 224, False
     if 'efficientnet' in getattr(args, 'arch', ''):
-        from efficientnet_pytorch import EfficientNet
+        try:
+            from efficientnet_pytorch import EfficientNet
+        except ImportError as e:
+            raise ImportError("efficientnet_* needs the third-party efficientnet_pytorch package (a dependency of the "
+                              "reference, util.py:4; not in this image)") from e
         image_size, bicubic = EfficientNet.get_image_size(args.arch.replace('_', '-')), True
     if root is None or not os.path.isdir(root):
         return synthetic_loader(getattr(args, 'images', None) or 256, args.batch_size, size=image_size,
