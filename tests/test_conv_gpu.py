@@ -241,7 +241,8 @@ def test_bn_relu_maxpool_encode():
     from oracle import tq_oracle as O
     from term_quantization_b200 import conv_codes
     g = torch.Generator(device="cuda").manual_seed(11)
-    for (N, H, W, C) in ((2, 112, 112, 64), (3, 17, 9, 8), (1, 7, 7, 20)):
+    # (tiled kernel: 64-channel blocks on maps of >= 4 x 7 pooled pixels, ragged edges; the rest: one thread per output)
+    for (N, H, W, C) in ((2, 112, 112, 64), (3, 17, 9, 8), (1, 7, 7, 20), (2, 57, 31, 128), (1, 23, 111, 24), (3, 30, 28, 64)):
         x = torch.randn(N, H, W, C, device="cuda", generator=g) * 2
         a = torch.randn(C, device="cuda", generator=g)            # negative slopes included
         b = torch.randn(C, device="cuda", generator=g)
