@@ -33,7 +33,16 @@
 // (a, h) drains column half h of every second tile (TMEM -> registers -> fused tail -> swizzled smem ->
 // TMA store).
 //
+// CTA pairs (template argument CG = 2, the streamed-weight halo mode on maps with at least one pair of tiles per TPC): two
+// CTAs of a cluster run ONE tcgen05.mma.cta_group::2 of M = 256, each holding the halo box of its own M tile and half of
+// the weight tile -- see the helpers below and DESIGN.md section 6.  Small maps (7x7) use a packed halo: several
+// whole images per tile with shared zero padding.
+//
 // Measurement / experiment switches (environment, read once; none is needed in normal use):
+//   TQ_CONV_PAIR=0 / TQ_CONV_PAIR3=1           single CTAs everywhere / CTA pairs also for the resident-weight halo mode
+//   TQ_CONV_NO_PACKED                          no packed halo for small maps (per-tap streaming instead)
+//   TQ_CONV_HALO_SLACK=n                       percent of extra tiles a halo tiling may cost (default 16)
+//   -DTQ_CONV_TRACE (tools/conv_trace.sh)      debug build: per-role cycle accounting printed by two CTAs per launch
 //   TQ_CONV_SKIP_EPI / _SKIP_MMA / _SKIP_TMA   run without the epilogue / the MMAs / the TMA loads (results are garbage;
 //                                              SKIP_TMA=2 / 4 in the streamed-weight halo mode: no weight / no halo loads):
 //                                              isolates which pipeline paces a layer (tools/conv_microbench.py)
