@@ -412,7 +412,8 @@ def run_b200(args):
                   "ms_per_step": float(t.item()) / args.steps,
                   "h2d_bytes_per_step": BATCH * 224 * 224 * 3 * world, "d2h_bytes_per_step": int(host_logits8.numel()) * 4 * world,
                   "note": "same engine fed uint8 NHWC images; ((u8 / 255) - mean) / std as the reference loader computes it "
-                          "(util.py:12-27), on the device (tq_u8_normalize_bf16), rounded to the bf16 the engine consumes"}
+                          "(util.py:12-27), rounded to the bf16 the engine consumes, inside the stem's fold pass on the device "
+                          "(tq_stem_conv7x7s2_u8; the same values as tq_u8_normalize_bf16)"}
         del runner8, front
     # what the box allows: the same host -> device copies alone, all ranks at once (max over ranks)
     import bench_extra

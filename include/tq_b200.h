@@ -238,6 +238,15 @@ int tq_stem_conv7x7s2(const float *x, void *x2_scratch, const void *w2, float *o
  * skipped: x2_scratch then needs N * (H/2+3) * (W/2+3) * 16 fp16. */
 int tq_stem_conv7x7s2_dt(const void *x, int x_dtype, void *x2_scratch, const void *w2, float *out,
                          int N, int H, int W, int Cout, void *stream);
+
+/*
+ * The same conv on uint8 NHWC images [N][H][W][3] with ToTensor + Normalize folded in: the value convolved is
+ * bf16(((u8 / 255) - mean3[c]) / std3[c]) -- what tq_u8_normalize_bf16 writes, each step one fp32 IEEE operation as
+ * torchvision computes it on the host (util.py:12-27) -- so a batch crosses PCIe as one byte per value and no
+ * normalised image is ever materialised.  mean3 / std3 are HOST arrays of 3 floats.
+ */
+int tq_stem_conv7x7s2_u8(const void *x_u8, const float *mean3, const float *std3, void *x2_scratch, const void *w2,
+                         float *out, int N, int H, int W, int Cout, void *stream);
 /*
  * The whole unquantised stem in one tensor-core kernel: conv 7x7/s2/p3 -> per-channel affine (BatchNorm) ->
  * ReLU (if relu) -> max-pool 3x3/s2/p1 -> fp32 NHWC [N, Hp, Wp, Cout] (Hp = (H/2 - 1)/2 + 1) and, if out_codes,

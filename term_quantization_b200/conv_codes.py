@@ -417,6 +417,28 @@ def stem_conv7x7s2(x_nhwc, w2, scratch=None, cout=None):
     return out, scratch
 
 
+def stem_conv7x7s2_u8(x_u8_nhwc, mean, std, w2, scratch=None, cout=None):
+    """uint8 [N, H, W, 3] images -> fp32 [N, H/2, W/2, Cout]: ToTensor + Normalize (rounded to bf16, exactly what
+    inference.normalize_u8 produces) folded into the stem conv's fold pass (tq_stem_conv7x7s2_u8)."""
+    import ctypes
+    if x_u8_nhwc.dtype != torch.uint8 or not x_u8_nhwc.is_contiguous() or not x_u8_nhwc.is_cuda or x_u8_nhwc.shape[-1] != 3:
+        raise RuntimeError("stem_conv7x7s2_u8 expects a contiguous uint8 CUDA [N, H, W, 3] tensor")
+    N, H, W, _ = x_u8_nhwc.shape
+    Cout = cout if cout is not None else 64
+    need = N * (H // 2 + 3) * (W // 2 + 3) * 16
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty(need, dtype=torch.float16, device=x_u8_nhwc.device)
+    out = torch.empty((N, H // 2, W // 2, Cout), dtype=torch.float32, device=x_u8_nhwc.device)
+    m = (ctypes.c_float * 3)(*mean)
+    s = (ctypes.c_float * 3)(*std)
+    with torch.cuda.device(x_u8_nhwc.device):
+        rc = _lib.lib().tq_stem_conv7x7s2_u8(x_u8_nhwc.data_ptr(), ctypes.cast(m, ctypes.c_void_p), ctypes.cast(s, ctypes.c_void_p),
+                                             scratch.data_ptr(), w2.data_ptr(), out.data_ptr(), N, H, W, Cout,
+                                             torch.cuda.current_stream(x_u8_nhwc.device).cuda_stream)
+    _lib.check(rc)
+    return out, scratch
+
+
 def stem_pool_operands(w, bn):
     """Operands of the one-kernel stem for a (Cout, 3, 7, 7) weight and BatchNorm affine (a, b): the kernel pools
     the raw conv sums and applies the affine once per pooled value, which needs a >= 0, so sign(a) moves into the

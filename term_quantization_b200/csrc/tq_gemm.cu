@@ -1826,9 +1826,20 @@ extern "C" int tq_conv_weight_l1(const void *wgt_f16, int RS, int Cout, int C, l
 // =============================================================================================
 namespace tq {
 
+// uint8 images: ToTensor + Normalize as torchvision computes them on the host in fp32 (util.py:12-27: x = u8 / 255, then
+// (x - mean[c]) / std[c], each one IEEE operation), rounded to bf16 -- exactly what tq_u8_normalize_bf16 writes -- folded
+// straight into the fp16 planes (a bf16 value is an fp16 value down to 2^-14)
+struct StemNorm { float mean[3], sd[3]; };
+__device__ __forceinline__ float stem_pixel(uint8_t v, int c, const StemNorm &nm)
+{
+    const float t = __fdiv_rn((float)v, 255.0f);
+    return __bfloat162float(__float2bfloat16_rn(__fdiv_rn(__fsub_rn(t, nm.mean[c]), nm.sd[c])));
+}
+template <typename T> __device__ __forceinline__ float stem_pixel(T v, int, const StemNorm &) { return Elem<T>::to_f32(v); }
+
 template <typename Tin, bool LO>
 __global__ void __launch_bounds__(256)
-stem_prepare_kernel(const Tin *__restrict__ x, __half *__restrict__ x2, int N, int H, int W, int Hs, int Ws)
+stem_prepare_kernel(const Tin *__restrict__ x, __half *__restrict__ x2, int N, int H, int W, int Hs, int Ws, StemNorm nm)
 {
     // one thread per folded pixel (n, hs, ws): 16 halves hi (+ 16 halves lo for fp32 input; bf16 / fp16
     // images are fp16-exact down to 2^-14, below that the residue is < 2^-25 absolute and is dropped)
@@ -1844,7 +1855,7 @@ stem_prepare_kernel(const Tin *__restrict__ x, __half *__restrict__ x2, int N, i
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 float v = 0.0f;
-                if (in && c < 3) v = Elem<Tin>::to_f32(x[(((int64_t)n * H + h) * W + w) * 3 + c]);
+                if (in && c < 3) v = stem_pixel(x[(((int64_t)n * H + h) * W + w) * 3 + c], c, nm);
                 const __half vh = __float2half_rn(v);
                 hi[d * 4 + c] = vh;
                 if (LO) lo[d * 4 + c] = __float2half_rn(v - __half2float(vh));
@@ -1865,11 +1876,20 @@ stem_prepare_kernel(const Tin *__restrict__ x, __half *__restrict__ x2, int N, i
 // (fp32 [N, Hp, Wp, Cout]) and, if out_codes, its fp16 term codes for the next layer's quantiser.
 static int stem_impl(const void *x, int x_dtype, void *x2_scratch, const void *w2, float *out, void *out_codes,
                      const float *bn_a, const float *bn_b, int relu, int pool, float next_sf, int next_bits,
-                     int next_terms, int N, int H, int W, int Cout, void *stream)
+                     int next_terms, int N, int H, int W, int Cout, void *stream, const float *mean3 = nullptr,
+                     const float *std3 = nullptr)
 {
     if (!x || !x2_scratch || !w2 || !out) return fail(TQ_ERR_INVALID, "NULL pointer");
-    if (x_dtype != TQ_F32 && x_dtype != TQ_BF16 && x_dtype != TQ_F16)
-        return fail(TQ_ERR_UNSUPPORTED, "stem conv input must be fp32, bf16 or fp16");
+    if (x_dtype != TQ_F32 && x_dtype != TQ_BF16 && x_dtype != TQ_F16 && x_dtype != TQ_U8)
+        return fail(TQ_ERR_UNSUPPORTED, "stem conv input must be fp32, bf16, fp16 or uint8");
+    StemNorm nm{};
+    if (x_dtype == TQ_U8) {
+        if (!mean3 || !std3) return fail(TQ_ERR_INVALID, "uint8 images need mean3 / std3");
+        for (int c = 0; c < 3; ++c) {
+            if (!(std3[c] > 0.0f)) return fail(TQ_ERR_INVALID, "std must be positive");
+            nm.mean[c] = mean3[c]; nm.sd[c] = std3[c];
+        }
+    }
     const bool lo_plane = x_dtype == TQ_F32;
     if (N < 1 || H < 2 || W < 2 || (H & 1) || (W & 1)) return fail(TQ_ERR_INVALID, "H and W must be even");
     if (Cout < 4 || Cout % 4) return fail(TQ_ERR_UNSUPPORTED, "Cout must be a multiple of 4");
@@ -1885,11 +1905,13 @@ static int stem_impl(const void *x, int x_dtype, void *x2_scratch, const void *w
         int64_t blocks = (total + 255) / 256;
         if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
         if (x_dtype == TQ_F32)
-            stem_prepare_kernel<float, true><<<(int)blocks, 256, 0, s>>>((const float *)x, (__half *)x2_scratch, N, H, W, Hs, Ws);
+            stem_prepare_kernel<float, true><<<(int)blocks, 256, 0, s>>>((const float *)x, (__half *)x2_scratch, N, H, W, Hs, Ws, nm);
         else if (x_dtype == TQ_BF16)
-            stem_prepare_kernel<__nv_bfloat16, false><<<(int)blocks, 256, 0, s>>>((const __nv_bfloat16 *)x, (__half *)x2_scratch, N, H, W, Hs, Ws);
+            stem_prepare_kernel<__nv_bfloat16, false><<<(int)blocks, 256, 0, s>>>((const __nv_bfloat16 *)x, (__half *)x2_scratch, N, H, W, Hs, Ws, nm);
+        else if (x_dtype == TQ_U8)
+            stem_prepare_kernel<uint8_t, false><<<(int)blocks, 256, 0, s>>>((const uint8_t *)x, (__half *)x2_scratch, N, H, W, Hs, Ws, nm);
         else
-            stem_prepare_kernel<__half, false><<<(int)blocks, 256, 0, s>>>((const __half *)x, (__half *)x2_scratch, N, H, W, Hs, Ws);
+            stem_prepare_kernel<__half, false><<<(int)blocks, 256, 0, s>>>((const __half *)x, (__half *)x2_scratch, N, H, W, Hs, Ws, nm);
         count_launch();
         int rc = check_launch("stem_prepare_kernel");
         if (rc != TQ_OK) return rc;
@@ -2005,6 +2027,13 @@ extern "C" int tq_stem_conv7x7s2_pool(const void *x, int x_dtype, void *x2_scrat
     if ((((uintptr_t)bn_a | (uintptr_t)bn_b | (uintptr_t)out_codes) & 15u) != 0) return fail(TQ_ERR_INVALID, "pointers must be 16-byte aligned");
     return stem_impl(x, x_dtype, x2_scratch, w2, out, out_codes, bn_a, bn_b, relu, 1, next_sf, next_bits, next_terms,
                      N, H, W, Cout, stream);
+}
+
+extern "C" int tq_stem_conv7x7s2_u8(const void *x_u8, const float *mean3, const float *std3, void *x2_scratch, const void *w2,
+                                    float *out, int N, int H, int W, int Cout, void *stream)
+{
+    return stem_impl(x_u8, TQ_U8, x2_scratch, w2, out, nullptr, nullptr, nullptr, 0, 0, 1.0f, 1, 0, N, H, W, Cout, stream,
+                     mean3, std3);
 }
 
 extern "C" int tq_stem_conv7x7s2(const float *x, void *x2_scratch, const void *w2, float *out,

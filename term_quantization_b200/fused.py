@@ -138,19 +138,37 @@ class FusedResNet(nn.Module):
         return [(d(c1), d(c2), d(down)) for c1, c2, down in self.blocks]
 
     @torch.no_grad()
-    def forward(self, x, capture=None):
+    def forward_u8(self, x_u8_nhwc, mean, std):
+        """uint8 [N, H, W, 3] images (1 byte per value over PCIe): ToTensor + Normalize happen inside the stem's fold
+        pass when the two-launch tensor-core stem runs; otherwise the images are normalised first (same values)."""
+        H, W = x_u8_nhwc.shape[1], x_u8_nhwc.shape[2]
+        if (self.fuse_stem and self.stem_w is not None and self.stem_mode != "tcgen05_pool" and H % 2 == 0 and W % 2 == 0
+                and (H // 2) * (W // 2) >= 128):
+            return self.forward(x_u8_nhwc, u8_norm=(tuple(mean), tuple(std)))
+        from . import inference
+        return self.forward(inference.normalize_u8(x_u8_nhwc, mean, std))
+
+    def forward(self, x, capture=None, u8_norm=None):
         """x: [N, 3, H, W] images, fp32 or bf16 / fp16 (16-bit images are used as they are: the values the
         reference would see after `images.float()`), any memory format (channels_last avoids a copy).
         capture: optional dict that receives 'stem' (the fp32 NHWC tensor reaching layer1) and 'final' (the
-        last block's fp32 NHWC output) -- the two ends of the chain the CPU emulation checks."""
+        last block's fp32 NHWC output) -- the two ends of the chain the CPU emulation checks.
+        u8_norm: (mean, std) when x is a uint8 [N, H, W, 3] batch (see forward_u8)."""
         m = self.model
         if not torch.cuda.is_current_stream_capturing():
             for blk in self.blocks:
                 for c in blk:
                     if c is not None:
                         c.check_fresh()
-        x = x.contiguous(memory_format=torch.channels_last)
-        if self.fuse_stem:
+        if u8_norm is not None:
+            # uint8 NHWC batch: normalisation inside the fold pass of the two-launch tensor-core stem (forward_u8 checked)
+            q0 = self.blocks[0][0].quant
+            y, self._stem_scratch = conv_codes.stem_conv7x7s2_u8(x, u8_norm[0], u8_norm[1], self.stem_w, self._stem_scratch,
+                                                                 cout=m.conv1.out_channels)
+            cur, c0 = conv_codes.bn_relu_maxpool_encode(y, self.stem_bn, relu=True, next_quant=q0)
+            codes = {q0: c0}
+        elif self.fuse_stem:
+            x = x.contiguous(memory_format=torch.channels_last)
             # stem conv (never wrapped, fp32 arithmetic), then bn1 + relu + maxpool + first encode in one pass
             q0 = self.blocks[0][0].quant
             if self.stem_w is not None and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0 \
@@ -169,6 +187,7 @@ class FusedResNet(nn.Module):
                 cur, c0 = conv_codes.bn_relu_maxpool_encode(y, self.stem_bn, relu=True, next_quant=q0)
             codes = {q0: c0}                             # quantiser -> fp16 codes of `cur`
         else:
+            x = x.contiguous(memory_format=torch.channels_last)
             x = m.maxpool(m.relu(m.bn1(m.conv1(x.float()))))
             cur = x.permute(0, 2, 3, 1)                  # fp32 [N, H, W, C], contiguous
             codes = {}

@@ -74,6 +74,8 @@ class U8Frontend(torch.nn.Module):
         self.model, self.mean, self.std = model, tuple(mean), tuple(std)
 
     def forward(self, x_u8_nhwc):
+        if hasattr(self.model, "forward_u8"):       # fused engines that fold the normalisation into their first pass
+            return self.model.forward_u8(x_u8_nhwc, self.mean, self.std)
         return self.model(normalize_u8(x_u8_nhwc, self.mean, self.std))
 
 

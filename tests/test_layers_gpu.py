@@ -620,3 +620,24 @@ def test_u8_normalize_matches_torchvision_arithmetic():
     assert got.shape == want.shape and torch.equal(got, want)
     net = torch.nn.Conv2d(3, 4, 3).cuda().bfloat16()
     assert torch.equal(inference.U8Frontend(net)(x), net(want))
+
+
+def test_fused_resnet_takes_uint8_images_through_the_stem_fold():
+    """FusedResNet.forward_u8 (tq_stem_conv7x7s2_u8): ToTensor + Normalize inside the stem's fold pass -- the logits must
+    EQUAL those of the same engine fed normalize_u8's bf16 images (same values, one pass and one tensor less)."""
+    import torchvision
+    from term_quantization_b200 import cnn_models, fused, inference
+    torch.manual_seed(0)
+    base = torchvision.models.resnet18(weights=None).cuda().eval()
+    q = cnn_models.convert_model(base, cnn_models.static_conv_layer_settings(base, 9, 8, 12), 9, 3)
+    g = torch.Generator(device="cuda").manual_seed(8)
+    x8 = torch.randint(0, 256, (4, 96, 128, 3), device="cuda", dtype=torch.uint8, generator=g)
+    inference.calibrate(q, [inference.normalize_u8(x8).float()])
+    f = fused.FusedResNet(q.to(memory_format=torch.channels_last))
+    with torch.no_grad():
+        want = f(inference.normalize_u8(x8))
+        got = inference.U8Frontend(f)(x8)
+        assert torch.equal(got, want)
+        # odd map: falls back to normalising first
+        x_odd = x8[:, :95].contiguous()
+        assert torch.equal(inference.U8Frontend(f)(x_odd), f(inference.normalize_u8(x_odd)))
