@@ -60,6 +60,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include "tq_common.cuh"
@@ -1843,6 +1844,12 @@ stem_prepare_kernel(const Tin *__restrict__ x, __half *__restrict__ x2, int N, i
 {
     // one thread per folded pixel (n, hs, ws): 16 halves hi (+ 16 halves lo for fp32 input; bf16 / fp16
     // images are fp16-exact down to 2^-14, below that the residue is < 2^-25 absolute and is dropped)
+    // uint8 images: the 3 x 256 possible normalised values once per CTA (two IEEE divisions each), then one lookup per value
+    __shared__ __half norm_lut[std::is_same<Tin, uint8_t>::value ? 768 : 1];
+    if constexpr (std::is_same<Tin, uint8_t>::value) {
+        for (int i = threadIdx.x; i < 768; i += blockDim.x) norm_lut[i] = __float2half_rn(stem_pixel((uint8_t)(i & 255), i >> 8, nm));
+        __syncthreads();
+    }
     const int64_t total = (int64_t)N * Hs * Ws;
     const int64_t plane = total * 16;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -1854,16 +1861,20 @@ stem_prepare_kernel(const Tin *__restrict__ x, __half *__restrict__ x2, int N, i
             const bool in = h >= 0 && h < H && w >= 0 && w < W;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                float v = 0.0f;
-                if (in && c < 3) v = stem_pixel(x[(((int64_t)n * H + h) * W + w) * 3 + c], c, nm);
-                const __half vh = __float2half_rn(v);
-                hi[d * 4 + c] = vh;
-                if (LO) lo[d * 4 + c] = __float2half_rn(v - __half2float(vh));
+                if constexpr (std::is_same<Tin, uint8_t>::value) {
+                    hi[d * 4 + c] = (in && c < 3) ? norm_lut[c * 256 + (int)x[(((int64_t)n * H + h) * W + w) * 3 + c]] : __float2half_rn(0.0f);
+                } else {
+                    float v = 0.0f;
+                    if (in && c < 3) v = stem_pixel(x[(((int64_t)n * H + h) * W + w) * 3 + c], c, nm);
+                    const __half vh = __float2half_rn(v);
+                    hi[d * 4 + c] = vh;
+                    if (LO) lo[d * 4 + c] = __float2half_rn(v - __half2float(vh));
+                }
             }
         }
         uint4 *dh = reinterpret_cast<uint4 *>(x2 + t * 16);
         dh[0] = reinterpret_cast<const uint4 *>(hi)[0]; dh[1] = reinterpret_cast<const uint4 *>(hi)[1];
-        if (LO) {
+        if constexpr (LO) {
             uint4 *dl = reinterpret_cast<uint4 *>(x2 + plane + t * 16);
             dl[0] = reinterpret_cast<const uint4 *>(lo)[0]; dl[1] = reinterpret_cast<const uint4 *>(lo)[1];
         }
@@ -1871,6 +1882,9 @@ stem_prepare_kernel(const Tin *__restrict__ x, __half *__restrict__ x2, int N, i
 }
 
 }  // namespace tq
+
+// (image dtype of the uint8 entry point inside stem_impl: the public TQ_U8 is a CODE dtype and shares its value with TQ_F16)
+constexpr int STEM_U8 = 100;
 
 // pool = 0: out = conv (fp32 [N, H/2, W/2, Cout]).  pool = 1: out = maxpool3x3s2p1(relu?(fma(conv, bn_a, bn_b)))
 // (fp32 [N, Hp, Wp, Cout]) and, if out_codes, its fp16 term codes for the next layer's quantiser.
@@ -1880,10 +1894,10 @@ static int stem_impl(const void *x, int x_dtype, void *x2_scratch, const void *w
                      const float *std3 = nullptr)
 {
     if (!x || !x2_scratch || !w2 || !out) return fail(TQ_ERR_INVALID, "NULL pointer");
-    if (x_dtype != TQ_F32 && x_dtype != TQ_BF16 && x_dtype != TQ_F16 && x_dtype != TQ_U8)
+    if (x_dtype != TQ_F32 && x_dtype != TQ_BF16 && x_dtype != TQ_F16 && x_dtype != STEM_U8)
         return fail(TQ_ERR_UNSUPPORTED, "stem conv input must be fp32, bf16, fp16 or uint8");
     StemNorm nm{};
-    if (x_dtype == TQ_U8) {
+    if (x_dtype == STEM_U8) {
         if (!mean3 || !std3) return fail(TQ_ERR_INVALID, "uint8 images need mean3 / std3");
         for (int c = 0; c < 3; ++c) {
             if (!(std3[c] > 0.0f)) return fail(TQ_ERR_INVALID, "std must be positive");
@@ -1908,7 +1922,7 @@ static int stem_impl(const void *x, int x_dtype, void *x2_scratch, const void *w
             stem_prepare_kernel<float, true><<<(int)blocks, 256, 0, s>>>((const float *)x, (__half *)x2_scratch, N, H, W, Hs, Ws, nm);
         else if (x_dtype == TQ_BF16)
             stem_prepare_kernel<__nv_bfloat16, false><<<(int)blocks, 256, 0, s>>>((const __nv_bfloat16 *)x, (__half *)x2_scratch, N, H, W, Hs, Ws, nm);
-        else if (x_dtype == TQ_U8)
+        else if (x_dtype == STEM_U8)
             stem_prepare_kernel<uint8_t, false><<<(int)blocks, 256, 0, s>>>((const uint8_t *)x, (__half *)x2_scratch, N, H, W, Hs, Ws, nm);
         else
             stem_prepare_kernel<__half, false><<<(int)blocks, 256, 0, s>>>((const __half *)x, (__half *)x2_scratch, N, H, W, Hs, Ws, nm);
@@ -2032,7 +2046,7 @@ extern "C" int tq_stem_conv7x7s2_pool(const void *x, int x_dtype, void *x2_scrat
 extern "C" int tq_stem_conv7x7s2_u8(const void *x_u8, const float *mean3, const float *std3, void *x2_scratch, const void *w2,
                                     float *out, int N, int H, int W, int Cout, void *stream)
 {
-    return stem_impl(x_u8, TQ_U8, x2_scratch, w2, out, nullptr, nullptr, nullptr, 0, 0, 1.0f, 1, 0, N, H, W, Cout, stream,
+    return stem_impl(x_u8, STEM_U8, x2_scratch, w2, out, nullptr, nullptr, nullptr, 0, 0, 1.0f, 1, 0, N, H, W, Cout, stream,
                      mean3, std3);
 }
 
