@@ -136,6 +136,21 @@ def test_k_chunk_accumulators_exact_beyond_2_24(case, amp, groups):
     assert torch.equal(out, want.float()), float((out.double() - want).abs().max())
     if groups > 1:
         assert plan.bound * groups >= 2 ** 24                      # a single accumulator would not have been provable
+    if N >= 40 and stride == 1:
+        # the same layer with the whole fused tail (BN, residual, ReLU, fp32 tile + next codes): at this batch the halo
+        # modes run on CTA pairs (and 7x7 maps on the packed halo), with 2 / 4 accumulator groups per tile
+        from oracle import tq_oracle as O
+        scale = np.float32(2.1e-7)
+        a = torch.rand(Cout, device="cuda", generator=g) + 0.5
+        b = torch.randn(Cout, device="cuda", generator=g)
+        res = torch.randn(want.shape, device="cuda", generator=g)
+        t = torch.relu(((want.float() * scale).double() * a.double() + b.double()).float() + res)
+        nq = (max(float(t.max()), 1e-3) / 512, 9, 3)
+        o2, codes = conv_codes.conv2d_codes_fused(act.half().contiguous(), wh, (k, k), stride, pad, scale, bn=(a, b), residual=res,
+                                                  relu=True, next_quant=nq, plan=plan)
+        assert torch.equal(o2, t)
+        _, wc = O.tr(t.cpu().numpy().reshape(1, -1, 1, 1), nq[0], nq[1], 1, nq[2], return_codes=True)
+        assert np.array_equal(codes.cpu().numpy().astype(np.int32).reshape(-1), wc.reshape(-1))
 
 
 def test_i8_plane_engine_plane_counts():
