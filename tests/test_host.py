@@ -187,3 +187,37 @@ def test_pybind_adapter_loads_and_keeps_the_reference_checks():
     assert "Term Revealing (TR) (CUDA)" in m.tr.__doc__
     with pytest.raises(RuntimeError, match="input must be a CUDA tensor"):
         m.tr(torch.zeros(2, 8), 1.0, 8, 1, 3)
+
+
+def test_fused_executor_host_rules():
+    """Host-side rules of the fused executors added in round 2 (no GPU): which unwrapped first convs and max-pools go to
+    the library kernels, the first-conv weight layout, the uint8 front end's dispatch, and the loud CPU rejections."""
+    import pytest
+    import torch
+    import torch.nn as nn
+    from term_quantization_b200 import conv_codes, fused, inference
+    ok = nn.Conv2d(3, 64, 3, 1, 1)
+    assert fused._first_conv_ok(ok) and fused._first_conv_ok(nn.Conv2d(3, 32, 3, 2, 1, bias=False))
+    for bad in (nn.Conv2d(3, 64, 7, 2, 3), nn.Conv2d(3, 48, 3, 1, 1), nn.Conv2d(4, 64, 3, 1, 1), nn.Conv2d(3, 64, 3, 1, 0),
+                nn.Conv2d(3, 64, 3, 1, 1, dilation=2), nn.Conv2d(3, 64, 3, 3, 1)):
+        assert not fused._first_conv_ok(bad)
+    assert fused._square(nn.MaxPool2d(2, 2)) and fused._square(nn.MaxPool2d(3, 2, 1)) and fused._square(nn.MaxPool2d(3))
+    assert not fused._square(nn.MaxPool2d((2, 3), 2)) and not fused._square(nn.MaxPool2d(9, 2))
+    # [filter row][filter column][input channel][output channel]
+    w = torch.arange(64 * 27, dtype=torch.float32).view(64, 3, 3, 3)
+    p = conv_codes.pack_first_conv_weight(w)
+    assert p.shape == (3, 3, 3, 64) and p.is_contiguous() and float(p[1, 2, 0, 5]) == float(w[5, 0, 1, 2])
+    with pytest.raises(RuntimeError):
+        conv_codes.pack_first_conv_weight(torch.zeros(64, 3, 7, 7))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        conv_codes.maxpool_codes(torch.zeros(1, 4, 4, 8, dtype=torch.float16), 2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        conv_codes.first_conv3x3_fused(torch.zeros(1, 8, 8, 3), p, next_quant=(1.0, 8, 3))
+    with pytest.raises(RuntimeError, match="uint8"):
+        conv_codes.stem_conv7x7s2_u8(torch.zeros(1, 8, 8, 3), (0, 0, 0), (1, 1, 1), None)
+
+    class Engine(nn.Module):                     # an engine that folds the normalisation into its first pass
+        def forward_u8(self, x, mean, std):
+            return ("folded", tuple(mean), tuple(std))
+    out = inference.U8Frontend(Engine(), mean=(0.1, 0.2, 0.3), std=(1.0, 2.0, 3.0))(torch.zeros(1, 2, 2, 3, dtype=torch.uint8))
+    assert out == ("folded", (0.1, 0.2, 0.3), (1.0, 2.0, 3.0))
