@@ -131,3 +131,32 @@ def run_mobilenet_chain(desc, stem_codes):
         cur, codes = fused_conv_act(h, proj, residual=cur if use_res else None, relu=False, next_quant=nq)
     out, _ = fused_conv_act(codes, desc["last"], relu="relu6")
     return out
+
+
+def maxpool_nhwc(x, k, stride, pad):
+    """nn.MaxPool2d(k, stride, pad) (floor mode) on an NHWC array (integer codes or fp32): -inf padding."""
+    t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).permute(0, 3, 1, 2)
+    return F.max_pool2d(t, k, stride, pad).permute(0, 2, 3, 1).contiguous().numpy()
+
+
+def run_vgg_chain(stages, stem_codes):
+    """stages = fused.FusedVGG.chain_description(); stem_codes: int codes [N,H,W,C] reaching the first wrapped conv (the
+    unwrapped first conv + BN + ReLU + first encode are outside the chain).  Every conv is the exact integer conv of the
+    codes -> fl32 * scale (+ bias) -> fmaf BN -> ReLU -> the next quantiser's codes; max-pools act on the codes
+    (monotone for g = 1) or, after the last conv, on the fp32 map.  Returns the fp32 map the average pool reads."""
+    codes = np.asarray(stem_codes).astype(np.int32)
+    out = None
+    for i, st in enumerate(stages):
+        if st[0] == "conv":
+            _, conv, relu = st
+            nxt = next((s[1]["quant"] for s in stages[i + 1:] if s[0] == "conv"), None)
+            out, codes = fused_conv(codes, conv, relu=relu, next_quant=nxt)
+            if nxt is not None:
+                out = None
+        else:
+            _, k, stride, pad = st
+            if codes is not None:
+                codes = maxpool_nhwc(codes, k, stride, pad).astype(np.int32)
+            else:
+                out = maxpool_nhwc(out, k, stride, pad).astype(np.float32)
+    return out

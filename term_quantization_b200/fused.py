@@ -277,8 +277,27 @@ class FusedVGG(nn.Module):
             if not self.stages[k][1][1]:
                 raise NotImplementedError("FusedVGG: conv without ReLU before a quantiser")
 
+    def chain_description(self):
+        """The stages after the first wrapped conv's quantiser as plain data for oracle/fused_emul.run_vgg_chain:
+        ('conv', dict, relu) and ('pool', kernel, stride, padding)."""
+        out = []
+        for kind, payload in self.stages[self.first_tr:]:
+            if kind == "conv":
+                c, relu = payload
+                out.append(("conv", {"w": c.w.cpu().numpy().astype("int32"), "ks": tuple(c.ks), "stride": c.stride, "pad": c.pad,
+                                     "scale": c.scale, "bias": None if c.bias is None else c.bias.detach().float().cpu().numpy(),
+                                     "bn": None if c.bn is None else (c.bn[0].cpu().numpy(), c.bn[1].cpu().numpy()),
+                                     "quant": c.quant, "engine": c.plan.engine, "groups": c.plan.groups}, bool(relu)))
+            else:
+                one = lambda v: v if isinstance(v, int) else v[0]   # noqa: E731
+                out.append(("pool", one(payload.kernel_size), one(payload.stride if payload.stride is not None else payload.kernel_size),
+                            one(payload.padding)))
+        return out
+
     @torch.no_grad()
-    def forward(self, x):
+    def forward(self, x, capture=None):
+        """capture: optional dict that receives 'stem_codes' (the fp16 codes reaching the first wrapped conv) and 'final'
+        (the fp32 NHWC map the average pool reads) -- the two ends of the chain the CPU emulation checks."""
         m = self.model
         if not torch.cuda.is_current_stream_capturing():
             for kind, payload in self.stages:
@@ -312,6 +331,8 @@ class FusedVGG(nn.Module):
             for mod in stem:                                      # any other stem: module by module on torch
                 x = mod(x)
             codes = FusedResNet._encode(x.permute(0, 2, 3, 1), q0)                  # NHWC fp16 codes
+        if capture is not None:
+            capture["stem_codes"] = codes
         out = None
         for k in range(self.first_tr, len(self.stages)):
             kind, payload = self.stages[k]
@@ -334,6 +355,8 @@ class FusedVGG(nn.Module):
                     codes = t.contiguous()
                 else:
                     out = t.contiguous()
+        if capture is not None:
+            capture["final"] = out
         y = out.permute(0, 3, 1, 2)
         return m.classifier(torch.flatten(m.avgpool(y), 1))
 

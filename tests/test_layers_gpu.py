@@ -555,6 +555,30 @@ def test_fused_vgg_pools_on_codes():
     assert torch.equal(pc.float() * 0.0371, pv)
 
 
+def test_fused_vgg16_bit_exact_against_cpu_emulation():
+    """BASELINE configs[2]: from the codes reaching the first wrapped conv to the map the average pool reads, FusedVGG
+    (12 tcgen05 convs with bias / BN / ReLU / next encode in the epilogue, 4 max-pools on fp16 codes in the library's
+    kernel, the last pool on the fp32 map) must EQUAL the CPU emulation of the chain bit for bit."""
+    import torchvision
+    from oracle import fused_emul
+    from term_quantization_b200 import cnn_models, fused, inference
+    torch.manual_seed(0)
+    base = torchvision.models.vgg16_bn(weights=None).cuda().eval()
+    _randomise_bn(base, seed=9)
+    q = cnn_models.convert_model(base, cnn_models.static_conv_layer_settings(base, 9, 8, 12), 9, 3)
+    x = torch.randn(2, 3, 64, 96, device="cuda", generator=torch.Generator(device="cuda").manual_seed(14))
+    inference.calibrate(q, [x])
+    f = fused.FusedVGG(q.to(memory_format=torch.channels_last))
+    cap = {}
+    with torch.no_grad():
+        f(x, capture=cap)
+    stages = f.chain_description()
+    assert sum(s[0] == "conv" for s in stages) == 12 and sum(s[0] == "pool" for s in stages) == 5
+    want = fused_emul.run_vgg_chain(stages, cap["stem_codes"].cpu().numpy().astype(np.int32))
+    got = cap["final"].cpu().numpy()
+    assert got.shape == want.shape and np.array_equal(got, want), float(np.abs(got - want).max())
+
+
 def test_linear_and_lstm_input_projection_on_tensor_cores():
     """BASELINE configs[0] / [4]: the Linear layers of the MLP and the LSTM's layer-0 input projection
     W_ih . q(emb) (T x B = 2,800 tokens, K = 650 zero-padded to 656, 4H = 2,600; evaluate_lstm.py:17-37,
